@@ -1,0 +1,162 @@
+/*
+ * cdq.h -- C ABI of the B200-native batched leaf evaluator (libcdq.so).
+ *
+ * The reference (thistleknot/chess-deep-q) has no FFI layer: its boundary for this path is a
+ * Python call surface.  Each entry point below names the reference call it replaces
+ * (file:line relative to the reference checkout).  Python binds these with ctypes
+ * (see INTEGRATION.md); nothing here mentions torch.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = CDQ_E_* below;
+ *   - no global mutable state except lazily-initialised read-only device tables, so calls are
+ *     re-entrant (the reference is called from a thread pool, mcts.py:77);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef CDQ_H
+#define CDQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDQ_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes (negative; positive values are cudaError_t) ---- */
+#define CDQ_E_BADARG (-1)   /* NULL pointer, negative count, misaligned buffer        */
+#define CDQ_E_NODEVICE (-2) /* no CUDA device / wrong architecture (needs sm_100)      */
+#define CDQ_E_WORKSPACE (-3)/* workspace smaller than cdq_workspace_bytes(n)           */
+#define CDQ_E_BADBOARD (-4) /* a record has >1 king per colour or overlapping boards   */
+
+/* ---- PackedBoard: the wire format (72 bytes, little endian) -------------------------
+ * Everything evaluation.py / board_to_tensor / ChessQNetwork read from a python-chess
+ * Board, as the Board's own public integer attributes:
+ *   bb[0..5] = board.pawns, .knights, .bishops, .rooks, .queens, .kings
+ *   bb[6]    = board.occupied_co[chess.WHITE]     bb[7] = board.occupied_co[chess.BLACK]
+ * bit i of a bitboard = square i, a1 = 0 ... h8 = 63 (python-chess numbering, so plane
+ * `ch` of board_to_tensor (board_utils.py:33-38) is bit-for-bit bb[type] & bb[6 + colour]).
+ * meta:
+ *   bit  0       turn, 1 = white to move (chess.WHITE == True)
+ *   bits 1..4    clean castling rights: 1 = white h1 (K), 2 = white a1 (Q),
+ *                                        3 = black h8 (k), 4 = black a8 (q)
+ *   bits 8..14   raw board.ep_square + 1 (0 = None)
+ *   bit  16      rep3: host-computed board.is_repetition(3) (history dependent;
+ *                evaluation.py:55, mcts.py:209).  0 for history-less boards.
+ *   other bits   reserved, must be 0
+ */
+typedef struct CdqBoard {
+    uint64_t bb[8];
+    uint64_t meta;
+} CdqBoard;
+
+#define CDQ_META_TURN_WHITE 0x1ull
+#define CDQ_META_CASTLE_WK 0x2ull
+#define CDQ_META_CASTLE_WQ 0x4ull
+#define CDQ_META_CASTLE_BK 0x8ull
+#define CDQ_META_CASTLE_BQ 0x10ull
+#define CDQ_META_EP_SHIFT 8
+#define CDQ_META_EP_MASK 0x7full
+#define CDQ_META_REP3 0x10000ull
+
+/* ---- integer evaluation terms: int32 [n][CDQ_NTERMS], the unit of the bit-exact check ----
+ * Row/col names follow evaluation.py:66-209. */
+enum {
+    CDQ_T_W_MAT = 0,   CDQ_T_B_MAT = 1,     /* material sums, evaluation.py:67-70           */
+    CDQ_T_W_MOB = 2,   CDQ_T_B_MOB = 3,     /* legal-move counts, turn forced, :78-84       */
+    CDQ_T_W_ATT = 4,   CDQ_T_B_ATT = 5,     /* |attacked squares|, :90-94                   */
+    CDQ_T_W_KATT = 6,  CDQ_T_B_KATT = 7,    /* "king attackers" (enemy piece count), :106-120 */
+    CDQ_T_W_CASTLED = 8, CDQ_T_B_CASTLED = 9,   /* king on g1/c1, g8/c8, :126-127            */
+    CDQ_T_W_KCENTRE = 10, CDQ_T_B_KCENTRE = 11, /* king on d4/e4/d5/e5, :128-129             */
+    CDQ_T_W_DBL = 12,  CDQ_T_B_DBL = 13,    /* doubled pawns, :149-150                      */
+    CDQ_T_W_ISO = 14,  CDQ_T_B_ISO = 15,    /* isolated pawns, :156-176                     */
+    CDQ_T_W_CENTRE = 16, CDQ_T_B_CENTRE = 17,   /* attacked centre squares, :185-186         */
+    CDQ_T_W_EXT = 18,  CDQ_T_B_EXT = 19,    /* attacked extended centre, :187-188           */
+    CDQ_T_W_DEF = 20,  CDQ_T_B_DEF = 21,    /* defended own pieces, :196-202                */
+    CDQ_T_CHECK = 22,                       /* +1 black to move in check, -1 white, :207-209 */
+    CDQ_T_TERMINAL = 23,                    /* CDQ_TERM_* below, :50-57 / mcts.py:202-210   */
+    CDQ_NTERMS = 24
+};
+enum { CDQ_TERM_NONE = 0, CDQ_TERM_CHECKMATE = 1, CDQ_TERM_STALEMATE = 2,
+       CDQ_TERM_INSUFFICIENT = 3, CDQ_TERM_REP3 = 4 };
+
+/* flags word per position */
+#define CDQ_F_TERM_MASK 0x7u        /* CDQ_TERM_* (first true of checkmate, stalemate, insufficient, rep3) */
+#define CDQ_F_CHECK 0x8u            /* side to move is in check                                          */
+#define CDQ_F_CHECKMATE 0x10u
+#define CDQ_F_STALEMATE 0x20u
+#define CDQ_F_INSUFFICIENT 0x40u
+#define CDQ_F_REP3 0x80u
+#define CDQ_F_STM_MOVES_SHIFT 8     /* bits 8..15: legal moves of the side to move (saturates at 255)     */
+#define CDQ_F_BADBOARD 0x80000000u  /* record violates the format (see CDQ_E_BADBOARD)                    */
+
+/* ---- ChessQNetwork parameters (neural_network.py:16-27), fp32, PyTorch layouts ---- */
+typedef struct CdqWeights {
+    const float* conv1_w; /* [32,12,3,3] */
+    const float* conv1_b; /* [32]        */
+    const float* conv2_w; /* [64,32,3,3] */
+    const float* conv2_b; /* [64]        */
+    const float* fc1_w;   /* [256,4096]  column index = c*64 + row*8 + col (neural_network.py:33) */
+    const float* fc1_b;   /* [256]       */
+    const float* fc2_w;   /* [1,256]     */
+    const float* fc2_b;   /* [1]         */
+} CdqWeights;
+#define CDQ_NPARAMS 1071073
+
+/* Opaque handle: weights repacked for the tensor-core kernels (fp16, UMMA tile order).
+ * Rebuild after every optimizer step / load_state_dict. */
+typedef struct CdqNet CdqNet;
+
+int cdq_version(void);
+const char* cdq_error_string(int code);
+
+/* Replaces evaluation.fast_evaluate_position (evaluation.py:30-229) for a batch.
+ * Any of d_terms / d_score / d_flags may be NULL.  ignore_checkmate as evaluation.py:30. */
+int cdq_eval_terms(const CdqBoard* d_boards, int64_t n, int ignore_checkmate,
+                   int32_t* d_terms /*[n][24]*/, double* d_score /*[n]*/,
+                   uint32_t* d_flags /*[n]*/, void* stream);
+
+/* Replaces board_utils.board_to_tensor (board_utils.py:12-40) /
+ * archive boards_to_tensor_batch (archive/board_utils.py:2-10): fp32 planes [n,12,8,8]. */
+int cdq_encode_planes(const CdqBoard* d_boards, int64_t n, float* d_planes, void* stream);
+
+/* Network handle: repack fp32 PyTorch-layout parameters (device pointers) for the kernels. */
+int cdq_net_create(CdqNet** out);
+int cdq_net_load(CdqNet* net, const CdqWeights* d_weights, void* stream);
+void cdq_net_destroy(CdqNet* net);
+
+/* Workspace (device bytes) needed by cdq_value_fwd / cdq_leaf_eval for n positions. */
+size_t cdq_workspace_bytes(int64_t n);
+
+/* Replaces ChessQNetwork.forward(board_to_tensor(b)) (neural_network.py:29-37, mcts.py:216-219)
+ * for a batch of packed boards: d_value[i] = tanh(fc2(...)), fp32. */
+int cdq_value_fwd(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float* d_value,
+                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces ParallelRussianDollMCTS._evaluate_position (mcts.py:196-232) plus the handcrafted
+ * score for a batch: d_leaf[i] = -1/+1 checkmate, 0 draw, else clamp(net value, -1, 1);
+ * d_score / d_flags as cdq_eval_terms.  d_value_raw (optional) = unclamped network output. */
+int cdq_leaf_eval(const CdqNet* net, const CdqBoard* d_boards, int64_t n,
+                  float* d_leaf, double* d_score, uint32_t* d_flags, float* d_value_raw,
+                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience used by the Python drop-ins and bench `e2e`: copies h_boards to the
+ * device (pinned or pageable), runs cdq_leaf_eval, copies results back, synchronises. */
+int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
+                       float* h_leaf, double* h_score, uint32_t* h_flags);
+
+/* Synthetic workload: n random playouts from the start position on the device.
+ * Position i plays plies_i = U{0..max_plies} uniformly random legal moves (counter-based RNG
+ * keyed by (seed, i, ply)); stops early at no-legal-move / insufficient material. */
+int cdq_random_playouts(CdqBoard* d_boards, int64_t n, uint64_t seed, int max_plies, void* stream);
+
+/* Kernel launch counter (all cdq_* kernels launched by this process), for bench gpu_launches. */
+uint64_t cdq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDQ_H */

@@ -1,0 +1,172 @@
+"""CPU ORACLE bindings -- test infrastructure, NOT product code.
+
+ctypes wrapper around oracle/_build/libcdq_oracle.so (cdq_oracle.c) plus a numpy/torch-CPU
+fp32 restatement of the reference network (neural_network.py:16-37) and DQN step
+(neural_network.py:218-252).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcdq_oracle.so")
+
+# numpy view of include/cdq.h::CdqBoard (72 bytes)
+BOARD_DTYPE = np.dtype([("bb", "<u8", (8,)), ("meta", "<u8")])
+assert BOARD_DTYPE.itemsize == 72
+NTERMS = 24
+
+TERM_NAMES = [
+    "w_mat", "b_mat", "w_mob", "b_mob", "w_att", "b_att", "w_katt", "b_katt",
+    "w_castled", "b_castled", "w_kcentre", "b_kcentre", "w_dbl", "b_dbl", "w_iso", "b_iso",
+    "w_centre", "b_centre", "w_ext", "b_ext", "w_def", "b_def", "check", "terminal",
+]
+
+
+def build(force=False):
+    """Compile the C oracle (gcc, seconds)."""
+    src = os.path.join(_HERE, "cdq_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        vp, i64, i32, u64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64
+        L.cdq_oracle_startpos.argtypes = [vp]
+        L.cdq_oracle_from_fen.argtypes = [ctypes.c_char_p, vp]
+        L.cdq_oracle_from_fen.restype = i32
+        L.cdq_oracle_perft.argtypes = [vp, i32]
+        L.cdq_oracle_perft.restype = u64
+        L.cdq_oracle_legal_moves.argtypes = [vp, i32, vp]
+        L.cdq_oracle_legal_moves.restype = i32
+        L.cdq_oracle_push.argtypes = [vp, ctypes.c_uint16]
+        L.cdq_oracle_eval.argtypes = [vp, i64, i32, vp, vp, vp, i32]
+        L.cdq_oracle_encode_planes.argtypes = [vp, i64, vp]
+        L.cdq_oracle_playouts.argtypes = [u64, i64, i32, vp]
+        L.cdq_oracle_init()
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def startpos():
+    b = np.zeros(1, BOARD_DTYPE)
+    lib().cdq_oracle_startpos(_ptr(b))
+    return b
+
+
+def from_fen(fen):
+    b = np.zeros(1, BOARD_DTYPE)
+    if lib().cdq_oracle_from_fen(fen.encode(), _ptr(b)) != 0:
+        raise ValueError("bad FEN: %r" % fen)
+    return b
+
+
+def from_fens(fens):
+    return np.concatenate([from_fen(f) for f in fens]) if len(fens) else np.zeros(0, BOARD_DTYPE)
+
+
+def perft(board, depth):
+    return int(lib().cdq_oracle_perft(_ptr(np.ascontiguousarray(board)), depth))
+
+
+def legal_moves(board, force_turn=-1):
+    mv = np.zeros(512, np.uint16)
+    n = lib().cdq_oracle_legal_moves(_ptr(np.ascontiguousarray(board)), force_turn, _ptr(mv))
+    return mv[:n].copy()
+
+
+def push(board, move):
+    b = np.ascontiguousarray(board).copy()
+    lib().cdq_oracle_push(_ptr(b), int(move))
+    return b
+
+
+def playouts(n, seed=42, max_plies=199):
+    """Synthetic random-playout positions (SURVEY.md 8d recipe)."""
+    out = np.zeros(n, BOARD_DTYPE)
+    lib().cdq_oracle_playouts(seed, n, max_plies, _ptr(out))
+    return out
+
+
+def evaluate(boards, ignore_checkmate=False, nthreads=1):
+    """-> (terms int32 [n,24], score f64 [n], flags u32 [n]) per evaluation.py:30-229."""
+    boards = np.ascontiguousarray(boards)
+    n = len(boards)
+    terms = np.zeros((n, NTERMS), np.int32)
+    score = np.zeros(n, np.float64)
+    flags = np.zeros(n, np.uint32)
+    lib().cdq_oracle_eval(_ptr(boards), n, int(bool(ignore_checkmate)), _ptr(terms), _ptr(score),
+                          _ptr(flags), nthreads)
+    return terms, score, flags
+
+
+def encode_planes(boards):
+    """board_to_tensor for a batch (board_utils.py:12-40): float32 [n,12,8,8]."""
+    boards = np.ascontiguousarray(boards)
+    out = np.zeros((len(boards), 12, 8, 8), np.float32)
+    lib().cdq_oracle_encode_planes(_ptr(boards), len(boards), _ptr(out))
+    return out
+
+
+def leaf_value(flags, net_value):
+    """mcts.py:196-232: terminal short-circuits, else clamp(net, -1, 1).  `flags` as cdq.h."""
+    flags = np.asarray(flags)
+    v = np.clip(np.asarray(net_value, np.float32), -1.0, 1.0)
+    # checkmate: -1 if white to move else +1.  Turn is not in flags; callers pass it via boards.
+    return v
+
+
+# ------------------------------------------------------------------ network oracle (fp32, CPU)
+PARAM_SHAPES = [
+    ("conv1.weight", (32, 12, 3, 3)), ("conv1.bias", (32,)),
+    ("conv2.weight", (64, 32, 3, 3)), ("conv2.bias", (64,)),
+    ("fc1.weight", (256, 4096)), ("fc1.bias", (256,)),
+    ("fc2.weight", (1, 256)), ("fc2.bias", (1,)),
+]
+
+
+def init_params(seed=42, scale=1.0):
+    """Parameters distributed like torch's default Conv2d/Linear init (kaiming_uniform a=sqrt(5)
+    => U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias), from a numpy RNG so the same
+    values exist on any box.  `scale` multiplies the weight matrices ("trained-like" ranges)."""
+    rng = np.random.default_rng(seed)
+    p = {}
+    for name, shape in PARAM_SHAPES:
+        layer = name.split(".")[0]
+        fan_in = {"conv1": 12 * 9, "conv2": 32 * 9, "fc1": 4096, "fc2": 256}[layer]
+        bound = 1.0 / np.sqrt(fan_in)
+        a = rng.uniform(-bound, bound, size=shape).astype(np.float32)
+        if name.endswith("weight"):
+            a = (a * scale).astype(np.float32)
+        p[name] = a
+    return p
+
+
+def net_forward(params, planes, return_acts=False):
+    """ChessQNetwork.forward (neural_network.py:29-37) in fp32 on torch-CPU."""
+    import torch
+    import torch.nn.functional as F
+    x = torch.as_tensor(planes, dtype=torch.float32)
+    t = {k: torch.as_tensor(v) for k, v in params.items()}
+    a1 = F.relu(F.conv2d(x, t["conv1.weight"], t["conv1.bias"], padding=1))
+    a2 = F.relu(F.conv2d(a1, t["conv2.weight"], t["conv2.bias"], padding=1))
+    h = F.relu(F.linear(a2.reshape(-1, 4096), t["fc1.weight"], t["fc1.bias"]))
+    out = torch.tanh(F.linear(h, t["fc2.weight"], t["fc2.bias"]))
+    if return_acts:
+        return out.numpy(), a1.numpy(), a2.numpy(), h.numpy()
+    return out.numpy()

@@ -1,0 +1,103 @@
+"""CPU suite: pins the oracle (oracle/cdq_oracle.c, oracle/oracle.py) against
+  * perft known answers (public chessprogramming constants), and
+  * the golden vectors produced by the reference's own evaluation.py / board_utils.py /
+    neural_network.py (tests/golden/make_golden.py).
+"""
+import numpy as np
+import pytest
+
+PERFT = [
+    ("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1", [20, 400, 8902, 197281, 4865609]),
+    ("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -", [48, 2039, 97862, 4085603]),
+    ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -", [14, 191, 2812, 43238, 674624]),
+    ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq -", [6, 264, 9467, 422333]),
+    ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8", [44, 1486, 62379, 2103487]),
+    ("r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10", [46, 2079, 89890, 3894594]),
+]
+
+
+@pytest.mark.parametrize("fen,expected", PERFT)
+def test_perft_known_answers(oracle, fen, expected):
+    b = oracle.from_fen(fen)
+    assert [oracle.perft(b, d + 1) for d in range(len(expected))] == expected
+
+
+# provisional vectors of SURVEY.md 8c (fen, score)
+SURVEY_SCORES = [
+    ("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1", 0.0),
+    ("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq -", 0.09999999999999998),
+    ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - -", -0.21500000000000002),
+    ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8", 0.26),
+    ("4k3/8/8/8/8/8/4R3/4K3 b", 56.51),
+    ("4k3/3P4/8/8/8/8/8/4K3 b", 51.69),
+    ("7k/8/8/8/8/8/8/K6r w", -55.655),
+    ("7k/8/8/8/8/8/8/1K5r w", -56.05),
+    ("rnb1kbnr/pppp1ppp/8/4p3/6Pq/5P2/PPPPP2P/RNBQKBNR w KQkq -", -50.0),
+    ("7k/5Q2/6K1/8/8/8/8/8 b", 0.0),
+    ("8/8/4k3/8/8/3K4/8/8 w", 0.0),
+    ("rnbqkbnr/ppp1pppp/8/8/3pP3/8/PPPP1PPP/RNBQKBNR b KQkq e3", -0.25),
+]
+
+
+@pytest.mark.parametrize("fen,expected", SURVEY_SCORES)
+def test_survey_scores(oracle, fen, expected):
+    _, s, _ = oracle.evaluate(oracle.from_fen(fen))
+    assert s[0] == expected
+
+
+def test_survey_quirks(oracle):
+    T = oracle.TERM_NAMES.index
+    t, _, _ = oracle.evaluate(oracle.from_fen("4k3/8/8/8/8/8/4R3/4K3 b"))
+    assert t[0, T("w_mob")] == 17 and t[0, T("b_katt")] == 2      # king-capture counted
+    t, _, _ = oracle.evaluate(oracle.from_fen("4k3/3P4/8/8/8/8/8/4K3 b"))
+    assert t[0, T("w_mob")] == 13                                  # x4 promotions onto the king
+    t, _, _ = oracle.evaluate(oracle.from_fen("7k/8/8/8/8/8/8/K6r w"))
+    assert t[0, T("w_katt")] == 0                                  # a1 king is falsy
+    t, _, _ = oracle.evaluate(oracle.from_fen("7k/8/8/8/8/8/8/1K5r w"))
+    assert t[0, T("w_katt")] == 2
+    t, _, _ = oracle.evaluate(oracle.from_fen("rnbqkbnr/ppp1pppp/8/8/3pP3/8/PPPP1PPP/RNBQKBNR b KQkq e3"))
+    assert (t[0, T("w_mob")], t[0, T("b_mob")]) == (29, 30)
+
+
+def test_eval_matches_reference_golden(oracle, eval_golden):
+    g = eval_golden
+    boards = g["boards"]
+    terms, score, flags = oracle.evaluate(boards)
+    _, score_ic, _ = oracle.evaluate(boards, ignore_checkmate=True)
+    assert np.array_equal(score, g["score"])                    # fp64 bit-exact
+    assert np.array_equal(score_ic, g["score_ignore_checkmate"])
+    assert np.array_equal(terms[:, 23], g["terminal"])
+    assert np.array_equal(flags & 7, g["terminal"].astype(np.uint32))
+    has = g["has_terms"]
+    assert has.sum() > 1000
+    assert np.array_equal(terms[has][:, :23], g["terms"][has][:, :23])
+    # both colours' multi-threaded evaluation agree with the single-thread run
+    t2, s2, f2 = oracle.evaluate(boards, nthreads=4)
+    assert np.array_equal(t2, terms) and np.array_equal(s2, score) and np.array_equal(f2, flags)
+
+
+def test_planes_match_board_to_tensor(oracle, eval_golden):
+    g = eval_golden
+    planes = oracle.encode_planes(g["boards"])
+    bits = (planes.reshape(len(planes), 12, 64) > 0.5).astype(np.uint64)
+    packed = (bits << np.arange(64, dtype=np.uint64)).sum(2, dtype=np.uint64)
+    assert np.array_equal(packed, g["planes_packed"])
+    assert set(np.unique(planes)) <= {0.0, 1.0}
+
+
+def test_playouts_are_deterministic_and_match_fixture(oracle, eval_golden):
+    n_special = int(eval_golden["n_special"])
+    again = oracle.playouts(1024, seed=42, max_plies=199)
+    assert np.array_equal(again, eval_golden["boards"][n_special:])
+
+
+def test_net_oracle_matches_reference_class(oracle, eval_golden, net_golden):
+    planes = oracle.encode_planes(net_golden["boards"])
+    for tag, scale in (("s1", 1.0), ("s2", 2.0), ("s3", 3.0)):
+        v = oracle.net_forward(oracle.init_params(42, scale), planes).reshape(-1)
+        assert np.abs(v - net_golden["value_" + tag]).max() < 2e-6
+
+
+def test_empty_batch(oracle):
+    t, s, f = oracle.evaluate(np.zeros(0, oracle.BOARD_DTYPE))
+    assert t.shape == (0, 24) and s.shape == (0,) and f.shape == (0,)
