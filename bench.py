@@ -1,0 +1,261 @@
+"""bench.py -- headline benchmark: batched leaf evaluation (handcrafted score + CNN value).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--positions P] [--impl reference]
+
+Metric (BASELINE.json): leaf positions/sec.  One "step" = one pass of the hot path
+(cdq_leaf_eval: K1 bitboard eval -> K2a conv stack -> K2b fc head) over one batch of synthetic
+random-playout positions.  N=1 workload = BASELINE configs[1]: 1 048 576 positions on one B200.
+Under torchrun every rank evaluates its own 1M positions (weak scaling, no data-path collective).
+
+  value       whole-job positions/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e         same metric through LeafEvaluator.evaluate_host: pinned HOST buffers in, host out
+  roofline    dominant kernel: algorithmic FLOP per launch / mean launch time (CUDA events on the
+              launching stream, recorded inside the timed region) vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (C eval on all cores + torch-CPU fp32 CNN) on a bounded sample
+--impl reference times that CPU port as the reference arm (the reference itself is Python over
+python-chess, which is not installable here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "leaf positions/sec (handcrafted eval + CNN value)"
+UNIT = "positions/s"
+FLOP_CONV = 2 * (221184 + 1179648)      # conv1 + conv2, dense convention
+FLOP_FC = 2 * (1048576 + 256)
+H2D_PER_POS, D2H_PER_POS = 72, 16       # record in; leaf f32 + score f64 + flags u32 out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops": p.get("bf16_tflops_sustained", 1368.3), "hbm": p.get("hbm_gbs", 6490.5), "src": "measured"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_throughput(n_sample, steps=1):
+    """The reference path's CPU port: oracle C evaluation (all host threads) + fp32 torch-CPU CNN."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    boards = O.playouts(n_sample, seed=42)
+    params = O.init_params(42, 2.0)
+    planes = None
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.evaluate(boards, nthreads=0)
+        planes = O.encode_planes(boards)
+        with torch.no_grad():
+            for i in range(0, n_sample, 4096):
+                O.net_forward(params, planes[i:i + 4096])
+        times.append(time.perf_counter() - t0)
+    return n_sample / (sum(times) / len(times)), sum(times) / len(times), os.cpu_count(), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = args.ref_sample
+    for _ in range(args.warmup):
+        cpu_port_throughput(min(n_sample, 8192))
+    v, sec, cores, tthreads = cpu_port_throughput(n_sample, steps=args.steps)
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 score / fp32 CNN", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "CPU port of the reference path on %d random-playout positions per step" % n_sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d positions/step: C oracle eval on %d threads + torch-CPU fp32 CNN (%d threads)"
+                                       % (n_sample, cores, tthreads)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--positions", type=int, default=1 << 20, help="positions per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=131072)
+    ap.add_argument("--cpu-sample", type=int, default=131072)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import chess_deep_q_b200 as cdq
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = cdq._lib.lib()
+    n = args.positions
+    W = max(args.warmup, 3)
+
+    # ---- synthetic inputs, generated on the device by the product's own move generator
+    boards = torch.empty((n, 9), dtype=torch.int64, device="cuda")
+    cdq._lib.check(L.cdq_random_playouts(boards.data_ptr(), n, 42 + rank, 199, cdq._lib.stream_ptr()))
+    # weights: same distribution as torch's default init, numpy RNG (portable), x2 "trained-like" range
+    rng = np.random.default_rng(42)
+    net = cdq.ChessQNetwork()
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            fan_in = {"conv1": 108, "conv2": 288, "fc1": 4096, "fc2": 256}[name.split(".")[0]]
+            a = rng.uniform(-1, 1, size=tuple(p.shape)).astype(np.float32) / np.sqrt(fan_in)
+            p.copy_(torch.from_numpy(a * (2.0 if name.endswith("weight") else 1.0)))
+    net = net.cuda()
+    ev = cdq.LeafEvaluator(net)
+
+    def step():
+        return ev.evaluate_device(boards)
+
+    for _ in range(W):
+        out = step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+
+    # ---- timed region: K steps, device-timed, per-kernel events recorded inside it
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.cdq_profile_enable(1)
+    launches0 = L.cdq_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.cdq_launch_count() - launches0
+    L.cdq_profile_enable(0)
+    kms = (cdq._lib.ctypes.c_double * 8)()
+    kcnt = (cdq._lib.ctypes.c_uint64 * 8)()
+    cdq._lib.check(L.cdq_profile_collect(kms, kcnt))
+    clocks = sampler.stop()
+    if dist:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host buffers through the public host API, copies inside the timed region
+    h_boards = torch.empty((n, 9), dtype=torch.int64).pin_memory()
+    h_boards.copy_(boards)
+    h_out = {"leaf": torch.empty(n, dtype=torch.float32).pin_memory(),
+             "score": torch.empty(n, dtype=torch.float64).pin_memory(),
+             "flags": torch.empty(n, dtype=torch.int32).pin_memory()}
+    for _ in range(2):
+        ev.evaluate_host(h_boards, h_out)
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        ev.evaluate_host(h_boards, h_out)       # synchronises before returning
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * n * e2e_steps / e2e_s
+    assert torch.equal(h_out["leaf"].cuda(), out["leaf"]), "host path and device path disagree"
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tensor bound)
+    peaks = measured_peaks()
+    kinds = {0: ("eval_terms_kernel", None), 1: ("conv_stack_kernel", FLOP_CONV), 2: ("fc_head_kernel", FLOP_FC)}
+    dom = max((1, 2), key=lambda k: kms[k])
+    per_launch_pos = n * args.steps / max(1, kcnt[dom])
+    avg_ms = kms[dom] / max(1, kcnt[dom])
+    achieved = per_launch_pos * kinds[dom][1] / (avg_ms * 1e-3) / 1e12
+    roofline = {"kernel": kinds[dom][0], "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                "peak_source": peaks["src"] + " bf16_tflops_sustained (kind::f16 shares the bf16 rate)",
+                "kernel_ms_per_step": {kinds[k][0]: kms[k] / args.steps for k in kinds},
+                "eval_kernel_hbm": {"achieved_GBps": n * args.steps * 84 / (kms[0] * 1e-3) / 1e9 if kms[0] else None,
+                                    "peak_GBps": peaks["hbm"], "note": "84 B/position; integer-issue bound"}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, sec, cores, tthreads = cpu_port_throughput(args.cpu_sample)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d positions: C oracle eval on %d threads + torch-CPU fp32 CNN (%d threads), %.1f s"
+                         % (args.cpu_sample, cores, tthreads, sec)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bitboards + f64 score; fp16 operands / fp32 accumulate CNN", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: %d random-playout positions per GPU per step, "
+                                   "handcrafted eval + 12-channel CNN value" % n,
+                       "positions_per_gpu": n, "l2": "per-step working set (act2 %.1f GB) >> 126 MB L2" % (n * 8192 / 1e9),
+                       "weights": "numpy seed 42, torch-default init ranges, weight matrices x2"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * H2D_PER_POS, "d2h_bytes_per_step": n * D2H_PER_POS},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

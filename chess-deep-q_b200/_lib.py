@@ -1,0 +1,76 @@
+"""ctypes binding of libcdq.so (include/cdq.h).  Fails loudly when the library is missing or a
+call returns an error; nothing here falls back to the CPU."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcdq.so")
+
+c_void_p, c_int64, c_int, c_uint64, c_size_t = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                                 ctypes.c_uint64, ctypes.c_size_t)
+
+# name -> (restype, argtypes); must list every symbol include/cdq.h declares
+SIGNATURES = {
+    "cdq_version": (c_int, []),
+    "cdq_error_string": (ctypes.c_char_p, [c_int]),
+    "cdq_eval_terms": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cdq_encode_planes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "cdq_net_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "cdq_net_load": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cdq_net_destroy": (None, [c_void_p]),
+    "cdq_workspace_bytes": (c_size_t, [c_int64]),
+    "cdq_value_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdq_leaf_eval": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_size_t, c_void_p]),
+    "cdq_leaf_eval_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cdq_random_playouts": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
+    "cdq_expand": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "cdq_launch_count": (c_uint64, []),
+    "cdq_profile_enable": (None, [c_int]),
+    "cdq_profile_collect": (c_int, [c_void_p, c_void_p]),
+    "cdq_debug_conv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class CdqWeights(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class CdqError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libcdq.so (built by chess-deep-q_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise CdqError("libcdq.so is not built: run `python chess-deep-q_b200/build.py` "
+                           "(there is no CPU fallback)")
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise CdqError("libcdq error %d: %s" % (code, lib().cdq_error_string(code).decode()))
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CdqError("no CUDA device: chess-deep-q_b200 computes only on a B200 (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())

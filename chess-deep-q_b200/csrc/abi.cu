@@ -1,0 +1,260 @@
+// abi.cu -- the extern "C" boundary of libcdq.so (include/cdq.h).  Thin: argument checks, chunking,
+// stream plumbing.  All compute is in the kernels; there is no CPU path.
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+#include "cnn.cuh"
+
+namespace cdq {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+
+// ---- profiling: event pairs around kernel launches, summed per kernel kind on collect
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+ProfileScope::ProfileScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_) {
+    if (!g_profile.load(std::memory_order_relaxed)) return;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+}
+ProfileScope::~ProfileScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    g_prof.push_back({kind, a, b});
+}
+
+constexpr long long FWD_CHUNK = 128 * 1024; // positions per conv->fc pass (act2 = 1 GiB)
+static inline long long tiles_of(long long n) { return (n + 127) / 128; }
+
+static int check_device() {
+    static int state = 0; // 0 unknown, 1 ok, <0 error
+    if (state == 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); state = CDQ_E_NODEVICE; return state; }
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        state = (major == 10) ? 1 : CDQ_E_NODEVICE;
+    }
+    return state == 1 ? 0 : state;
+}
+} // namespace cdq
+
+using namespace cdq;
+
+extern "C" {
+
+int cdq_version(void) { return CDQ_VERSION; }
+
+const char* cdq_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case CDQ_E_BADARG: return "cdq: bad argument";
+        case CDQ_E_NODEVICE: return "cdq: no sm_100 CUDA device (this library has no CPU fallback)";
+        case CDQ_E_WORKSPACE: return "cdq: workspace too small (see cdq_workspace_bytes)";
+        case CDQ_E_BADBOARD: return "cdq: malformed board record";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "cdq: unknown error";
+    }
+}
+
+uint64_t cdq_launch_count(void) { return g_launches.load(); }
+
+void cdq_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+
+// Waits for all recorded launches, adds their device time (ms) and count per kernel kind
+// (0 eval, 1 conv stack, 2 fc head, 3 encode planes, 4 playouts/expand, 5 weight pack, 6 train)
+// into ms[8] / launches[8], then clears the records.
+int cdq_profile_collect(double* ms, uint64_t* launches) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e != cudaSuccess) return (int)e;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        if (ms) ms[r.kind] += t;
+        if (launches) launches[r.kind] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return 0;
+}
+
+int cdq_eval_terms(const CdqBoard* d_boards, int64_t n, int ignore_checkmate, int32_t* d_terms, double* d_score,
+                   uint32_t* d_flags, void* stream) {
+    if (n < 0 || (n > 0 && !d_boards)) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_eval_terms(d_boards, n, ignore_checkmate, d_terms, d_score, d_flags, (cudaStream_t)stream);
+}
+
+int cdq_encode_planes(const CdqBoard* d_boards, int64_t n, float* d_planes, void* stream) {
+    if (n < 0 || (n > 0 && (!d_boards || !d_planes))) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_encode_planes(d_boards, n, d_planes, (cudaStream_t)stream);
+}
+
+int cdq_random_playouts(CdqBoard* d_boards, int64_t n, uint64_t seed, int max_plies, void* stream) {
+    if (n < 0 || max_plies < 0 || (n > 0 && !d_boards)) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_random_playouts(d_boards, n, seed, max_plies, (cudaStream_t)stream);
+}
+
+int cdq_expand(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* d_children, int32_t* d_counts,
+               void* stream) {
+    if (n < 0 || max_children < 0 || (n > 0 && (!d_boards || !d_children || !d_counts))) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_expand(d_boards, n, max_children, d_children, d_counts, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ network handle
+static const size_t W1P_HALFS = 9 * 32 * 16, W2P_HALFS = 9 * 64 * 32, FC1P_HALFS = 64ull * 256 * 64;
+
+int cdq_net_create(CdqNet** out) {
+    if (!out) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    CdqNet* net = new CdqNet();
+    const size_t halfs = W1P_HALFS + W2P_HALFS + FC1P_HALFS;
+    const size_t bytes = halfs * 2 + (64 + 256 + 256 + 4) * 4;
+    cudaError_t e = cudaMalloc(&net->blob, bytes);
+    if (e != cudaSuccess) { delete net; return (int)e; }
+    __half* h = (__half*)net->blob;
+    float* f = (float*)(h + halfs);
+    net->p.w1p = h;
+    net->p.w2p = h + W1P_HALFS;
+    net->p.fc1p = h + W1P_HALFS + W2P_HALFS;
+    net->p.conv2_b = f;
+    net->p.fc1_b = f + 64;
+    net->p.fc2_w = f + 64 + 256;
+    net->p.fc2_b = f + 64 + 512;
+    net->loaded = 0;
+    *out = net;
+    return 0;
+}
+
+int cdq_net_load(CdqNet* net, const CdqWeights* w, void* stream) {
+    if (!net || !w || !w->conv1_w || !w->conv1_b || !w->conv2_w || !w->conv2_b || !w->fc1_w || !w->fc1_b ||
+        !w->fc2_w || !w->fc2_b)
+        return CDQ_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = launch_pack_weights(*w, (__half*)net->p.w1p, (__half*)net->p.w2p, (__half*)net->p.fc1p, st)) return e;
+    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.conv2_b, w->conv2_b, 64 * 4, cudaMemcpyDeviceToDevice, st));
+    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc1_b, w->fc1_b, 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc2_w, w->fc2_w, 256 * 4, cudaMemcpyDeviceToDevice, st));
+    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc2_b, w->fc2_b, 4, cudaMemcpyDeviceToDevice, st));
+    net->loaded = 1;
+    return 0;
+}
+
+void cdq_net_destroy(CdqNet* net) {
+    if (!net) return;
+    cudaFree(net->blob);
+    delete net;
+}
+
+size_t cdq_workspace_bytes(int64_t n) {
+    if (n <= 0) return 0;
+    const long long c = n < FWD_CHUNK ? n : FWD_CHUNK;
+    return (size_t)tiles_of(c) << 20; // one 1 MiB fp16 act2 block per 128 positions
+}
+
+// conv -> fc over chunks of at most FWD_CHUNK positions
+static int forward_chunks(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float* d_value,
+                          const uint32_t* d_flags, float* d_leaf, void* ws, size_t ws_bytes, __half* dbg_act1,
+                          cudaStream_t st) {
+    if (!net || !net->loaded || n < 0 || (n > 0 && (!d_boards || !ws))) return CDQ_E_BADARG;
+    if (ws_bytes < cdq_workspace_bytes(n)) return CDQ_E_WORKSPACE;
+    if ((uintptr_t)ws & 15) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    for (int64_t off = 0; off < n; off += FWD_CHUNK) {
+        const int64_t c = (n - off) < FWD_CHUNK ? (n - off) : FWD_CHUNK;
+        if (int e = launch_conv_stack(d_boards + off, c, net->p, (__half*)ws, dbg_act1 ? dbg_act1 + off * 2048 : nullptr, st))
+            return e;
+        if (int e = launch_fc_head((const __half*)ws, c, net->p, d_value ? d_value + off : nullptr,
+                                   d_flags ? d_flags + off : nullptr, d_leaf ? d_leaf + off : nullptr, st))
+            return e;
+    }
+    return 0;
+}
+
+int cdq_value_fwd(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float* d_value, void* d_workspace,
+                  size_t workspace_bytes, void* stream) {
+    if (n > 0 && !d_value) return CDQ_E_BADARG;
+    return forward_chunks(net, d_boards, n, d_value, nullptr, nullptr, d_workspace, workspace_bytes, nullptr,
+                          (cudaStream_t)stream);
+}
+
+int cdq_leaf_eval(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float* d_leaf, double* d_score,
+                  uint32_t* d_flags, float* d_value_raw, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (n > 0 && (!d_leaf || !d_flags)) return CDQ_E_BADARG;
+    if (int e = cdq_eval_terms(d_boards, n, 0, nullptr, d_score, d_flags, stream)) return e;
+    return forward_chunks(net, d_boards, n, d_value_raw, d_flags, d_leaf, d_workspace, workspace_bytes, nullptr,
+                          (cudaStream_t)stream);
+}
+
+// debug/parity hook: also dumps ReLU(conv1) as fp16 [n][64 squares][32 channels] and act2 tiles
+int cdq_debug_conv(const CdqNet* net, const CdqBoard* d_boards, int64_t n, void* d_act1, void* d_act2_tiles,
+                   void* stream) {
+    if (!net || !net->loaded || n <= 0 || n > FWD_CHUNK || !d_boards || !d_act2_tiles) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_conv_stack(d_boards, n, net->p, (__half*)d_act2_tiles, (__half*)d_act1, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-buffer path (e2e)
+namespace {
+struct HostPath {
+    static constexpr long long CHUNK = 256 * 1024;
+    std::mutex mu;
+    bool ready = false;
+    cudaStream_t st[2];
+    CdqBoard* boards[2];
+    float* leaf[2];
+    double* score[2];
+    uint32_t* flags[2];
+    void* ws[2];
+    size_t ws_bytes = 0;
+    int init() {
+        if (ready) return 0;
+        ws_bytes = cdq_workspace_bytes(CHUNK);
+        for (int i = 0; i < 2; i++) {
+            CDQ_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            CDQ_CUDA(cudaMalloc(&boards[i], CHUNK * sizeof(CdqBoard)));
+            CDQ_CUDA(cudaMalloc(&leaf[i], CHUNK * 4));
+            CDQ_CUDA(cudaMalloc(&score[i], CHUNK * 8));
+            CDQ_CUDA(cudaMalloc(&flags[i], CHUNK * 4));
+            CDQ_CUDA(cudaMalloc(&ws[i], ws_bytes));
+        }
+        ready = true;
+        return 0;
+    }
+};
+HostPath g_host;
+} // namespace
+
+int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n, float* h_leaf, double* h_score,
+                       uint32_t* h_flags) {
+    if (!net || n < 0 || (n > 0 && (!h_boards || !h_leaf))) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    if (int e = g_host.init()) return e;
+    int c_idx = 0;
+    for (int64_t off = 0; off < n; off += HostPath::CHUNK, c_idx++) {
+        const int s = c_idx & 1;
+        const int64_t c = (n - off) < HostPath::CHUNK ? (n - off) : HostPath::CHUNK;
+        cudaStream_t st = g_host.st[s];
+        // the slot's previous use (two chunks ago) is ordered before this one by the stream itself
+        CDQ_CUDA(cudaMemcpyAsync(g_host.boards[s], h_boards + off, c * sizeof(CdqBoard), cudaMemcpyHostToDevice, st));
+        if (int e = cdq_leaf_eval(net, g_host.boards[s], c, g_host.leaf[s], g_host.score[s], g_host.flags[s], nullptr,
+                                  g_host.ws[s], g_host.ws_bytes, st))
+            return e;
+        CDQ_CUDA(cudaMemcpyAsync(h_leaf + off, g_host.leaf[s], c * 4, cudaMemcpyDeviceToHost, st));
+        if (h_score) CDQ_CUDA(cudaMemcpyAsync(h_score + off, g_host.score[s], c * 8, cudaMemcpyDeviceToHost, st));
+        if (h_flags) CDQ_CUDA(cudaMemcpyAsync(h_flags + off, g_host.flags[s], c * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CDQ_CUDA(cudaStreamSynchronize(g_host.st[0]));
+    CDQ_CUDA(cudaStreamSynchronize(g_host.st[1]));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,33 @@
+// cnn.cuh -- packed network handle shared by cnn_kernels.cu and abi.cu.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include "../../include/cdq.h"
+
+namespace cdq {
+
+// device pointers; passed to kernels by value
+struct PackedNet {
+    const __half* w1p;   // conv1: [9 taps][2 chunks][4 groups][8 n][8 k]  (k 12 = bias, centre tap)
+    const __half* w2p;   // conv2: [9 taps][4 chunks][8 groups][8 n][8 k]
+    const __half* fc1p;  // fc1:   [64 squares][8 chunks][32 groups][8 n][8 k]
+    const float* conv2_b;
+    const float* fc1_b;
+    const float* fc2_w;
+    const float* fc2_b;
+};
+
+int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, cudaStream_t st);
+int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
+                      cudaStream_t st);
+int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
+                   float* leaf, cudaStream_t st);
+
+} // namespace cdq
+
+// what the opaque C handle points to
+struct CdqNet {
+    cdq::PackedNet p;
+    void* blob;      // one device allocation holding everything above
+    int loaded;
+};

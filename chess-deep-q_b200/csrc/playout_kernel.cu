@@ -1,0 +1,217 @@
+// playout_kernel.cu -- synthetic workload generator: n random playouts from the
+// start position, one thread per game, entirely on the device.  It reuses the set-wise legal move
+// generator of bitboard.cuh with a visitor that SELECTS the r-th legal move instead of counting,
+// so the generator that makes the benchmark inputs is the same code K1's mobility term is built
+// from (and the tests check every generated position against the CPU oracle).
+//
+// Recipe per game i: plies = U{0..max_plies}; each ply picks a uniformly random legal move
+// (counter-based splitmix64 keyed by (seed, i, ply)); stops early when there is no legal move or
+// the material is insufficient.  Reference context: games cap at 200 plies (chess_ai.py:117) and
+// the reference seeds everything with 42 (main.py:19-21).
+#include "bitboard.cuh"
+#include "common.cuh"
+
+namespace cdq {
+
+__device__ __forceinline__ u64 mix64(u64 z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ int nth_bit(u64 b, int k) {
+    for (int i = 0; i < k; i++) b &= b - 1;
+    return lsb_sq(b);
+}
+
+enum { MV_NORMAL = 0, MV_CASTLE_K = 1, MV_CASTLE_Q = 2, MV_EP = 3, MV_DOUBLE = 4 };
+enum { PT_P = 0, PT_N = 1, PT_B = 2, PT_R = 3, PT_Q = 4, PT_K = 5 };
+
+struct SelectVisitor {
+    int r;           // index of the wanted move among the remaining classes
+    bool found = false;
+    int from = 0, to = 0, promo = -1, special = MV_NORMAL;
+    u64 occ;
+    bool white;
+
+    __device__ SelectVisitor(int r_, u64 occ_, bool w) : r(r_), occ(occ_), white(w) {}
+
+    __device__ __forceinline__ bool pick(u64 t, int mult, int& sq, int& sub) {
+        if (found) return false;
+        const int c = popc(t) * mult;
+        if (r >= c) { r -= c; return false; }
+        sq = nth_bit(t, r / mult);
+        sub = r % mult;
+        found = true;
+        return true;
+    }
+    template <int D> __device__ __forceinline__ void slide(u64 t) {
+        int sq, sub;
+        if (!pick(t, 1, sq, sub)) return;
+        to = sq;
+        const int delta = Dir<D>::left ? Dir<D>::s : -Dir<D>::s;
+        int f = sq - delta;
+        while (!((occ >> f) & 1)) f -= delta; // origin = first piece behind the target
+        from = f;
+    }
+    template <int J> __device__ __forceinline__ void knight(u64 t) {
+        int sq, sub;
+        if (!pick(t, 1, sq, sub)) return;
+        to = sq; from = sq - knight_delta(J);
+    }
+    u64 king_bb = 0;
+    __device__ __forceinline__ void king(u64 t) {
+        int sq, sub;
+        if (!pick(t, 1, sq, sub)) return;
+        to = sq; from = lsb_sq(king_bb);
+    }
+    __device__ __forceinline__ void pawn_to(u64 t, int delta, int sp) {
+        const u64 last = RANK_1 | RANK_8;
+        int sq, sub;
+        if (pick(t & ~last, 1, sq, sub)) { to = sq; from = sq - delta; special = sp; return; }
+        if (pick(t & last, 4, sq, sub)) { to = sq; from = sq - delta; promo = PT_Q - sub; }
+    }
+    __device__ __forceinline__ void pawn_push(u64 s, u64 d) {
+        pawn_to(s, white ? 8 : -8, MV_NORMAL);
+        pawn_to(d, white ? 16 : -16, MV_DOUBLE);
+    }
+    template <int D> __device__ __forceinline__ void pawn_cap(u64 t) {
+        pawn_to(t, Dir<D>::left ? Dir<D>::s : -Dir<D>::s, MV_NORMAL);
+    }
+    __device__ __forceinline__ void castle(bool k, bool q) {
+        int sq, sub;
+        const int e = white ? 4 : 60;
+        if (pick(k ? 1ull : 0ull, 1, sq, sub)) { from = e; to = e + 2; special = MV_CASTLE_K; return; }
+        if (pick(q ? 1ull : 0ull, 1, sq, sub)) { from = e; to = e - 2; special = MV_CASTLE_Q; }
+    }
+    __device__ __forceinline__ void ep(u64 caps, int epsq) {
+        int sq, sub;
+        if (pick(caps, 1, sq, sub)) { from = sq; to = epsq; special = MV_EP; }
+    }
+};
+
+__device__ __forceinline__ u64& type_board(Pos& p, int t) {
+    switch (t) {
+        case PT_P: return p.P; case PT_N: return p.N; case PT_B: return p.B;
+        case PT_R: return p.R; case PT_Q: return p.Q; default: return p.K;
+    }
+}
+
+// Board.push for standard chess on the packed representation (keeps castling rights clean).
+__device__ __forceinline__ void apply_move(Pos& p, const SelectVisitor& m) {
+    const bool white = p.meta & CDQ_META_TURN_WHITE;
+    const int us = white ? 1 : 0, them = us ^ 1;
+    const u64 fb = 1ull << m.from, tb = 1ull << m.to;
+    int pt = PT_K;
+    if (p.P & fb) pt = PT_P; else if (p.N & fb) pt = PT_N; else if (p.B & fb) pt = PT_B;
+    else if (p.R & fb) pt = PT_R; else if (p.Q & fb) pt = PT_Q;
+    // captured piece (if any) leaves
+    p.P &= ~tb; p.N &= ~tb; p.B &= ~tb; p.R &= ~tb; p.Q &= ~tb; p.K &= ~tb;
+    p.co[them] &= ~tb;
+    // mover
+    type_board(p, pt) &= ~fb;
+    p.co[us] &= ~fb;
+    type_board(p, m.promo >= 0 ? m.promo : pt) |= tb;
+    p.co[us] |= tb;
+    if (m.special == MV_EP) {
+        const u64 cap = white ? (tb >> 8) : (tb << 8);
+        p.P &= ~cap; p.co[them] &= ~cap;
+    } else if (m.special == MV_CASTLE_K || m.special == MV_CASTLE_Q) {
+        const int base = white ? 0 : 56;
+        const u64 rf = 1ull << (base + (m.special == MV_CASTLE_K ? 7 : 0));
+        const u64 rt = 1ull << (base + (m.special == MV_CASTLE_K ? 5 : 3));
+        p.R = (p.R & ~rf) | rt;
+        p.co[us] = (p.co[us] & ~rf) | rt;
+    }
+    // meta: flip turn, clear ep, update rights
+    u64 meta = p.meta;
+    meta ^= CDQ_META_TURN_WHITE;
+    meta &= ~(CDQ_META_EP_MASK << CDQ_META_EP_SHIFT);
+    if (m.special == MV_DOUBLE) meta |= (u64)((white ? m.from + 8 : m.from - 8) + 1) << CDQ_META_EP_SHIFT;
+    const u64 touched = fb | tb;
+    if (touched & (1ull << 7)) meta &= ~CDQ_META_CASTLE_WK;
+    if (touched & (1ull << 0)) meta &= ~CDQ_META_CASTLE_WQ;
+    if (touched & (1ull << 63)) meta &= ~CDQ_META_CASTLE_BK;
+    if (touched & (1ull << 56)) meta &= ~CDQ_META_CASTLE_BQ;
+    if (pt == PT_K) meta &= white ? ~(CDQ_META_CASTLE_WK | CDQ_META_CASTLE_WQ) : ~(CDQ_META_CASTLE_BK | CDQ_META_CASTLE_BQ);
+    p.meta = meta;
+}
+
+__device__ __forceinline__ Pos start_position() {
+    Pos p;
+    p.P = 0x00ff00000000ff00ull; p.N = 0x4200000000000042ull; p.B = 0x2400000000000024ull;
+    p.R = 0x8100000000000081ull; p.Q = 0x0800000000000008ull; p.K = 0x1000000000000010ull;
+    p.co[1] = 0xffffull; p.co[0] = 0xffff000000000000ull;
+    p.meta = CDQ_META_TURN_WHITE | CDQ_META_CASTLE_WK | CDQ_META_CASTLE_WQ | CDQ_META_CASTLE_BK | CDQ_META_CASTLE_BQ;
+    return p;
+}
+
+__global__ void __launch_bounds__(128)
+random_playouts_kernel(CdqBoard* __restrict__ boards, long long n, u64 seed, int max_plies) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pos p = start_position();
+    const u64 key = mix64(seed ^ mix64((u64)i));
+    const int plies = (int)(mix64(key) % (u64)(max_plies + 1));
+    for (int k = 0; k < plies; k++) {
+        const u64 occ = p.co[0] | p.co[1];
+        const Props q = make_props(~occ);
+        const bool white = p.meta & CDQ_META_TURN_WHITE;
+        const u64 att_opp = white ? attack_map<0>(p, q) : attack_map<1>(p, q);
+        CountVisitor cv;
+        if (white) gen_side<1>(p, q, att_opp, cv); else gen_side<0>(p, q, att_opp, cv);
+        if (cv.n == 0 || insufficient_material(p)) break;
+        SelectVisitor sv((int)(mix64(key + 1 + (u64)k) % (u64)cv.n), occ, white);
+        sv.king_bb = p.K & p.co[white ? 1 : 0];
+        if (white) gen_side<1>(p, q, att_opp, sv); else gen_side<0>(p, q, att_opp, sv);
+        apply_move(p, sv);
+    }
+    store_pos(p, reinterpret_cast<u64*>(boards) + i * 9);
+}
+
+// All legal successors of each position (side to move), the building block of a batched tree
+// expansion (mcts.py:166-194 calls list(board.legal_moves) + push per child).  children is
+// [n][max_children]; counts[i] = number of legal moves (children beyond max_children are dropped).
+__global__ void __launch_bounds__(128)
+expand_kernel(const CdqBoard* __restrict__ boards, long long n, int max_children,
+              CdqBoard* __restrict__ children, int* __restrict__ counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Pos p = load_pos(reinterpret_cast<const u64*>(boards) + i * 9);
+    const u64 occ = p.co[0] | p.co[1];
+    const Props q = make_props(~occ);
+    const bool white = p.meta & CDQ_META_TURN_WHITE;
+    const u64 att_opp = white ? attack_map<0>(p, q) : attack_map<1>(p, q);
+    CountVisitor cv;
+    if (white) gen_side<1>(p, q, att_opp, cv); else gen_side<0>(p, q, att_opp, cv);
+    counts[i] = cv.n;
+    const int m = cv.n < max_children ? cv.n : max_children;
+    for (int r = 0; r < m; r++) {
+        SelectVisitor sv(r, occ, white);
+        sv.king_bb = p.K & p.co[white ? 1 : 0];
+        if (white) gen_side<1>(p, q, att_opp, sv); else gen_side<0>(p, q, att_opp, sv);
+        Pos c = p;
+        apply_move(c, sv);
+        store_pos(c, reinterpret_cast<u64*>(children) + (i * max_children + r) * 9);
+    }
+}
+
+int launch_expand(const CdqBoard* boards, long long n, int max_children, CdqBoard* children, int* counts,
+                  cudaStream_t st) {
+    if (n == 0) return 0;
+    ProfileScope ps(KK_PLAYOUT, st);
+    expand_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(boards, n, max_children, children, counts);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int launch_random_playouts(CdqBoard* boards, long long n, unsigned long long seed, int max_plies, cudaStream_t st) {
+    if (n == 0) return 0;
+    ProfileScope ps(KK_PLAYOUT, st);
+    random_playouts_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(boards, n, seed, max_plies);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+} // namespace cdq

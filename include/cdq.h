@@ -91,6 +91,7 @@ enum { CDQ_TERM_NONE = 0, CDQ_TERM_CHECKMATE = 1, CDQ_TERM_STALEMATE = 2,
 #define CDQ_F_INSUFFICIENT 0x40u
 #define CDQ_F_REP3 0x80u
 #define CDQ_F_STM_MOVES_SHIFT 8     /* bits 8..15: legal moves of the side to move (saturates at 255)     */
+#define CDQ_F_WHITE_TO_MOVE 0x10000u /* copy of meta bit 0, so consumers of flags need not re-read boards */
 #define CDQ_F_BADBOARD 0x80000000u  /* record violates the format (see CDQ_E_BADBOARD)                    */
 
 /* ---- ChessQNetwork parameters (neural_network.py:16-27), fp32, PyTorch layouts ---- */
@@ -153,8 +154,24 @@ int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
  * keyed by (seed, i, ply)); stops early at no-legal-move / insufficient material. */
 int cdq_random_playouts(CdqBoard* d_boards, int64_t n, uint64_t seed, int max_plies, void* stream);
 
+/* All legal successor positions of each board's side to move (list(board.legal_moves) + push,
+ * mcts.py:166-194): d_children is [n][max_children] records, d_counts[i] = legal move count. */
+int cdq_expand(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* d_children,
+               int32_t* d_counts, void* stream);
+
 /* Kernel launch counter (all cdq_* kernels launched by this process), for bench gpu_launches. */
 uint64_t cdq_launch_count(void);
+
+/* Per-kernel device timing (CUDA events on the launching stream), used by bench.py's roofline
+ * line.  Kinds: 0 eval, 1 conv stack, 2 fc head, 3 encode planes, 4 playouts/expand,
+ * 5 weight pack, 6 train. */
+void cdq_profile_enable(int on);
+int cdq_profile_collect(double* ms_per_kind /*[8]*/, uint64_t* launches_per_kind /*[8]*/);
+
+/* Parity/debug hook: runs only the conv stack; dumps ReLU(conv1) as fp16 [n][64][32] (optional)
+ * and the fc1 operand tiles (fp16, ceil(n/128) MiB). */
+int cdq_debug_conv(const CdqNet* net, const CdqBoard* d_boards, int64_t n, void* d_act1,
+                   void* d_act2_tiles, void* stream);
 
 #ifdef __cplusplus
 }
