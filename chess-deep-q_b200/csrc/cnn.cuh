@@ -17,6 +17,7 @@ struct PackedNet {
     const float* fc2_b;
 };
 
+int device_sm_count();
 int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, cudaStream_t st);
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                       cudaStream_t st);
