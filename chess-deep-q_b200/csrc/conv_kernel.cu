@@ -125,7 +125,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
             for (int t = 0; t < 4; t++) {
                 mbar_wait(bars + B_C1_EMPTY + t, (j & 1) ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -137,7 +137,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
                 }
                 __syncwarp();
             }
-            if (lane == 0) umma_commit(bars + B_PL_EMPTY + buf);
+            if (elect_one_sync()) umma_commit(bars + B_PL_EMPTY + buf);
             __syncwarp();
         };
         auto issue_c2 = [&](int j) {
@@ -149,7 +149,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
             for (int t = 0; t < 4; t++) {
                 mbar_wait(bars + B_C2_EMPTY + t, (j & 1) ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -163,7 +163,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
                 }
                 __syncwarp();
             }
-            if (lane == 0) umma_commit(bars + B_A1_EMPTY + buf);
+            if (elect_one_sync()) umma_commit(bars + B_A1_EMPTY + buf);
             __syncwarp();
         };
         if (n_local > 0) issue_c1(0);
