@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcdq.so")
+SO_PATH = os.environ.get("CDQ_LIBCDQ") or os.path.join(_HERE, "libcdq.so")  # env override: A/B builds
 
 c_void_p, c_int64, c_int, c_uint64, c_size_t = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                                  ctypes.c_uint64, ctypes.c_size_t)

@@ -37,10 +37,12 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an A/B variant, e.g. build(defines=["CDQ_ALL_LANES_POLL"], out="libcdq_alt.so")."""
+    if out is None and not force and not stale():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", OUT] + sources()
+    target = os.path.join(HERE, out) if out else OUT
+    cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", target] + sources()
     env = dict(os.environ)
     env.pop("CC", None)  # this image exports a CC wrapper that nvcc's host compile does not need
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
@@ -52,8 +54,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libcdq.so")
     if verbose:
         print(log)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

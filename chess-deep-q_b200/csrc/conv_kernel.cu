@@ -106,7 +106,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
 
     if (warp == 0) {
         // =============================== MMA issuer (warp-uniform control, lane 0 issues)
-        mbar_wait(bars + B_W, 0);
+        mbar_wait_warp(lane, bars + B_W, 0);
         const uint32_t smem_a = smem_u32(smem);
         constexpr uint32_t IDESC1 = make_idesc_f16(128, 32);
         constexpr uint32_t IDESC2 = make_idesc_f16(128, 64);
@@ -118,12 +118,12 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
 
         auto issue_c1 = [&](int j) {
             const int buf = j & 1;
-            mbar_wait(bars + B_PL_FULL + buf, (j >> 1) & 1);
+            mbar_wait_warp(lane, bars + B_PL_FULL + buf, (j >> 1) & 1);
             tc_fence_after();
             const uint64_t a_base = A_HI | A_LBO | (uint64_t)(((smem_a + OFF_PLANES + buf * PLANES_BYTES) >> 4) & 0x3fff);
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                mbar_wait(bars + B_C1_EMPTY + t, (j & 1) ^ 1);
+                mbar_wait_warp(lane, bars + B_C1_EMPTY + t, (j & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one_sync()) {
 #pragma unroll
@@ -142,12 +142,12 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
         };
         auto issue_c2 = [&](int j) {
             const int buf = j & 1;
-            mbar_wait(bars + B_A1_FULL + buf, (j >> 1) & 1);
+            mbar_wait_warp(lane, bars + B_A1_FULL + buf, (j >> 1) & 1);
             tc_fence_after();
             const uint64_t a_base = A_HI | A_LBO | (uint64_t)(((smem_a + OFF_ACT1 + buf * ACT1_BYTES) >> 4) & 0x3fff);
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                mbar_wait(bars + B_C2_EMPTY + t, (j & 1) ^ 1);
+                mbar_wait_warp(lane, bars + B_C2_EMPTY + t, (j & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one_sync()) {
 #pragma unroll
@@ -190,26 +190,27 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
 
         auto encode = [&](int j) {
             const int buf = j & 1;
-            mbar_wait(bars + B_PL_EMPTY + buf, ((j >> 1) & 1) ^ 1);
+            mbar_wait_warp(lane, bars + B_PL_EMPTY + buf, ((j >> 1) & 1) ^ 1);
             named_bar_sync(1, 128);             // previous encode finished reading srec
             if (e < 72) srec[e] = next_word;
             named_bar_sync(1, 128);
             next_word = fetch(j + 1);           // in flight during this encode and the next epilogue
-            // thread = (position e/16, rank (e/2)%8, half-rank e%2) -> 4 squares x 32 B one-hot
-            const int p = e >> 4, y = (e >> 1) & 7, x0 = (e & 1) * 4;
+            // thread = (half-board e/64, position (e/8)%8, file e%8) -> 4 ranks x 32 B one-hot.  A
+            // quarter-warp (8 files of one position) writes 128 contiguous bytes: no bank conflicts.
+            const int p = (e >> 3) & 7, y0 = (e >> 6) * 4, xf = e & 7;
             const u64* r = srec + p * 9;
-            const int sh = 8 * y + x0;
-            unsigned tb[6];
+            const int sh = 8 * y0 + xf;
+            unsigned tb[6];       // bit 8*k = rank y0+k of this file
 #pragma unroll
-            for (int t = 0; t < 6; t++) tb[t] = (unsigned)(r[t] >> sh) & 0xfu;
-            const unsigned wb = (unsigned)(r[6] >> sh) & 0xfu, bb = (unsigned)(r[7] >> sh) & 0xfu;
-            uint8_t* dst0 = smem + OFF_PLANES + buf * PLANES_BYTES + (y + 1) * RANK_BYTES + p * ROW_BYTES + (x0 + 1) * CELL;
+            for (int t = 0; t < 6; t++) tb[t] = (unsigned)(r[t] >> sh) & 0x01010101u;
+            const unsigned wb = (unsigned)(r[6] >> sh) & 0x01010101u, bb = (unsigned)(r[7] >> sh) & 0x01010101u;
+            uint8_t* dst0 = smem + OFF_PLANES + buf * PLANES_BYTES + (y0 + 1) * RANK_BYTES + p * ROW_BYTES + (xf + 1) * CELL;
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
+            for (int x = 0; x < 4; x++) {   // x = rank offset; bit position 8*x
                 int t = -1;
 #pragma unroll
-                for (int k = 0; k < 6; k++) if ((tb[k] >> x) & 1) t = k;
-                const bool isw = (wb >> x) & 1, isb = (bb >> x) & 1;
+                for (int k = 0; k < 6; k++) if ((tb[k] >> (8 * x)) & 1) t = k;
+                const bool isw = (wb >> (8 * x)) & 1, isb = (bb >> (8 * x)) & 1;
                 const int ch = (t >= 0 && (isw || isb)) ? (isw ? t : t + 6) : -1;   // board_utils.py:17-30
                 u64 lo0 = 0, hi0 = 0, lo1 = 0;
                 const u64 one = 0x3C00ull;                                          // fp16 1.0
@@ -217,9 +218,9 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
                 else if (ch >= 4 && ch < 8) hi0 = one << (16 * (ch - 4));
                 else if (ch >= 8) lo1 = one << (16 * (ch - 8));
                 const u64 hi1 = one;            // channel 12: constant one (carries conv1's bias)
-                *reinterpret_cast<uint4*>(dst0 + x * CELL) =
+                *reinterpret_cast<uint4*>(dst0 + x * RANK_BYTES) =
                     make_uint4((unsigned)lo0, (unsigned)(lo0 >> 32), (unsigned)hi0, (unsigned)(hi0 >> 32));
-                *reinterpret_cast<uint4*>(dst0 + CHUNK_BYTES + x * CELL) =
+                *reinterpret_cast<uint4*>(dst0 + CHUNK_BYTES + x * RANK_BYTES) =
                     make_uint4((unsigned)lo1, (unsigned)(lo1 >> 32), (unsigned)hi1, (unsigned)(hi1 >> 32));
             }
             fence_proxy_async();
@@ -228,11 +229,11 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
         };
         auto epilogue1 = [&](int j) {
             const int buf = j & 1;
-            mbar_wait(bars + B_A1_EMPTY + buf, ((j >> 1) & 1) ^ 1);   // conv2 of group j-2 has read this buffer
+            mbar_wait_warp(lane, bars + B_A1_EMPTY + buf, ((j >> 1) & 1) ^ 1);   // conv2 of group j-2 has read this buffer
             const long long pos = (blockIdx.x + (long long)j * gridDim.x) * GROUP + r_pos;
 #pragma unroll 1
             for (int t = 0; t < 4; t++) {
-                mbar_wait(bars + B_C1_FULL + t, j & 1);
+                mbar_wait_warp(lane, bars + B_C1_FULL + t, j & 1);
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_C1 + 32 * t, v);
@@ -268,7 +269,9 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int r_yy = row >> 6, r_pos = (row >> 3) & 7, r_x = row & 7;
-        const float4* sb2 = reinterpret_cast<const float4*>(smem + OFF_B2);
+        float4 b2r[16];   // conv2 bias, kept in registers for the whole kernel
+#pragma unroll
+        for (int k = 0; k < 16; k++) b2r[k] = reinterpret_cast<const float4*>(smem + OFF_B2)[k];
         for (int i = 0; i < n_local; i++) {
             const long long pos = (blockIdx.x + (long long)i * gridDim.x) * GROUP + r_pos;
             const int pr = (int)(pos & 127);
@@ -277,7 +280,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
             uint8_t* base = reinterpret_cast<uint8_t*>(act2) + ((pos >> 7) << 20) + (pr >> 3) * 128 + (pr & 7) * 16;
 #pragma unroll 1
             for (int t = 0; t < 4; t++) {
-                mbar_wait(bars + B_C2_FULL + t, i & 1);
+                mbar_wait_warp(lane, bars + B_C2_FULL + t, i & 1);
                 tc_fence_after();
                 uint32_t v0[32], v1[32];
                 const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + 64 * t;
@@ -292,7 +295,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
 #pragma unroll
                 for (int kc = 0; kc < 8; kc++) {
                     const uint32_t* v = kc < 4 ? v0 + kc * 8 : v1 + (kc - 4) * 8;
-                    const float4 ba = sb2[kc * 2], bb = sb2[kc * 2 + 1];
+                    const float4 ba = b2r[kc * 2], bb = b2r[kc * 2 + 1];
                     uint4 o;
                     o.x = relu_pack_f16(__uint_as_float(v[0]) + ba.x, __uint_as_float(v[1]) + ba.y);
                     o.y = relu_pack_f16(__uint_as_float(v[2]) + ba.z, __uint_as_float(v[3]) + ba.w);

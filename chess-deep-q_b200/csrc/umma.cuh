@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Whole-warp wait.  All lanes poll: measured on B200, letting only lane 0 poll while the others
+// park on __syncwarp DOUBLED the conv kernel's time (3.47 -> 7.38 ms per 1M positions), so the
+// single-lane form is kept only as an A/B switch.
+__device__ __forceinline__ void mbar_wait_warp(int lane, uint64_t* bar, uint32_t parity) {
+#ifndef CDQ_ONE_LANE_POLLS
+    (void)lane;
+    mbar_wait(bar, parity);
+#else
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+#endif
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -95,6 +108,22 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// Weight-stationary form: B is held in collector buffer b0 across MMAs.  MODE 0 = fill (read B
+// from shared memory and keep it), 1 = use (reuse the kept B), 2 = lastuse, 3 = discard.
+template <int MODE>
+__device__ __forceinline__ void umma_f16_ws(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+#define CDQ_WS_ASM(M)                                                                                    \
+    asm volatile(                                                                                        \
+        "{\n\t.reg .pred p;\n\t"                                                                         \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                                      \
+        "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::" M " [%0], %1, %2, %3, p;\n\t}"           \
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory")
+    if (MODE == 0) CDQ_WS_ASM("fill");
+    else if (MODE == 1) CDQ_WS_ASM("use");
+    else if (MODE == 2) CDQ_WS_ASM("lastuse");
+    else CDQ_WS_ASM("discard");
+#undef CDQ_WS_ASM
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
