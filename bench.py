@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dqn", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -217,6 +218,41 @@ def main():
     e2e = world * n * e2e_steps / e2e_s
     assert torch.equal(h_out["leaf"].cuda(), out["leaf"]), "host path and device path disagree"
 
+    # ---- second metric (BASELINE configs[3]): DQN replay step, global batch 4096 split over the ranks
+    #      (strong scaling), one NCCL all-reduce of the flat gradient per step
+    dqn = None
+    if not args.no_dqn:
+        from chess_deep_q_b200.train import FusedAdam, dqn_train_step, shard_range
+        B = 4096
+        lo, hi = shard_range(B, rank, world)
+        tgt = cdq.ChessQNetwork().cuda()
+        tgt.load_state_dict(net.state_dict())
+        opt = FusedAdam(net, lr=1e-3)
+        s_b, ns_b = boards[lo:hi].contiguous(), boards[lo + 1:hi + 1].contiguous()
+        sc, fl = cdq.evaluate_batch(ns_b)
+        rew = (0.01 * torch.tanh(sc / 10.0)).float()                  # chess_ai.py:183
+        dn = ((fl & 7) != 0).float()
+        for _ in range(3):
+            dqn_train_step(net, tgt, opt, s_b, ns_b, rew, dn, 0.99)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        dsteps = 20
+        for _ in range(dsteps):
+            dloss = dqn_train_step(net, tgt, opt, s_b, ns_b, rew, dn, 0.99)
+        t1e.record()
+        torch.cuda.synchronize()
+        dms = t0e.elapsed_time(t1e)
+        if dist:
+            t = torch.tensor([dms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dms = float(t.item())
+        dqn = {"metric": "DQN samples/sec", "value": B * dsteps / (dms * 1e-3), "unit": "samples/s", "global_batch": B,
+               "ms_per_step": dms / dsteps, "scaling": "strong", "loss": float(dloss.item()),
+               "parallelism": "dp%d, one NCCL all-reduce of 1 071 073 fp32 grads per step" % world if world > 1 else "single GPU"}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -251,7 +287,7 @@ def main():
                        "positions_per_gpu": n, "l2": "per-step working set (act2 %.1f GB) >> 126 MB L2" % (n * 8192 / 1e9),
                        "weights": "numpy seed 42, torch-default init ranges, weight matrices x2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * H2D_PER_POS, "d2h_bytes_per_step": n * D2H_PER_POS},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dqn": dqn}
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

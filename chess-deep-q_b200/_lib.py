@@ -23,6 +23,11 @@ SIGNATURES = {
     "cdq_leaf_eval": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "cdq_leaf_eval_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cdq_train_workspace_bytes": (c_size_t, [c_int64]),
+    "cdq_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdq_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.c_float, ctypes.c_float,
+                              ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
     "cdq_random_playouts": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
     "cdq_expand": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "cdq_launch_count": (c_uint64, []),

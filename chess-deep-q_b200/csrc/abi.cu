@@ -172,7 +172,7 @@ static int forward_chunks(const CdqNet* net, const CdqBoard* d_boards, int64_t n
         if (int e = launch_conv_stack(d_boards + off, c, net->p, (__half*)ws, dbg_act1 ? dbg_act1 + off * 2048 : nullptr, st))
             return e;
         if (int e = launch_fc_head((const __half*)ws, c, net->p, d_value ? d_value + off : nullptr,
-                                   d_flags ? d_flags + off : nullptr, d_leaf ? d_leaf + off : nullptr, st))
+                                   d_flags ? d_flags + off : nullptr, d_leaf ? d_leaf + off : nullptr, nullptr, st))
             return e;
     }
     return 0;
@@ -199,6 +199,29 @@ int cdq_debug_conv(const CdqNet* net, const CdqBoard* d_boards, int64_t n, void*
     if (!net || !net->loaded || n <= 0 || n > FWD_CHUNK || !d_boards || !d_act2_tiles) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
     return launch_conv_stack(d_boards, n, net->p, (__half*)d_act2_tiles, (__half*)d_act1, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ DQN replay step
+size_t cdq_train_workspace_bytes(int64_t n) { return train_workspace_bytes(n); }
+
+int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
+                      const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,
+                      const float* d_done, int64_t n, float gamma, int loss_kind, const CdqWeights* d_grads,
+                      float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!net || !target_net || !net->loaded || !target_net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 ||
+        !d_states || !d_next_states || !d_reward || !d_done || !d_workspace || (loss_kind != 0 && loss_kind != 1))
+        return CDQ_E_BADARG;
+    if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
+    if (int e = check_device()) return e;
+    return train_fwd_bwd(net, target_net, *d_weights, d_states, d_next_states, d_reward, d_done, n, gamma, loss_kind,
+                         *d_grads, d_loss, d_workspace, (cudaStream_t)stream);
+}
+
+int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n_params, int step, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    if (!d_params || !d_grads || !d_m || !d_v || n_params < 0 || step < 1) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_adam(d_params, d_grads, d_m, d_v, n_params, step, lr, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ host-buffer path (e2e)

@@ -22,9 +22,20 @@ int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* f
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                       cudaStream_t st);
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
-                   float* leaf, cudaStream_t st);
+                   float* leaf, float* hidden, cudaStream_t st);
+
+size_t train_workspace_bytes(long long n);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2,
+                float eps, float grad_scale, cudaStream_t st);
 
 } // namespace cdq
+
+struct CdqNet;
+namespace cdq {
+int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
+                  const CdqBoard* next_states, const float* reward, const float* done, long long n, float gamma,
+                  int loss_kind, const CdqWeights& g, float* loss, void* ws_base, cudaStream_t st);
+}
 
 // what the opaque C handle points to
 struct CdqNet {

@@ -26,7 +26,8 @@ constexpr int FC_THREADS = 192; // warp 0: bulk-copy producer, warp 1: MMA issue
 
 __global__ void __launch_bounds__(FC_THREADS, 1)
 fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net,
-               float* __restrict__ value, const unsigned* __restrict__ flags, float* __restrict__ leaf) {
+               float* __restrict__ value, const unsigned* __restrict__ flags, float* __restrict__ leaf,
+               float* __restrict__ hidden /* optional [n][256] ReLU(fc1), kept for the backward pass */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* sb1 = reinterpret_cast<float*>(smem + FC_OFF_VEC);
     float* sw2 = sb1 + 256;
@@ -99,6 +100,7 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
             mbar_wait(acc_full + ab, (tcount >> 1) & 1);
             tc_fence_after();
             float dot = 0.f;
+            const long long pos = (t << 7) + q * 32 + lane;
 #pragma unroll 1
             for (int c = 0; c < 8; c++) {
                 uint32_t v[32];
@@ -108,12 +110,19 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
                 for (int j = 0; j < 32; j++) {
                     const float h = fmaxf(__uint_as_float(v[j]) + sb1[c * 32 + j], 0.f);
                     dot = fmaf(h, sw2[c * 32 + j], dot);
+                    v[j] = __float_as_uint(h);
+                }
+                if (hidden && pos < n) {
+                    float4* hp = reinterpret_cast<float4*>(hidden + pos * 256 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        hp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + ab);
-            const long long pos = (t << 7) + q * 32 + lane;
             if (pos < n) {
                 const float v = tanhf(dot + sb2[0]);
                 if (value) value[pos] = v;
@@ -179,7 +188,7 @@ int device_sm_count() {
 }
 
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
-                   float* leaf, cudaStream_t st) {
+                   float* leaf, float* hidden, cudaStream_t st) {
     if (n == 0) return 0;
     const long long tiles = (n + 127) / 128;
     static bool attr_set = false;
@@ -190,7 +199,7 @@ int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float*
     const int sms = device_sm_count();
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     ProfileScope ps(KK_FC, st);
-    fc_head_kernel<<<grid, FC_THREADS, FC_SMEM, st>>>(act2, n, net, value, flags, leaf);
+    fc_head_kernel<<<grid, FC_THREADS, FC_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -1,0 +1,355 @@
+// train_kernels.cu -- K3/K4: one DQN replay step (neural_network.py:218-252) on packed boards:
+//   q  = net(states)              forward with the tcgen05 kernels, keeping ReLU(conv1), ReLU(conv2)
+//   q' = target_net(next_states)  and ReLU(fc1) for the backward pass
+//   y  = r + (1 - done) * gamma * q'          (neural_network.py:238)
+//   loss = mean((q - y)^2)  (or Huber)        (neural_network.py:241)
+//   backward through tanh, fc2, fc1, conv2, conv1; Adam (neural_network.py:65,244-246)
+//
+// Round-1 state of the backward pass: correct and all on the device, but the GEMMs still run on a
+// shared-memory-tiled fp32 SIMT kernel (gemm_kernel below) over im2col buffers; moving them to
+// tcgen05 with the board-in-shared-memory operands of conv_kernel.cu is the next step.
+// Layout conventions: activations are NHWC-like, [position][square][channel]; weight gradients are
+// written in PyTorch order (the epilogues permute).
+#include "common.cuh"
+#include "cnn.cuh"
+#include <cmath>
+
+namespace cdq {
+
+// ------------------------------------------------------------------------------------------
+// C[M][N] (+)= A x B with fp32 accumulation.  A is stored [K][M] (A_KM) or [M][K]; B is [K][N].
+// blockIdx.z splits K (results combined with atomicAdd when the epilogue allows it).
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_FC1_DGRAD = 2, EPI_FC1_WGRAD = 3, EPI_CONV2_WGRAD = 4, EPI_CONV1_WGRAD = 5 };
+
+struct GemmAux {
+    const __half* mask;   // EPI_FC1_DGRAD: ReLU(conv2) in [position][square][channel] order
+};
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+
+template <typename TA, typename TB, bool A_KM, int BM, int BN, int EPI>
+__global__ void __launch_bounds__(256)
+gemm_kernel(const TA* __restrict__ A, const TB* __restrict__ B, float* __restrict__ C, int M, int N, long long K,
+            long long lda, long long ldb, long long ldc, long long k_chunk, GemmAux aux) {
+    constexpr int BK = 16, TM = BM / 16, TN = BN / 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const long long k_begin = (long long)blockIdx.z * k_chunk;
+    const long long k_end = k_begin + k_chunk < K ? k_begin + k_chunk : K;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+    for (long long k0 = k_begin; k0 < k_end; k0 += BK) {
+        for (int idx = tid; idx < BK * BM; idx += 256) {
+            int k, m;
+            if (A_KM) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
+            float v = 0.f;
+            if (m0 + m < M && k0 + k < k_end)
+                v = to_f(A_KM ? A[(k0 + k) * lda + m0 + m] : A[(long long)(m0 + m) * lda + k0 + k]);
+            As[k][m] = v;
+        }
+        for (int idx = tid; idx < BK * BN; idx += 256) {
+            const int k = idx / BN, nn = idx % BN;
+            float v = 0.f;
+            if (n0 + nn < N && k0 + k < k_end) v = to_f(B[(k0 + k) * ldb + n0 + nn]);
+            Bs[k][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < TN; j++) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            const int m = m0 + ty + 16 * i, nn = n0 + tx + 16 * j;
+            if (m >= M || nn >= N) continue;
+            const float v = acc[i][j];
+            if (EPI == EPI_STORE) C[(long long)m * ldc + nn] = v;
+            else if (EPI == EPI_ATOMIC) atomicAdd(C + (long long)m * ldc + nn, v);
+            else if (EPI == EPI_FC1_DGRAD) {
+                // nn = c*64 + sq (reference column order) -> [position][sq][c]; ReLU mask of conv2's output
+                const long long o = (long long)m * 4096 + (nn & 63) * 64 + (nn >> 6);
+                C[o] = __half2float(aux.mask[o]) > 0.f ? v : 0.f;
+            } else if (EPI == EPI_FC1_WGRAD) {
+                // nn = sq*64 + c -> fc1.weight[m][c*64 + sq]
+                atomicAdd(C + (long long)m * 4096 + (nn & 63) * 64 + (nn >> 6), v);
+            } else if (EPI == EPI_CONV2_WGRAD) {
+                // nn = tap*32 + ci -> conv2.weight[m][ci][tap]
+                atomicAdd(C + (long long)m * 288 + (nn & 31) * 9 + (nn >> 5), v);
+            } else if (EPI == EPI_CONV1_WGRAD) {
+                // nn = tap*16 + p (p < 12) -> conv1.weight[m][p][tap]
+                if ((nn & 15) < 12) atomicAdd(C + (long long)m * 108 + (nn & 15) * 9 + (nn >> 4), v);
+            }
+        }
+}
+
+template <typename TA, typename TB, bool A_KM, int BM, int BN, int EPI>
+static int run_gemm(const TA* A, const TB* B, float* C, int M, int N, long long K, long long lda, long long ldb,
+                    long long ldc, int k_splits, GemmAux aux, cudaStream_t st) {
+    long long k_chunk = (K + k_splits - 1) / k_splits;
+    k_chunk = (k_chunk + 15) / 16 * 16;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (unsigned)((K + k_chunk - 1) / k_chunk));
+    ProfileScope ps(KK_TRAIN, st);
+    gemm_kernel<TA, TB, A_KM, BM, BN, EPI><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, k_chunk, aux);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// act2 tiles (fc1 A-operand order) -> [position][square][channel] fp16
+__global__ void untile_act2_kernel(const __half* __restrict__ tiles, long long n, __half* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pos, sq, kc)
+    if (i >= n * 512) return;
+    const int kc = (int)(i & 7), sq = (int)((i >> 3) & 63);
+    const long long pos = i >> 9;
+    const int pr = (int)(pos & 127);
+    const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(tiles) + (((pos >> 7) * 64 + sq) << 14) +
+                                                    kc * 2048 + (pr >> 3) * 128 + (pr & 7) * 16);
+    *reinterpret_cast<uint4*>(out + pos * 4096 + sq * 64 + kc * 8) = v;
+}
+
+// loss + backward through tanh and fc2; one warp per position (grid-stride)
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const float* __restrict__ reward,
+                const float* __restrict__ done, const float* __restrict__ hidden, const float* __restrict__ fc2_w,
+                long long n, float gamma, int loss_kind, float* __restrict__ dz1, float* __restrict__ g_fc2_w,
+                float* __restrict__ g_fc2_b, float* __restrict__ loss) {
+    __shared__ float s_gw[8][256];
+    __shared__ float s_misc[8][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gw[8], gb = 0.f, ls = 0.f, w2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { gw[i] = 0.f; w2[i] = fc2_w[lane + 32 * i]; }
+    const float inv_n = 1.f / (float)n;
+    for (long long b = (long long)blockIdx.x * 8 + warp; b < n; b += (long long)gridDim.x * 8) {
+        const float qv = q[b];
+        const float y = reward[b] + (1.f - done[b]) * gamma * qn[b];      // neural_network.py:238
+        const float d = qv - y;
+        float dl;                                                          // d loss / d q
+        if (loss_kind == 0) { ls += d * d; dl = 2.f * d; }                 // F.mse_loss (neural_network.py:241)
+        else { const float ad = fabsf(d); ls += ad < 1.f ? 0.5f * d * d : ad - 0.5f; dl = fminf(1.f, fmaxf(-1.f, d)); }
+        const float dz2 = dl * inv_n * (1.f - qv * qv);                    // through tanh
+        gb += dz2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int j = lane + 32 * i;
+            const float h = hidden[b * 256 + j];
+            gw[i] = fmaf(dz2, h, gw[i]);
+            dz1[b * 256 + j] = h > 0.f ? dz2 * w2[i] : 0.f;                // through fc2 and ReLU
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_gw[warp][lane + 32 * i] = gw[i];
+    if (lane == 0) { s_misc[warp][0] = gb; s_misc[warp][1] = ls; }        // identical in all lanes
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += s_gw[w][threadIdx.x];
+    atomicAdd(g_fc2_w + threadIdx.x, t);
+    if (threadIdx.x == 0) {
+        float b0 = 0.f, l0 = 0.f;
+        for (int w = 0; w < 8; w++) { b0 += s_misc[w][0]; l0 += s_misc[w][1]; }
+        atomicAdd(g_fc2_b, b0);
+        atomicAdd(loss, l0 * inv_n);
+    }
+}
+
+// column sums of a [rows][cols] fp32 matrix (bias gradients), cols <= 256
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* __restrict__ out) {
+    const int c = threadIdx.x % cols, sub = threadIdx.x / cols, nsub = 256 / cols;
+    if (sub >= nsub) return;
+    float s = 0.f;
+    for (long long r = (long long)blockIdx.x * nsub + sub; r < rows; r += (long long)gridDim.x * nsub) s += x[r * cols + c];
+    atomicAdd(out + c, s);
+}
+
+// im2col of ReLU(conv1): col1[(b,sq)][tap*32 + ci] = a1[b][sq + tap][ci]  (fp16, zero outside)
+__global__ void im2col_act1_kernel(const __half* __restrict__ a1, long long n, __half* __restrict__ col) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, sq, tap, quarter)
+    if (i >= n * 64 * 9 * 4) return;
+    const int qd = (int)(i & 3), tap = (int)((i >> 2) % 9), sq = (int)((i / 36) & 63);
+    const long long b = i / (36 * 64);
+    const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < 8 && x >= 0 && x < 8) v = *reinterpret_cast<const uint4*>(a1 + (b * 64 + y * 8 + x) * 32 + qd * 8);
+    *reinterpret_cast<uint4*>(col + (b * 64 + sq) * 288 + tap * 32 + qd * 8) = v;
+}
+
+// im2col of the one-hot planes: col0[(b,sq)][tap*16 + p] (fp16)
+__global__ void im2col_planes_kernel(const CdqBoard* __restrict__ boards, long long n, __half* __restrict__ col) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, sq, tap)
+    if (i >= n * 64 * 9) return;
+    const int tap = (int)(i % 9), sq = (int)((i / 9) & 63);
+    const long long b = i / (9 * 64);
+    const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
+    unsigned long long lo = 0, hi = 0, lo1 = 0;
+    if (y >= 0 && y < 8 && x >= 0 && x < 8) {
+        const unsigned long long* r = reinterpret_cast<const unsigned long long*>(boards) + b * 9;
+        const int s = y * 8 + x;
+        int t = -1;
+        for (int k = 0; k < 6; k++) if ((r[k] >> s) & 1) t = k;
+        const bool isw = (r[6] >> s) & 1, isb = (r[7] >> s) & 1;
+        const int ch = (t >= 0 && (isw || isb)) ? (isw ? t : t + 6) : -1;
+        const unsigned long long one = 0x3C00ull;
+        if (ch >= 0 && ch < 4) lo = one << (16 * ch);
+        else if (ch >= 4 && ch < 8) hi = one << (16 * (ch - 4));
+        else if (ch >= 8) lo1 = one << (16 * (ch - 8));
+    }
+    uint4* o = reinterpret_cast<uint4*>(col + (b * 64 + sq) * 144 + tap * 16);
+    o[0] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+    o[1] = make_uint4((unsigned)lo1, (unsigned)(lo1 >> 32), 0u, 0u);
+}
+
+// col2im + ReLU mask: dz1c[b][sq][ci] = a1 > 0 ? sum_tap dcol[b][sq - tap][ci*9 + tap] : 0
+__global__ void fold_conv2_dgrad_kernel(const float* __restrict__ dcol, const __half* __restrict__ a1, long long n,
+                                        float* __restrict__ dz) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, sq, ci)
+    if (i >= n * 64 * 32) return;
+    const int ci = (int)(i & 31), sq = (int)((i >> 5) & 63);
+    const long long b = i >> 11;
+    float s = 0.f;
+    if (__half2float(a1[i]) > 0.f) {
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const int y = (sq >> 3) - (tap / 3 - 1), x = (sq & 7) - (tap % 3 - 1);   // output square that read us
+            if (y >= 0 && y < 8 && x >= 0 && x < 8) s += dcol[(b * 64 + y * 8 + x) * 288 + ci * 9 + tap];
+        }
+    }
+    dz[i] = s;
+}
+
+// Adam (torch.optim.Adam defaults: no weight decay, no amsgrad); grads are pre-multiplied by grad_scale
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    // torch: denom = sqrt(v)/sqrt(bias_correction2) + eps ; p -= (lr / bias_correction1) * m / denom
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2,
+                float eps, float grad_scale, cudaStream_t st) {
+    if (n == 0) return 0;
+    const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+    ProfileScope ps(KK_TRAIN, st);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace carve-up (bytes per position; everything 256-byte aligned per section)
+struct TrainWs {
+    __half* act2_tiles; __half* act1; __half* a2; float* hidden; float* q; float* qn; float* dz1; float* dz2c;
+    __half* col1; float* dcol1; float* dz1c; __half* col0;
+    size_t total;
+};
+static TrainWs carve(void* base, long long n) {
+    TrainWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? (uint8_t*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
+    const long long tiles = (n + 127) / 128;
+    w.act2_tiles = (__half*)take((size_t)tiles << 20);
+    w.act1 = (__half*)take((size_t)n * 64 * 32 * 2);
+    w.a2 = (__half*)take((size_t)n * 4096 * 2);
+    w.hidden = (float*)take((size_t)n * 256 * 4);
+    w.q = (float*)take((size_t)n * 4);
+    w.qn = (float*)take((size_t)n * 4);
+    w.dz1 = (float*)take((size_t)n * 256 * 4);
+    w.dz2c = (float*)take((size_t)n * 4096 * 4);
+    w.col1 = (__half*)take((size_t)n * 64 * 288 * 2);
+    w.dcol1 = (float*)take((size_t)n * 64 * 288 * 4);
+    w.dz1c = (float*)take((size_t)n * 64 * 32 * 4);
+    w.col0 = (__half*)take((size_t)n * 64 * 144 * 2);
+    w.total = off;
+    return w;
+}
+size_t train_workspace_bytes(long long n) { return n > 0 ? carve(nullptr, n).total : 0; }
+
+int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
+                  const CdqBoard* next_states, const float* reward, const float* done, long long n, float gamma,
+                  int loss_kind, const CdqWeights& g /* gradient outputs, pre-zeroed */, float* loss, void* ws_base,
+                  cudaStream_t st) {
+    TrainWs ws = carve(ws_base, n);
+    int e;
+    // ---- forward: target value of next_states (inference), then q of states keeping activations
+    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_tiles, nullptr, st))) return e;
+    if ((e = launch_fc_head(ws.act2_tiles, n, target->p, ws.qn, nullptr, nullptr, nullptr, st))) return e;
+    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, ws.act1, st))) return e;
+    if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
+    {
+        ProfileScope ps(KK_TRAIN, st);
+        untile_act2_kernel<<<(unsigned)((n * 512 + 255) / 256), 256, 0, st>>>(ws.act2_tiles, n, ws.a2);
+        count_launch();
+    }
+    // ---- loss, tanh, fc2
+    {
+        ProfileScope ps(KK_TRAIN, st);
+        const unsigned blocks = (unsigned)((n + 7) / 8 < 1184 ? (n + 7) / 8 : 1184);
+        head_bwd_kernel<<<blocks, 256, 0, st>>>(ws.q, ws.qn, reward, done, ws.hidden, w.fc2_w, n, gamma, loss_kind, ws.dz1,
+                                                (float*)g.fc2_w, (float*)g.fc2_b, loss);
+        count_launch();
+    }
+    GemmAux aux{ws.a2};
+    // ---- fc1: weight gradient (contraction over the batch), bias gradient, data gradient
+    if ((e = run_gemm<float, __half, true, 128, 128, EPI_FC1_WGRAD>(ws.dz1, ws.a2, (float*)g.fc1_w, 256, 4096, n, 256, 4096, 4096,
+                                                                    n >= 2048 ? 4 : 1, aux, st))) return e;
+    {
+        ProfileScope ps(KK_TRAIN, st);
+        colsum_kernel<<<148, 256, 0, st>>>(ws.dz1, n, 256, (float*)g.fc1_b);
+        count_launch();
+    }
+    if ((e = run_gemm<float, float, false, 128, 128, EPI_FC1_DGRAD>(ws.dz1, w.fc1_w, ws.dz2c, (int)n, 4096, 256, 256, 4096, 4096, 1, aux, st)))
+        return e;
+    // ---- conv2: bias, weight gradient over im2col(ReLU(conv1)), data gradient via col2im
+    const long long rows = n * 64;
+    const int ks = (int)(rows / 2048 < 1 ? 1 : (rows / 2048 > 512 ? 512 : rows / 2048));
+    {
+        ProfileScope ps(KK_TRAIN, st);
+        colsum_kernel<<<296, 256, 0, st>>>(ws.dz2c, rows, 64, (float*)g.conv2_b);
+        im2col_act1_kernel<<<(unsigned)((rows * 36 + 255) / 256), 256, 0, st>>>(ws.act1, n, ws.col1);
+        count_launch(2);
+    }
+    if ((e = run_gemm<float, __half, true, 64, 128, EPI_CONV2_WGRAD>(ws.dz2c, ws.col1, (float*)g.conv2_w, 64, 288, rows, 64, 288, 288, ks, aux, st)))
+        return e;
+    if ((e = run_gemm<float, float, false, 128, 128, EPI_STORE>(ws.dz2c, w.conv2_w, ws.dcol1, (int)rows, 288, 64, 64, 288, 288, 1, aux, st)))
+        return e;
+    {
+        ProfileScope ps(KK_TRAIN, st);
+        fold_conv2_dgrad_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(ws.dcol1, ws.act1, n, ws.dz1c);
+        colsum_kernel<<<296, 256, 0, st>>>(ws.dz1c, rows, 32, (float*)g.conv1_b);
+        im2col_planes_kernel<<<(unsigned)((rows * 9 + 255) / 256), 256, 0, st>>>(states, n, ws.col0);
+        count_launch(3);
+    }
+    // ---- conv1: weight gradient over im2col(one-hot planes)
+    if ((e = run_gemm<float, __half, true, 64, 128, EPI_CONV1_WGRAD>(ws.dz1c, ws.col0, (float*)g.conv1_w, 32, 144, rows, 32, 144, 108, ks, aux, st)))
+        return e;
+    return (int)cudaGetLastError();
+}
+
+} // namespace cdq

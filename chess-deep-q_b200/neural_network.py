@@ -68,6 +68,11 @@ class ChessQNetwork(nn.Module):
             self._packed_key = key
         return self._handle
 
+    def invalidate_packed(self):
+        """Force a repack on the next forward (used after the fused optimizer wrote the flat
+        parameter buffer directly, which autograd's version counters do not see)."""
+        self._packed_key = None
+
     def __del__(self):
         try:
             if self._handle is not None:

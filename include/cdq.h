@@ -149,6 +149,23 @@ int cdq_leaf_eval(const CdqNet* net, const CdqBoard* d_boards, int64_t n,
 int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
                        float* h_leaf, double* h_score, uint32_t* h_flags);
 
+/* ---- DQN replay training step (replaces DQNAgent.train, neural_network.py:218-252) ----
+ * cdq_train_fwd_bwd: q = net(states), q' = target_net(next_states), y = r + (1-done)*gamma*q',
+ * loss = mean((q-y)^2) (loss_kind 0, the reference's F.mse_loss) or mean Huber(delta=1) (loss_kind 1),
+ * backward through the whole network.  d_weights = the fp32 master parameters (PyTorch layouts) that
+ * `net` was packed from; d_grads = where to ACCUMULATE the gradients (same layouts; zero them first);
+ * *d_loss is accumulated too (zero it first).  A terminal next_state is the all-zero board
+ * (neural_network.py:215).  After an N-rank data-parallel step, sum the gradients over ranks and
+ * pass grad_scale = 1/N to cdq_adam_step.
+ * cdq_adam_step: torch.optim.Adam defaults (neural_network.py:65) over one flat fp32 buffer. */
+size_t cdq_train_workspace_bytes(int64_t n);
+int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
+                      const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,
+                      const float* d_done, int64_t n, float gamma, int loss_kind, const CdqWeights* d_grads,
+                      float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
+int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n_params, int step,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* Synthetic workload: n random playouts from the start position on the device.
  * Position i plays plies_i = U{0..max_plies} uniformly random legal moves (counter-based RNG
  * keyed by (seed, i, ply)); stops early at no-legal-move / insufficient material. */

@@ -170,3 +170,39 @@ def net_forward(params, planes, return_acts=False):
     if return_acts:
         return out.numpy(), a1.numpy(), a2.numpy(), h.numpy()
     return out.numpy()
+
+
+def dqn_step_reference(params, target_params, states_planes, next_planes, reward, done, gamma=0.99, huber=False):
+    """Restatement of DQNAgent.train()'s maths (neural_network.py:232-245) with fp32 torch-CPU
+    autograd: returns (loss float, {name: gradient ndarray})."""
+    import torch
+    import torch.nn.functional as F
+
+    def fwd(t, x):
+        a1 = F.relu(F.conv2d(x, t["conv1.weight"], t["conv1.bias"], padding=1))
+        a2 = F.relu(F.conv2d(a1, t["conv2.weight"], t["conv2.bias"], padding=1))
+        h = F.relu(F.linear(a2.reshape(-1, 4096), t["fc1.weight"], t["fc1.bias"]))
+        return torch.tanh(F.linear(h, t["fc2.weight"], t["fc2.bias"]))
+
+    t = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+    tt = {k: torch.tensor(v) for k, v in target_params.items()}
+    q = fwd(t, torch.as_tensor(states_planes)).squeeze()
+    with torch.no_grad():
+        qn = fwd(tt, torch.as_tensor(next_planes)).squeeze()
+    y = torch.as_tensor(reward) + (1 - torch.as_tensor(done)) * gamma * qn
+    loss = F.huber_loss(q, y) if huber else F.mse_loss(q, y)
+    loss.backward()
+    return float(loss.detach()), {k: v.grad.numpy().copy() for k, v in t.items()}
+
+
+def adam_reference(params, grads_seq, lr=1e-3):
+    """torch.optim.Adam (the reference's optimizer, neural_network.py:65) applied to a sequence of
+    gradient dicts; returns the updated parameters."""
+    import torch
+    t = {k: torch.nn.Parameter(torch.tensor(v)) for k, v in params.items()}
+    opt = torch.optim.Adam(list(t.values()), lr=lr)
+    for grads in grads_seq:
+        for k, p in t.items():
+            p.grad = torch.tensor(grads[k])
+        opt.step()
+    return {k: v.detach().numpy().copy() for k, v in t.items()}

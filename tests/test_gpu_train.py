@@ -1,0 +1,158 @@
+"""GPU parity tests of the DQN replay step (run on the B200 box: `pytest -m gpu`): the CUDA
+training path through the C ABI vs the fp32 oracle restatement of DQNAgent.train and vs the golden
+step recorded from the reference's own DQNAgent (tests/golden/train_golden.npz)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cdq():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import chess_deep_q_b200 as m
+    return m
+
+
+def _net(cdq, params):
+    net = cdq.ChessQNetwork()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    return net.cuda()
+
+
+def _golden_batch(oracle, eval_golden, train_golden):
+    idx = train_golden["idx"]
+    boards = eval_golden["boards"]
+    return boards[idx], boards[idx + 1], train_golden["reward"], train_golden["done"]
+
+
+def _run_step(cdq, q_net, t_net, opt, s, ns, r, d, **kw):
+    from chess_deep_q_b200.train import dqn_train_step
+    to_dev = cdq.board_utils.to_device
+    return dqn_train_step(q_net, t_net, opt, to_dev(s), to_dev(ns), torch.from_numpy(r).cuda(),
+                          torch.from_numpy(d).cuda(), 0.99, **kw)
+
+
+@pytest.mark.parametrize("tag,scale", [("s1", 1.0), ("s3", 3.0)])
+def test_train_step_gradients_and_loss_match_fp32_reference(cdq, oracle, eval_golden, train_golden, tag, scale):
+    from chess_deep_q_b200.train import FusedAdam, PARAM_ORDER
+    s, ns, r, d = _golden_batch(oracle, eval_golden, train_golden)
+    p, pt = oracle.init_params(42, scale), oracle.init_params(43, scale)
+    q_net, t_net = _net(cdq, p), _net(cdq, pt)
+    opt = FusedAdam(q_net, lr=1e-3)
+    loss = float(_run_step(cdq, q_net, t_net, opt, s, ns, r, d).item())
+    # (1) loss vs the reference's own DQNAgent.train() (golden) -- tolerance: rel 1e-3 (fp16 forward)
+    assert loss == pytest.approx(float(train_golden["loss_" + tag]), rel=1e-3)
+    # (2) gradients vs fp32 autograd of the oracle restatement: per tensor, max error <= 2% of max |g|
+    ref_loss, ref = oracle.dqn_step_reference(p, pt, oracle.encode_planes(s), oracle.encode_planes(ns), r, d)
+    gv = opt.grad_views()
+    for k in PARAM_ORDER:
+        g = gv[k].cpu().numpy()
+        err = np.abs(g - ref[k]).max()
+        assert err <= 2e-2 * np.abs(ref[k]).max() + 1e-9, (k, err, np.abs(ref[k]).max())
+    # (3) weights after the step vs the golden weights of the reference (lr*sign(g) moves; allow
+    #     sign flips only where the gradient is ~0)
+    sd = q_net.state_dict()
+    for k in PARAM_ORDER:
+        a = sd[k].cpu().numpy().reshape(-1)
+        got = a[:: max(1, a.size // 4096)][:4096]
+        bad = np.abs(got - train_golden["w_%s_%s" % (tag, k)]) > 1e-6
+        gref = ref[k].reshape(-1)[:: max(1, a.size // 4096)][:4096]
+        significant = np.abs(gref) > 0.05 * np.abs(ref[k]).max()
+        assert not (bad & significant).any(), (k, int((bad & significant).sum()))
+        assert bad.mean() < 0.10, (k, bad.mean())
+    # (4) second step exercises Adam's moments and the repack of the updated weights
+    loss2 = float(_run_step(cdq, q_net, t_net, opt, s, ns, r, d).item())
+    assert loss2 == pytest.approx(float(train_golden["loss2_" + tag]), rel=2e-2)
+    assert np.abs(q_net.state_dict()["fc2.weight"].cpu().numpy() - train_golden["fc2w2_" + tag]).max() < 2e-4
+
+
+def test_huber_loss_variant(cdq, oracle, eval_golden, train_golden):
+    from chess_deep_q_b200.train import FusedAdam, LOSS_HUBER, PARAM_ORDER
+    s, ns, r, d = _golden_batch(oracle, eval_golden, train_golden)
+    r = (r * 300).astype(np.float32)          # push some |q - y| beyond delta = 1
+    p, pt = oracle.init_params(42, 3.0), oracle.init_params(43, 3.0)
+    q_net, t_net = _net(cdq, p), _net(cdq, pt)
+    opt = FusedAdam(q_net)
+    loss = float(_run_step(cdq, q_net, t_net, opt, s, ns, r, d, loss_kind=LOSS_HUBER).item())
+    ref_loss, ref = oracle.dqn_step_reference(p, pt, oracle.encode_planes(s), oracle.encode_planes(ns), r, d, huber=True)
+    assert loss == pytest.approx(ref_loss, rel=2e-3)
+    gv = opt.grad_views()
+    for k in PARAM_ORDER:
+        # 4%: rewards x300 saturate tanh, which amplifies the fp16-operand forward error
+        assert np.abs(gv[k].cpu().numpy() - ref[k]).max() <= 4e-2 * np.abs(ref[k]).max() + 1e-9, k
+
+
+def test_fused_adam_matches_torch_adam_and_checkpoint_format(cdq, oracle):
+    from chess_deep_q_b200.train import FusedAdam, PARAM_ORDER
+    p = oracle.init_params(42, 1.0)
+    net = _net(cdq, p)
+    opt = FusedAdam(net, lr=1e-3)
+    rng = np.random.default_rng(0)
+    grads_seq = [{k: (rng.standard_normal(v.shape) * 1e-2).astype(np.float32) for k, v in p.items()} for _ in range(3)]
+    for grads in grads_seq:
+        for k, v in opt.grad_views().items():
+            v.copy_(torch.from_numpy(grads[k]))
+        opt.step()
+    ref = oracle.adam_reference(p, grads_seq)
+    sd = net.state_dict()
+    for k in PARAM_ORDER:
+        assert np.abs(sd[k].cpu().numpy() - ref[k]).max() < 2e-6, k
+    # torch.optim.Adam-format state dict loads into a real torch Adam and back (chess_ai.py:459,483)
+    osd = opt.state_dict()
+    tparams = [torch.nn.Parameter(torch.zeros_like(v)) for v in net.parameters()]
+    topt = torch.optim.Adam(tparams, lr=1e-3)
+    topt.load_state_dict(osd)
+    opt2 = FusedAdam(_net(cdq, p))
+    opt2.load_state_dict(topt.state_dict())
+    assert opt2.step_count == 3
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+
+
+def test_dqn_agent_drop_in(cdq, oracle):
+    torch.manual_seed(0)
+    agent = cdq.DQNAgent(batch_size=64)
+    assert agent.train() == 0                      # not enough samples (neural_network.py:220-221)
+    boards = oracle.playouts(201, seed=8)
+    _, sc, fl = oracle.evaluate(boards)
+    for i in range(200):
+        done = bool(fl[i + 1] & 7)
+        agent.store_transition(boards[i:i + 1], None, 0.01 * np.tanh(sc[i + 1] / 10.0),
+                               None if done else boards[i + 1:i + 2], done)
+    eps0 = agent.epsilon
+    losses = [agent.train() for _ in range(5)]
+    assert all(isinstance(x, float) and np.isfinite(x) and x >= 0 for x in losses)
+    assert agent.epsilon <= eps0
+    v0 = agent.get_q_value(boards[:1])
+    agent.update_target_network()
+    with torch.no_grad():
+        a = agent.q_network.forward_packed(boards[:8]).cpu().numpy()
+        b = agent.target_q_network.forward_packed(boards[:8]).cpu().numpy()
+    assert np.array_equal(a, b) and abs(v0 - float(a[0, 0])) < 1e-6
+    # training on a fixed batch reduces its loss
+    agent2 = cdq.DQNAgent(batch_size=200)
+    agent2.memory = agent.memory
+    l = [agent2.train() for _ in range(30)]
+    assert l[-1] < l[0]
+
+
+def test_train_step_batch_4096_properties(cdq, oracle):
+    """BASELINE config[3] size: finite loss/gradients and agreement of the loss with the oracle on
+    the same 4096 samples."""
+    from chess_deep_q_b200.train import FusedAdam
+    n = 4096
+    boards = oracle.playouts(n + 1, seed=77)
+    _, sc, fl = oracle.evaluate(boards[1:], nthreads=0)
+    r = (0.01 * np.tanh(sc / 10.0)).astype(np.float32)
+    d = ((fl & 7) != 0).astype(np.float32)
+    p, pt = oracle.init_params(42, 2.0), oracle.init_params(43, 2.0)
+    q_net, t_net = _net(cdq, p), _net(cdq, pt)
+    opt = FusedAdam(q_net)
+    loss = float(_run_step(cdq, q_net, t_net, opt, boards[:n], boards[1:], r, d).item())
+    ref_loss, ref = oracle.dqn_step_reference(p, pt, oracle.encode_planes(boards[:n]), oracle.encode_planes(boards[1:]), r, d)
+    assert loss == pytest.approx(ref_loss, rel=2e-3)
+    assert bool(torch.isfinite(opt.grad).all())
+    g = opt.grad_views()["fc1.weight"].cpu().numpy()
+    assert np.abs(g - ref["fc1.weight"]).max() <= 2e-2 * np.abs(ref["fc1.weight"]).max()
