@@ -100,7 +100,9 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const long long n_groups = (n + GROUP - 1) / GROUP;
+    // whole 128-position fc1 tiles are always written (missing boards count as empty boards), so
+    // every row of the act2 buffer holds finite values: the training kernels contract over them
+    const long long n_groups = ((n + 127) >> 7) * (128 / GROUP);
     // groups of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_local = (int)((n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
@@ -319,7 +321,7 @@ int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net,
         cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
         attr_set = true;
     }
-    const long long groups = (n + GROUP - 1) / GROUP;
+    const long long groups = ((n + 127) >> 7) * (128 / GROUP);
     const int sms = device_sm_count();
     const unsigned grid = (unsigned)(groups < sms ? groups : sms);
     ProfileScope ps(KK_CONV, st);

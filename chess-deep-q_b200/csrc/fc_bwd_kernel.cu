@@ -1,0 +1,264 @@
+// fc_bwd_kernel.cu -- backward of fc1 (4096 -> 256) on tcgen05, reusing the forward's tiles.
+//
+// dz1h: the gradient at fc1's pre-activation, fp16, scaled by a power of two so it stays in fp16's
+//       normal range, stored per 128 positions as [32 chunks of 8 outputs][16 row groups][8 positions]
+//       [8 halfs] (64 KB).  One 128-byte core matrix of it is simultaneously
+//         - a K-major core matrix (rows = positions, K = outputs)   -> A operand of the DATA gradient
+//         - an MN-major core matrix (M = outputs, K = positions)    -> A operand of the WEIGHT gradient
+// act2: the forward's fc1 A tiles; read MN-major (N = channels of a square, K = positions) they are
+//       the B operand of the weight gradient (tests/cuda/umma_mn_probe.cu checks the encoding).
+//
+//  fc1_dgrad_kernel   dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq]
+//                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
+//  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
+//                     M = 2 x 128 outputs, N = 128 (2 squares), K = positions (split over CTAs)
+#include "umma.cuh"
+#include "common.cuh"
+#include "cnn.cuh"
+
+namespace cdq {
+
+// ------------------------------------------------------------------------------------------ dgrad
+constexpr int DG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
+constexpr int DG_B_BYTES = 256 * 64 * 2;        // 32 KB: W1^T, 256 columns x 64 outputs
+constexpr int DG_STAGES = 4;
+constexpr int DG_OFF_B = DG_A_BYTES;
+constexpr int DG_OFF_BAR = DG_OFF_B + DG_STAGES * DG_B_BYTES;
+constexpr int DG_SMEM = DG_OFF_BAR + 128;
+constexpr int DG_THREADS = 192;
+
+__global__ void __launch_bounds__(DG_THREADS, 1)
+fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act2, const __half* __restrict__ fc1tp,
+                 long long n, float inv_scale, float* __restrict__ dz2) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + DG_OFF_BAR);   // [4]
+    uint64_t* empty = full + DG_STAGES;                                // [4]
+    uint64_t* a_full = empty + DG_STAGES;
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* acc_full = a_empty + 1;                                  // [2]
+    uint64_t* acc_empty = acc_full + 2;                                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < DG_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const long long n_items = ((n + 127) >> 7) * 4;     // (position tile, group of 4 column chunks)
+    constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            uint32_t it = 0, item_no = 0;
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, item_no++) {
+                const long long tile = item >> 2;
+                const int cg = (int)(item & 3);
+                mbar_wait(a_empty, (item_no & 1) ^ 1);
+                mbar_arrive_expect_tx(a_full, DG_A_BYTES);
+                bulk_g2s(smem, reinterpret_cast<const uint8_t*>(dz1h) + tile * DG_A_BYTES, DG_A_BYTES, a_full);
+                for (int c = 0; c < 4; c++)
+                    for (int s = 0; s < 4; s++, it++) {
+                        const int st = it % DG_STAGES;
+                        mbar_wait(empty + st, ((it / DG_STAGES) & 1) ^ 1);
+                        mbar_arrive_expect_tx(full + st, DG_B_BYTES);
+                        bulk_g2s(smem + DG_OFF_B + st * DG_B_BYTES,
+                                 reinterpret_cast<const uint8_t*>(fc1tp) + ((long long)((cg * 4 + c) * 4 + s) << 15), DG_B_BYTES, full + st);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            uint32_t it = 0, item_no = 0, chunk_no = 0;
+            const uint32_t a0 = smem_u32(smem);
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, item_no++) {
+                mbar_wait(a_full, item_no & 1);
+                for (int c = 0; c < 4; c++, chunk_no++) {
+                    const int ab = chunk_no & 1;
+                    mbar_wait(acc_empty + ab, ((chunk_no >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    for (int s = 0; s < 4; s++, it++) {
+                        const int st = it % DG_STAGES;
+                        mbar_wait(full + st, (it / DG_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t b0 = a0 + DG_OFF_B + st * DG_B_BYTES;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            umma_f16(tmem + ab * 256, make_smem_desc(a0 + (s * 8 + 2 * j) * 2048, 2048, 128),
+                                     make_smem_desc(b0 + j * 2 * 4096, 4096, 128), IDESC, (s | j) != 0);
+                        umma_commit(empty + st);
+                    }
+                    umma_commit(acc_full + ab);
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        uint32_t chunk_no = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const long long tile = item >> 2;
+            const int cg = (int)(item & 3);
+            const int pr = q * 32 + lane;
+            const long long pos = (tile << 7) + pr;
+            for (int c = 0; c < 4; c++, chunk_no++) {
+                const int ab = chunk_no & 1;
+                mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int p = 0; p < 8; p++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
+                    tmem_ld_wait();
+                    const int sq = (cg * 4 + c) * 4 + (p >> 1), ch0 = (p & 1) * 32;
+                    if (pos < n) {
+                        const uint8_t* mrow = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + sq) << 14) +
+                                              (ch0 >> 3) * 2048 + (pr >> 3) * 128 + (pr & 7) * 16;
+                        float4* o = reinterpret_cast<float4*>(dz2 + pos * 4096 + sq * 64 + ch0);
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            const uint4 m = *reinterpret_cast<const uint4*>(mrow + g * 2048);
+                            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
+                            float r[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) {
+                                const unsigned hbits = (mw[e >> 1] >> (16 * (e & 1))) & 0xffffu;   // ReLU output: > 0 iff bits != 0
+                                r[e] = hbits ? __uint_as_float(v[g * 8 + e]) * inv_scale : 0.f;
+                            }
+                            o[2 * g] = make_float4(r[0], r[1], r[2], r[3]);
+                            o[2 * g + 1] = make_float4(r[4], r[5], r[6], r[7]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + ab);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+constexpr int WG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
+constexpr int WG_B_BYTES = 2 * 16384;           // 32 KB: act2 blocks of two squares
+constexpr int WG_STAGE = WG_A_BYTES + WG_B_BYTES;
+constexpr int WG_OFF_BAR = 2 * WG_STAGE;
+constexpr int WG_SMEM = WG_OFF_BAR + 64;
+constexpr int WG_THREADS = 192;
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act2, long long n_tiles, int k_splits,
+                 float inv_scale, float* __restrict__ g_fc1_w) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_OFF_BAR);   // [2]
+    uint64_t* empty = full + 2;                                        // [2]
+    uint64_t* acc_full = empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int pair = blockIdx.x / k_splits, split = blockIdx.x % k_splits;   // squares 2*pair, 2*pair + 1
+    const long long my_tiles = split < n_tiles ? (n_tiles - split + k_splits - 1) / k_splits : 0;
+    constexpr uint32_t IDESC = make_idesc_f16_ex(128, 128, true, true);
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            for (long long i = 0; i < my_tiles; i++) {
+                const long long t = split + i * k_splits;
+                const int st = (int)(i & 1);
+                mbar_wait(empty + st, ((i >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(full + st, WG_STAGE);
+                bulk_g2s(smem + st * WG_STAGE, reinterpret_cast<const uint8_t*>(dz1h) + t * WG_A_BYTES, WG_A_BYTES, full + st);
+                bulk_g2s(smem + st * WG_STAGE + WG_A_BYTES,
+                         reinterpret_cast<const uint8_t*>(act2) + ((t * 64 + 2 * pair) << 14), WG_B_BYTES, full + st);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            for (long long i = 0; i < my_tiles; i++) {
+                const int st = (int)(i & 1);
+                mbar_wait(full + st, (i >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + st * WG_STAGE), b0 = a0 + WG_A_BYTES;
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int k = 0; k < 8; k++)      // K step = 16 positions = 2 row groups = 256 B
+                        umma_f16(tmem + h * 128, make_smem_desc(a0 + h * 32768 + k * 256, 128, 2048),
+                                 make_smem_desc(b0 + k * 256, 128, 2048), IDESC, (i | k) != 0);
+                umma_commit(empty + st);
+            }
+            if (my_tiles > 0) umma_commit(acc_full);
+        }
+    } else if (my_tiles > 0) {
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int j = h * 128 + q * 32 + lane;
+#pragma unroll 1
+            for (int p = 0; p < 4; p++) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 128 + p * 32, v);
+                tmem_ld_wait();
+                const int sq = 2 * pair + (p >> 1), ch0 = (p & 1) * 32;
+                float* dst = g_fc1_w + (long long)j * 4096 + ch0 * 64 + sq;   // reference column = ch*64 + sq
+#pragma unroll
+                for (int e = 0; e < 32; e++) atomicAdd(dst + e * 64, __uint_as_float(v[e]) * inv_scale);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, float inv_scale,
+                     float* dz2, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fc1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
+        cudaFuncSetAttribute(fc1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        attr_set = true;
+    }
+    const long long items = ((n + 127) >> 7) * 4;
+    const int sms = device_sm_count();
+    ProfileScope ps(KK_TRAIN, st);
+    fc1_dgrad_kernel<<<(unsigned)(items < sms ? items : sms), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, inv_scale, dz2);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float inv_scale, float* g_fc1_w, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fc1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
+        cudaFuncSetAttribute(fc1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        attr_set = true;
+    }
+    const long long tiles = (n + 127) >> 7;
+    const int k_splits = (int)(tiles < 4 ? tiles : 4);
+    ProfileScope ps(KK_TRAIN, st);
+    fc1_wgrad_kernel<<<32 * k_splits, WG_THREADS, WG_SMEM, st>>>(dz1h, act2, tiles, k_splits, inv_scale, g_fc1_w);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+} // namespace cdq

@@ -143,7 +143,7 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
 
 // ------------------------------------------------------------------------------------------
 // weight repacking: fp32 PyTorch layouts -> fp16 UMMA K-major no-swizzle tiles
-__global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p) {
+__global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N1 = 9 * 32 * 16, N2 = 9 * 64 * 32, N3 = 64ll * 256 * 64;
     if (i < N1) {
@@ -166,13 +166,19 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
         const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 31, kc = (j >> 11) & 7, sq = (int)(j >> 14);
         const int nn = ng * 8 + n8, c = kc * 8 + k8;
         fc1p[j] = __float2half_rn(w.fc1_w[(long long)nn * 4096 + c * 64 + sq]);
+    } else if (i < N1 + N2 + 2 * N3) {
+        // fc1tp[chunk 16][stage 4][kc 8][ng 32][n8][j8]: row n' = sq*64 + ch, K = fc1 output j
+        const long long j = i - N1 - N2 - N3;
+        const int j8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 31, kc = (j >> 11) & 7, sg = (j >> 14) & 3, ck = (int)(j >> 16);
+        const int np = ck * 256 + ng * 8 + n8, sq = np >> 6, ch = np & 63, jo = sg * 64 + kc * 8 + j8;
+        fc1tp[j] = __float2half_rn(w.fc1_w[(long long)jo * 4096 + ch * 64 + sq]);
     }
 }
 
-int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, cudaStream_t st) {
-    const long long total = 9 * 32 * 16 + 9 * 64 * 32 + 64ll * 256 * 64;
+int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, cudaStream_t st) {
+    const long long total = 9 * 32 * 16 + 9 * 64 * 32 + 2 * 64ll * 256 * 64;
     ProfileScope ps(KK_PACK, st);
-    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, w1p, w2p, fc1p);
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, w1p, w2p, fc1p, fc1tp);
     count_launch();
     return (int)cudaGetLastError();
 }

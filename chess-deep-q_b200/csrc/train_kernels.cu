@@ -114,56 +114,63 @@ static int run_gemm(const TA* A, const TB* B, float* C, int M, int N, long long 
 }
 
 // ------------------------------------------------------------------------------------------
-// act2 tiles (fc1 A-operand order) -> [position][square][channel] fp16
-__global__ void untile_act2_kernel(const __half* __restrict__ tiles, long long n, __half* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (pos, sq, kc)
-    if (i >= n * 512) return;
-    const int kc = (int)(i & 7), sq = (int)((i >> 3) & 63);
-    const long long pos = i >> 9;
-    const int pr = (int)(pos & 127);
-    const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(tiles) + (((pos >> 7) * 64 + sq) << 14) +
-                                                    kc * 2048 + (pr >> 3) * 128 + (pr & 7) * 16);
-    *reinterpret_cast<uint4*>(out + pos * 4096 + sq * 64 + kc * 8) = v;
-}
-
-// loss + backward through tanh and fc2; one warp per position (grid-stride)
+// loss + backward through tanh, fc2 and fc1's ReLU; one warp per position (grid-stride).  Writes
+// dz1h (fc_bwd_kernel.cu): fp16, scaled by `scale`, tiled [128-position tile][32 chunks][16 row
+// groups][8 positions][8 halfs]; rows beyond n are written as zeros (the weight gradient contracts
+// over whole tiles).  Lane l owns fc1 outputs 8l .. 8l+7.
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const float* __restrict__ reward,
                 const float* __restrict__ done, const float* __restrict__ hidden, const float* __restrict__ fc2_w,
-                long long n, float gamma, int loss_kind, float* __restrict__ dz1, float* __restrict__ g_fc2_w,
-                float* __restrict__ g_fc2_b, float* __restrict__ loss) {
+                long long n, float gamma, int loss_kind, float scale, __half* __restrict__ dz1h,
+                float* __restrict__ g_fc2_w, float* __restrict__ g_fc2_b, float* __restrict__ g_fc1_b,
+                float* __restrict__ loss) {
     __shared__ float s_gw[8][256];
+    __shared__ float s_gb1[8][256];
     __shared__ float s_misc[8][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float gw[8], gb = 0.f, ls = 0.f, w2[8];
+    float gw[8], gb1[8], gb = 0.f, ls = 0.f, w2[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { gw[i] = 0.f; w2[i] = fc2_w[lane + 32 * i]; }
+    for (int i = 0; i < 8; i++) { gw[i] = 0.f; gb1[i] = 0.f; w2[i] = fc2_w[lane * 8 + i]; }
     const float inv_n = 1.f / (float)n;
-    for (long long b = (long long)blockIdx.x * 8 + warp; b < n; b += (long long)gridDim.x * 8) {
-        const float qv = q[b];
-        const float y = reward[b] + (1.f - done[b]) * gamma * qn[b];      // neural_network.py:238
-        const float d = qv - y;
-        float dl;                                                          // d loss / d q
-        if (loss_kind == 0) { ls += d * d; dl = 2.f * d; }                 // F.mse_loss (neural_network.py:241)
-        else { const float ad = fabsf(d); ls += ad < 1.f ? 0.5f * d * d : ad - 0.5f; dl = fminf(1.f, fmaxf(-1.f, d)); }
-        const float dz2 = dl * inv_n * (1.f - qv * qv);                    // through tanh
-        gb += dz2;
+    const long long n_pad = ((n + 127) >> 7) << 7;
+    for (long long b = (long long)blockIdx.x * 8 + warp; b < n_pad; b += (long long)gridDim.x * 8) {
+        uint4 packed = make_uint4(0, 0, 0, 0);
+        if (b < n) {
+            const float qv = q[b];
+            const float y = reward[b] + (1.f - done[b]) * gamma * qn[b];      // neural_network.py:238
+            const float d = qv - y;
+            float dl;                                                          // d loss / d q
+            if (loss_kind == 0) { ls += d * d; dl = 2.f * d; }                 // F.mse_loss (neural_network.py:241)
+            else { const float ad = fabsf(d); ls += ad < 1.f ? 0.5f * d * d : ad - 0.5f; dl = fminf(1.f, fmaxf(-1.f, d)); }
+            const float dz2 = dl * inv_n * (1.f - qv * qv);                    // through tanh
+            gb += dz2;
+            const float4 h0 = *reinterpret_cast<const float4*>(hidden + b * 256 + lane * 8);
+            const float4 h1 = *reinterpret_cast<const float4*>(hidden + b * 256 + lane * 8 + 4);
+            const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float dz[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int j = lane + 32 * i;
-            const float h = hidden[b * 256 + j];
-            gw[i] = fmaf(dz2, h, gw[i]);
-            dz1[b * 256 + j] = h > 0.f ? dz2 * w2[i] : 0.f;                // through fc2 and ReLU
+            for (int i = 0; i < 8; i++) {
+                gw[i] = fmaf(dz2, h[i], gw[i]);
+                dz[i] = h[i] > 0.f ? dz2 * w2[i] : 0.f;                        // through fc2 and ReLU
+                gb1[i] += dz[i];
+            }
+            __half2 p0 = __floats2half2_rn(dz[0] * scale, dz[1] * scale), p1 = __floats2half2_rn(dz[2] * scale, dz[3] * scale);
+            __half2 p2 = __floats2half2_rn(dz[4] * scale, dz[5] * scale), p3 = __floats2half2_rn(dz[6] * scale, dz[7] * scale);
+            packed = make_uint4(*reinterpret_cast<unsigned*>(&p0), *reinterpret_cast<unsigned*>(&p1),
+                                *reinterpret_cast<unsigned*>(&p2), *reinterpret_cast<unsigned*>(&p3));
         }
+        const int pr = (int)(b & 127);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dz1h) + (b >> 7) * 65536 + lane * 2048 + (pr >> 3) * 128 + (pr & 7) * 16) = packed;
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++) s_gw[warp][lane + 32 * i] = gw[i];
+    for (int i = 0; i < 8; i++) { s_gw[warp][lane * 8 + i] = gw[i]; s_gb1[warp][lane * 8 + i] = gb1[i]; }
     if (lane == 0) { s_misc[warp][0] = gb; s_misc[warp][1] = ls; }        // identical in all lanes
     __syncthreads();
-    float t = 0.f;
+    float t = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; w++) t += s_gw[w][threadIdx.x];
+    for (int w = 0; w < 8; w++) { t += s_gw[w][threadIdx.x]; t1 += s_gb1[w][threadIdx.x]; }
     atomicAdd(g_fc2_w + threadIdx.x, t);
+    atomicAdd(g_fc1_b + threadIdx.x, t1);
     if (threadIdx.x == 0) {
         float b0 = 0.f, l0 = 0.f;
         for (int w = 0; w < 8; w++) { b0 += s_misc[w][0]; l0 += s_misc[w][1]; }
@@ -265,7 +272,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
-    __half* act2_tiles; __half* act1; __half* a2; float* hidden; float* q; float* qn; float* dz1; float* dz2c;
+    __half* act2_tiles; __half* act1; __half* dz1h; float* hidden; float* q; float* qn; float* dz2c;
     __half* col1; float* dcol1; float* dz1c; __half* col0;
     size_t total;
 };
@@ -276,11 +283,10 @@ static TrainWs carve(void* base, long long n) {
     const long long tiles = (n + 127) / 128;
     w.act2_tiles = (__half*)take((size_t)tiles << 20);
     w.act1 = (__half*)take((size_t)n * 64 * 32 * 2);
-    w.a2 = (__half*)take((size_t)n * 4096 * 2);
+    w.dz1h = (__half*)take((size_t)tiles << 16);
     w.hidden = (float*)take((size_t)n * 256 * 4);
     w.q = (float*)take((size_t)n * 4);
     w.qn = (float*)take((size_t)n * 4);
-    w.dz1 = (float*)take((size_t)n * 256 * 4);
     w.dz2c = (float*)take((size_t)n * 4096 * 4);
     w.col1 = (__half*)take((size_t)n * 64 * 288 * 2);
     w.dcol1 = (float*)take((size_t)n * 64 * 288 * 4);
@@ -302,30 +308,19 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     if ((e = launch_fc_head(ws.act2_tiles, n, target->p, ws.qn, nullptr, nullptr, nullptr, st))) return e;
     if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, ws.act1, st))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
+    // ---- loss, tanh, fc2, fc1 bias; then fc1 weight and data gradients on tcgen05 (fc_bwd_kernel.cu)
+    const float scale = 64.f * (float)n;      // power-of-two-ish lift into fp16's normal range; undone in the epilogues
     {
         ProfileScope ps(KK_TRAIN, st);
-        untile_act2_kernel<<<(unsigned)((n * 512 + 255) / 256), 256, 0, st>>>(ws.act2_tiles, n, ws.a2);
+        const long long n_pad = ((n + 127) >> 7) << 7;
+        const unsigned blocks = (unsigned)(n_pad / 8 < 1184 ? n_pad / 8 : 1184);
+        head_bwd_kernel<<<blocks, 256, 0, st>>>(ws.q, ws.qn, reward, done, ws.hidden, w.fc2_w, n, gamma, loss_kind, scale, ws.dz1h,
+                                                (float*)g.fc2_w, (float*)g.fc2_b, (float*)g.fc1_b, loss);
         count_launch();
     }
-    // ---- loss, tanh, fc2
-    {
-        ProfileScope ps(KK_TRAIN, st);
-        const unsigned blocks = (unsigned)((n + 7) / 8 < 1184 ? (n + 7) / 8 : 1184);
-        head_bwd_kernel<<<blocks, 256, 0, st>>>(ws.q, ws.qn, reward, done, ws.hidden, w.fc2_w, n, gamma, loss_kind, ws.dz1,
-                                                (float*)g.fc2_w, (float*)g.fc2_b, loss);
-        count_launch();
-    }
-    GemmAux aux{ws.a2};
-    // ---- fc1: weight gradient (contraction over the batch), bias gradient, data gradient
-    if ((e = run_gemm<float, __half, true, 128, 128, EPI_FC1_WGRAD>(ws.dz1, ws.a2, (float*)g.fc1_w, 256, 4096, n, 256, 4096, 4096,
-                                                                    n >= 2048 ? 4 : 1, aux, st))) return e;
-    {
-        ProfileScope ps(KK_TRAIN, st);
-        colsum_kernel<<<148, 256, 0, st>>>(ws.dz1, n, 256, (float*)g.fc1_b);
-        count_launch();
-    }
-    if ((e = run_gemm<float, float, false, 128, 128, EPI_FC1_DGRAD>(ws.dz1, w.fc1_w, ws.dz2c, (int)n, 4096, 256, 256, 4096, 4096, 1, aux, st)))
-        return e;
+    if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, st))) return e;
+    if ((e = launch_fc1_dgrad(ws.dz1h, ws.act2_tiles, net->p.fc1tp, n, 1.f / scale, ws.dz2c, st))) return e;
+    GemmAux aux{nullptr};
     // ---- conv2: bias, weight gradient over im2col(ReLU(conv1)), data gradient via col2im
     const long long rows = n * 64;
     const int ks = (int)(rows / 2048 < 1 ? 1 : (rows / 2048 > 512 ? 512 : rows / 2048));

@@ -101,6 +101,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with per-operand majorness: *_mn = true means the operand is MN-major (8 consecutive M/N
+// elements form the 16-byte vector, K advances by 16 bytes inside a 128-byte core matrix)
+__host__ __device__ constexpr uint32_t make_idesc_f16_ex(int M, int N, bool a_mn, bool b_mn) {
+    return make_idesc_f16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; single thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
     asm volatile(
