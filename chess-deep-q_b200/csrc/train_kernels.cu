@@ -201,29 +201,53 @@ __global__ void im2col_act1_kernel(const __half* __restrict__ a1, long long n, _
     *reinterpret_cast<uint4*>(col + (b * 64 + sq) * 288 + tap * 32 + qd * 8) = v;
 }
 
-// im2col of the one-hot planes: col0[(b,sq)][tap*16 + p] (fp16)
-__global__ void im2col_planes_kernel(const CdqBoard* __restrict__ boards, long long n, __half* __restrict__ col) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, sq, tap)
-    if (i >= n * 64 * 9) return;
-    const int tap = (int)(i % 9), sq = (int)((i / 9) & 63);
-    const long long b = i / (9 * 64);
-    const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
-    unsigned long long lo = 0, hi = 0, lo1 = 0;
-    if (y >= 0 && y < 8 && x >= 0 && x < 8) {
+// conv1 weight + bias gradient.  The input is one-hot, so the GEMM collapses to a scatter:
+// dW1[co][p][tap] += dz1c[b][sq][co] for the piece p standing on square sq+tap.  One warp per board
+// (lane = output channel), per-warp accumulators [9 taps][12 pieces][32] in shared memory (the
+// (tap, piece) index is warp-uniform, the lane is the bank: no conflicts, no atomics), one global
+// atomicAdd per accumulator cell per CTA at the end.
+constexpr int C1W_WARPS = 2;   // 2 x 13.6 KB of accumulators: under the 48 KB default
+__global__ void __launch_bounds__(C1W_WARPS * 32)
+conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
+                   float* __restrict__ g_w, float* __restrict__ g_b) {
+    extern __shared__ float acc_all[];                 // [warps][9*12 + 1][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* acc = acc_all + warp * (109 * 32);
+    for (int i = 0; i < 109; i++) acc[i * 32 + lane] = 0.f;
+    __syncwarp();
+    for (long long b = (long long)blockIdx.x * C1W_WARPS + warp; b < n; b += (long long)gridDim.x * C1W_WARPS) {
         const unsigned long long* r = reinterpret_cast<const unsigned long long*>(boards) + b * 9;
-        const int s = y * 8 + x;
-        int t = -1;
-        for (int k = 0; k < 6; k++) if ((r[k] >> s) & 1) t = k;
-        const bool isw = (r[6] >> s) & 1, isb = (r[7] >> s) & 1;
-        const int ch = (t >= 0 && (isw || isb)) ? (isw ? t : t + 6) : -1;
-        const unsigned long long one = 0x3C00ull;
-        if (ch >= 0 && ch < 4) lo = one << (16 * ch);
-        else if (ch >= 4 && ch < 8) hi = one << (16 * (ch - 4));
-        else if (ch >= 8) lo1 = one << (16 * (ch - 8));
+        // lanes 0..31 and a second pass: piece code of every square (12 = empty)
+        unsigned long long bb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) bb[k] = __ldg(r + k);
+        float bias = 0.f;
+        for (int sq = 0; sq < 64; sq++) {
+            const float gval = dz1c[(b * 64 + sq) * 32 + lane];
+            bias += gval;
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+                const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
+                if (y < 0 || y > 7 || x < 0 || x > 7) continue;          // warp-uniform
+                const int s = y * 8 + x;
+                int t = -1;
+#pragma unroll
+                for (int k = 0; k < 6; k++) if ((bb[k] >> s) & 1) t = k;
+                if (t < 0) continue;                                      // empty square (warp-uniform)
+                const int p = ((bb[6] >> s) & 1) ? t : t + 6;
+                acc[(tap * 12 + p) * 32 + lane] += gval;
+            }
+        }
+        acc[108 * 32 + lane] += bias;
     }
-    uint4* o = reinterpret_cast<uint4*>(col + (b * 64 + sq) * 144 + tap * 16);
-    o[0] = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
-    o[1] = make_uint4((unsigned)lo1, (unsigned)(lo1 >> 32), 0u, 0u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 109 * 32; i += C1W_WARPS * 32) {
+        float v = 0.f;
+        for (int w = 0; w < C1W_WARPS; w++) v += acc_all[w * (109 * 32) + i];
+        const int cell = i >> 5, co = i & 31;
+        if (cell == 108) atomicAdd(g_b + co, v);
+        else atomicAdd(g_w + co * 108 + (cell % 12) * 9 + cell / 12, v);   // conv1.weight[co][p][tap]
+    }
 }
 
 // col2im + ReLU mask: dz1c[b][sq][ci] = a1 > 0 ? sum_tap dcol[b][sq - tap][ci*9 + tap] : 0
@@ -273,7 +297,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
     __half* act2_tiles; __half* act1; __half* dz1h; float* hidden; float* q; float* qn; float* dz2c;
-    __half* col1; float* dcol1; float* dz1c; __half* col0;
+    __half* col1; float* dcol1; float* dz1c;
     size_t total;
 };
 static TrainWs carve(void* base, long long n) {
@@ -291,7 +315,6 @@ static TrainWs carve(void* base, long long n) {
     w.col1 = (__half*)take((size_t)n * 64 * 288 * 2);
     w.dcol1 = (float*)take((size_t)n * 64 * 288 * 4);
     w.dz1c = (float*)take((size_t)n * 64 * 32 * 4);
-    w.col0 = (__half*)take((size_t)n * 64 * 144 * 2);
     w.total = off;
     return w;
 }
@@ -337,13 +360,11 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     {
         ProfileScope ps(KK_TRAIN, st);
         fold_conv2_dgrad_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(ws.dcol1, ws.act1, n, ws.dz1c);
-        colsum_kernel<<<296, 256, 0, st>>>(ws.dz1c, rows, 32, (float*)g.conv1_b);
-        im2col_planes_kernel<<<(unsigned)((rows * 9 + 255) / 256), 256, 0, st>>>(states, n, ws.col0);
-        count_launch(3);
+        // ---- conv1: weight + bias gradient by scatter over the one-hot input
+        const unsigned blocks = (unsigned)((n + C1W_WARPS - 1) / C1W_WARPS < 1184 ? (n + C1W_WARPS - 1) / C1W_WARPS : 1184);
+        conv1_wgrad_kernel<<<blocks, C1W_WARPS * 32, C1W_WARPS * 109 * 32 * 4, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
+        count_launch(2);
     }
-    // ---- conv1: weight gradient over im2col(one-hot planes)
-    if ((e = run_gemm<float, __half, true, 64, 128, EPI_CONV1_WGRAD>(ws.dz1c, ws.col0, (float*)g.conv1_w, 32, 144, rows, 32, 144, 108, ks, aux, st)))
-        return e;
     return (int)cudaGetLastError();
 }
 
