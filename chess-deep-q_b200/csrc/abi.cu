@@ -115,7 +115,7 @@ int cdq_net_create(CdqNet** out) {
     if (!out) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
     CdqNet* net = new CdqNet();
-    const size_t halfs = W1P_HALFS + W2P_HALFS + 2 * FC1P_HALFS;
+    const size_t halfs = W1P_HALFS + 2 * W2P_HALFS + 2 * FC1P_HALFS;
     const size_t bytes = halfs * 2 + (64 + 256 + 256 + 4) * 4;
     cudaError_t e = cudaMalloc(&net->blob, bytes);
     if (e != cudaSuccess) { delete net; return (int)e; }
@@ -125,6 +125,7 @@ int cdq_net_create(CdqNet** out) {
     net->p.w2p = h + W1P_HALFS;
     net->p.fc1p = h + W1P_HALFS + W2P_HALFS;
     net->p.fc1tp = h + W1P_HALFS + W2P_HALFS + FC1P_HALFS;
+    net->p.w2tp = h + W1P_HALFS + W2P_HALFS + 2 * FC1P_HALFS;
     net->p.conv2_b = f;
     net->p.fc1_b = f + 64;
     net->p.fc2_w = f + 64 + 256;
@@ -139,7 +140,7 @@ int cdq_net_load(CdqNet* net, const CdqWeights* w, void* stream) {
         !w->fc2_w || !w->fc2_b)
         return CDQ_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int e = launch_pack_weights(*w, (__half*)net->p.w1p, (__half*)net->p.w2p, (__half*)net->p.fc1p, (__half*)net->p.fc1tp, st)) return e;
+    if (int e = launch_pack_weights(*w, (__half*)net->p.w1p, (__half*)net->p.w2p, (__half*)net->p.fc1p, (__half*)net->p.fc1tp, (__half*)net->p.w2tp, st)) return e;
     CDQ_CUDA(cudaMemcpyAsync((void*)net->p.conv2_b, w->conv2_b, 64 * 4, cudaMemcpyDeviceToDevice, st));
     CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc1_b, w->fc1_b, 256 * 4, cudaMemcpyDeviceToDevice, st));
     CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc2_w, w->fc2_w, 256 * 4, cudaMemcpyDeviceToDevice, st));

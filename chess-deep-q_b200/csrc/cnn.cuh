@@ -11,6 +11,7 @@ struct PackedNet {
     const __half* w1p;   // conv1: [9 taps][2 chunks][4 groups][8 n][8 k]  (k 12 = bias, centre tap)
     const __half* w2p;   // conv2: [9 taps][4 chunks][8 groups][8 n][8 k]
     const __half* fc1p;  // fc1:   [64 squares][8 chunks][32 groups][8 n][8 k]
+    const __half* w2tp;  // conv2 flipped for the data gradient: [9 taps][8 chunks of co][4 groups][8 ci][8 co]
     const __half* fc1tp; // fc1^T: [16 column chunks][4 K stages][8 chunks][32 groups][8 n][8 j]  (data gradient)
     const float* conv2_b;
     const float* fc1_b;
@@ -19,12 +20,15 @@ struct PackedNet {
 };
 
 int device_sm_count();
-int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, cudaStream_t st);
-int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, float inv_scale,
-                     float* dz2, cudaStream_t st);
+int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
+                        cudaStream_t st);
+int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, __half* dz2_boards,
+                     cudaStream_t st);
+int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
+                     float* g_w2, float* g_b2, float* dz1c, cudaStream_t st);
 int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float inv_scale, float* g_fc1_w, cudaStream_t st);
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
-                      cudaStream_t st);
+                      cudaStream_t st, __half* act1_boards = nullptr);
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
                    float* leaf, float* hidden, cudaStream_t st);
 

@@ -65,7 +65,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const PackedNet net,
-                  __half* __restrict__ act2, __half* __restrict__ dbg_act1) {
+                  __half* __restrict__ act2, __half* __restrict__ dbg_act1, __half* __restrict__ act1_boards) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -253,6 +253,9 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
                     o.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]), __uint_as_float(v[kc * 8 + 5]));
                     o.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]), __uint_as_float(v[kc * 8 + 7]));
                     *reinterpret_cast<uint4*>(dst + kc * CHUNK_BYTES) = o;
+                    if (act1_boards)   // training: keep ReLU(conv1) as boards (same offsets as in shared memory)
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 3) * ACT1_BYTES +
+                                                  (dst - (smem + OFF_ACT1 + buf * ACT1_BYTES)) + kc * CHUNK_BYTES) = o;
                     if (dbg_act1 && pos < n)
                         *reinterpret_cast<uint4*>(dbg_act1 + (pos * 64 + y * 8 + r_x) * 32 + kc * 8) = o;
                 }
@@ -314,7 +317,7 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
 }
 
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
-                      cudaStream_t st) {
+                      cudaStream_t st, __half* act1_boards) {
     if (n == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -325,7 +328,7 @@ int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net,
     const int sms = device_sm_count();
     const unsigned grid = (unsigned)(groups < sms ? groups : sms);
     ProfileScope ps(KK_CONV, st);
-    conv_stack_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(boards, n, net, act2, dbg_act1);
+    conv_stack_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(boards, n, net, act2, dbg_act1, act1_boards);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -8,7 +8,8 @@
 // act2: the forward's fc1 A tiles; read MN-major (N = channels of a square, K = positions) they are
 //       the B operand of the weight gradient (tests/cuda/umma_mn_probe.cu checks the encoding).
 //
-//  fc1_dgrad_kernel   dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq]
+//  fc1_dgrad_kernel   dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq], written (still
+//                     scaled, fp16) straight into the zero-bordered boards conv_bwd_kernel.cu consumes
 //                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
 //                     M = 2 x 128 outputs, N = 128 (2 squares), K = positions (split over CTAs)
@@ -29,7 +30,7 @@ constexpr int DG_THREADS = 192;
 
 __global__ void __launch_bounds__(DG_THREADS, 1)
 fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act2, const __half* __restrict__ fc1tp,
-                 long long n, float inv_scale, float* __restrict__ dz2) {
+                 long long n, __half* __restrict__ dz2_boards) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + DG_OFF_BAR);   // [4]
     uint64_t* empty = full + DG_STAGES;                                // [4]
@@ -119,19 +120,23 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                     if (pos < n) {
                         const uint8_t* mrow = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + sq) << 14) +
                                               (ch0 >> 3) * 2048 + (pr >> 3) * 128 + (pr & 7) * 16;
-                        float4* o = reinterpret_cast<float4*>(dz2 + pos * 4096 + sq * 64 + ch0);
+                        // conv2-backward board of this position's group: [8 chunks][10 ranks][8 pos][10 files][8 halfs]
+                        uint8_t* o = reinterpret_cast<uint8_t*>(dz2_boards) + (pos >> 3) * 102400 + (ch0 >> 3) * 12800 +
+                                     (((sq >> 3) + 1) * 8 + (int)(pos & 7)) * 160 + ((sq & 7) + 1) * 16;
 #pragma unroll
                         for (int g = 0; g < 4; g++) {
                             const uint4 m = *reinterpret_cast<const uint4*>(mrow + g * 2048);
                             const unsigned mw[4] = {m.x, m.y, m.z, m.w};
-                            float r[8];
+                            unsigned w[4];
 #pragma unroll
-                            for (int e = 0; e < 8; e++) {
-                                const unsigned hbits = (mw[e >> 1] >> (16 * (e & 1))) & 0xffffu;   // ReLU output: > 0 iff bits != 0
-                                r[e] = hbits ? __uint_as_float(v[g * 8 + e]) * inv_scale : 0.f;
+                            for (int e = 0; e < 4; e++) {
+                                // ReLU output > 0 iff its fp16 bits != 0; the value stays scaled (undone downstream)
+                                const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[g * 8 + 2 * e]) : 0.f;
+                                const float hi = (mw[e] >> 16) ? __uint_as_float(v[g * 8 + 2 * e + 1]) : 0.f;
+                                __half2 h2 = __floats2half2_rn(lo, hi);
+                                w[e] = *reinterpret_cast<unsigned*>(&h2);
                             }
-                            o[2 * g] = make_float4(r[0], r[1], r[2], r[3]);
-                            o[2 * g + 1] = make_float4(r[4], r[5], r[6], r[7]);
+                            *reinterpret_cast<uint4*>(o + g * 12800) = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
                 }
@@ -230,8 +235,8 @@ fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, float inv_scale,
-                     float* dz2, cudaStream_t st) {
+int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, __half* dz2_boards,
+                     cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(fc1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
@@ -241,7 +246,7 @@ int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp
     const long long items = ((n + 127) >> 7) * 4;
     const int sms = device_sm_count();
     ProfileScope ps(KK_TRAIN, st);
-    fc1_dgrad_kernel<<<(unsigned)(items < sms ? items : sms), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, inv_scale, dz2);
+    fc1_dgrad_kernel<<<(unsigned)(items < sms ? items : sms), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, dz2_boards);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -143,7 +143,7 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
 
 // ------------------------------------------------------------------------------------------
 // weight repacking: fp32 PyTorch layouts -> fp16 UMMA K-major no-swizzle tiles
-__global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp) {
+__global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N1 = 9 * 32 * 16, N2 = 9 * 64 * 32, N3 = 64ll * 256 * 64;
     if (i < N1) {
@@ -172,13 +172,20 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
         const int j8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 31, kc = (j >> 11) & 7, sg = (j >> 14) & 3, ck = (int)(j >> 16);
         const int np = ck * 256 + ng * 8 + n8, sq = np >> 6, ch = np & 63, jo = sg * 64 + kc * 8 + j8;
         fc1tp[j] = __float2half_rn(w.fc1_w[(long long)jo * 4096 + ch * 64 + sq]);
+    } else if (i < N1 + 2 * N2 + 2 * N3) {
+        // w2tp[u 9][kc 8 (co)][ng 4 (ci)][ci8][co8] = conv2.weight[co][ci][8 - u]   (flipped taps)
+        const long long j = i - N1 - N2 - 2 * N3;
+        const int co8 = j & 7, ci8 = (j >> 3) & 7, ng = (j >> 6) & 3, kc = (j >> 8) & 7, u = (int)(j >> 11);
+        const int co = kc * 8 + co8, ci = ng * 8 + ci8;
+        w2tp[j] = __float2half_rn(w.conv2_w[(co * 32 + ci) * 9 + (8 - u)]);
     }
 }
 
-int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, cudaStream_t st) {
-    const long long total = 9 * 32 * 16 + 9 * 64 * 32 + 2 * 64ll * 256 * 64;
+int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
+                        cudaStream_t st) {
+    const long long total = 9 * 32 * 16 + 2 * 9 * 64 * 32 + 2 * 64ll * 256 * 64;
     ProfileScope ps(KK_PACK, st);
-    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, w1p, w2p, fc1p, fc1tp);
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, w1p, w2p, fc1p, fc1tp, w2tp);
     count_launch();
     return (int)cudaGetLastError();
 }

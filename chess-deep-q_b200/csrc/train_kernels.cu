@@ -5,113 +5,17 @@
 //   loss = mean((q - y)^2)  (or Huber)        (neural_network.py:241)
 //   backward through tanh, fc2, fc1, conv2, conv1; Adam (neural_network.py:65,244-246)
 //
-// Round-1 state of the backward pass: correct and all on the device, but the GEMMs still run on a
-// shared-memory-tiled fp32 SIMT kernel (gemm_kernel below) over im2col buffers; moving them to
-// tcgen05 with the board-in-shared-memory operands of conv_kernel.cu is the next step.
-// Layout conventions: activations are NHWC-like, [position][square][channel]; weight gradients are
-// written in PyTorch order (the epilogues permute).
+// Every GEMM-shaped piece runs on tcgen05: the forward (conv_kernel.cu, fc_kernel.cu), fc1's data and
+// weight gradients (fc_bwd_kernel.cu) and conv2's data/weight/bias gradients (conv_bwd_kernel.cu).
+// This file holds the glue: the loss/tanh/fc2 head, conv1's weight gradient (a scatter, because its
+// input is one-hot), Adam, and the workspace carve-up.  Gradients flow between kernels as fp16
+// scaled by 64*n (a power of two for the usual batch sizes) and are unscaled in fp32 epilogues;
+// weight gradients are accumulated in PyTorch layout with atomicAdd.
 #include "common.cuh"
 #include "cnn.cuh"
 #include <cmath>
 
 namespace cdq {
-
-// ------------------------------------------------------------------------------------------
-// C[M][N] (+)= A x B with fp32 accumulation.  A is stored [K][M] (A_KM) or [M][K]; B is [K][N].
-// blockIdx.z splits K (results combined with atomicAdd when the epilogue allows it).
-enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_FC1_DGRAD = 2, EPI_FC1_WGRAD = 3, EPI_CONV2_WGRAD = 4, EPI_CONV1_WGRAD = 5 };
-
-struct GemmAux {
-    const __half* mask;   // EPI_FC1_DGRAD: ReLU(conv2) in [position][square][channel] order
-};
-
-__device__ __forceinline__ float to_f(float x) { return x; }
-__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
-
-template <typename TA, typename TB, bool A_KM, int BM, int BN, int EPI>
-__global__ void __launch_bounds__(256)
-gemm_kernel(const TA* __restrict__ A, const TB* __restrict__ B, float* __restrict__ C, int M, int N, long long K,
-            long long lda, long long ldb, long long ldc, long long k_chunk, GemmAux aux) {
-    constexpr int BK = 16, TM = BM / 16, TN = BN / 16;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const long long k_begin = (long long)blockIdx.z * k_chunk;
-    const long long k_end = k_begin + k_chunk < K ? k_begin + k_chunk : K;
-    float acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; i++)
-#pragma unroll
-        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
-
-    for (long long k0 = k_begin; k0 < k_end; k0 += BK) {
-        for (int idx = tid; idx < BK * BM; idx += 256) {
-            int k, m;
-            if (A_KM) { k = idx / BM; m = idx % BM; } else { m = idx / BK; k = idx % BK; }
-            float v = 0.f;
-            if (m0 + m < M && k0 + k < k_end)
-                v = to_f(A_KM ? A[(k0 + k) * lda + m0 + m] : A[(long long)(m0 + m) * lda + k0 + k]);
-            As[k][m] = v;
-        }
-        for (int idx = tid; idx < BK * BN; idx += 256) {
-            const int k = idx / BN, nn = idx % BN;
-            float v = 0.f;
-            if (n0 + nn < N && k0 + k < k_end) v = to_f(B[(k0 + k) * ldb + n0 + nn]);
-            Bs[k][nn] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < BK; k++) {
-            float a[TM], b[TN];
-#pragma unroll
-            for (int i = 0; i < TM; i++) a[i] = As[k][ty + 16 * i];
-#pragma unroll
-            for (int j = 0; j < TN; j++) b[j] = Bs[k][tx + 16 * j];
-#pragma unroll
-            for (int i = 0; i < TM; i++)
-#pragma unroll
-                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < TM; i++)
-#pragma unroll
-        for (int j = 0; j < TN; j++) {
-            const int m = m0 + ty + 16 * i, nn = n0 + tx + 16 * j;
-            if (m >= M || nn >= N) continue;
-            const float v = acc[i][j];
-            if (EPI == EPI_STORE) C[(long long)m * ldc + nn] = v;
-            else if (EPI == EPI_ATOMIC) atomicAdd(C + (long long)m * ldc + nn, v);
-            else if (EPI == EPI_FC1_DGRAD) {
-                // nn = c*64 + sq (reference column order) -> [position][sq][c]; ReLU mask of conv2's output
-                const long long o = (long long)m * 4096 + (nn & 63) * 64 + (nn >> 6);
-                C[o] = __half2float(aux.mask[o]) > 0.f ? v : 0.f;
-            } else if (EPI == EPI_FC1_WGRAD) {
-                // nn = sq*64 + c -> fc1.weight[m][c*64 + sq]
-                atomicAdd(C + (long long)m * 4096 + (nn & 63) * 64 + (nn >> 6), v);
-            } else if (EPI == EPI_CONV2_WGRAD) {
-                // nn = tap*32 + ci -> conv2.weight[m][ci][tap]
-                atomicAdd(C + (long long)m * 288 + (nn & 31) * 9 + (nn >> 5), v);
-            } else if (EPI == EPI_CONV1_WGRAD) {
-                // nn = tap*16 + p (p < 12) -> conv1.weight[m][p][tap]
-                if ((nn & 15) < 12) atomicAdd(C + (long long)m * 108 + (nn & 15) * 9 + (nn >> 4), v);
-            }
-        }
-}
-
-template <typename TA, typename TB, bool A_KM, int BM, int BN, int EPI>
-static int run_gemm(const TA* A, const TB* B, float* C, int M, int N, long long K, long long lda, long long ldb,
-                    long long ldc, int k_splits, GemmAux aux, cudaStream_t st) {
-    long long k_chunk = (K + k_splits - 1) / k_splits;
-    k_chunk = (k_chunk + 15) / 16 * 16;
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, (unsigned)((K + k_chunk - 1) / k_chunk));
-    ProfileScope ps(KK_TRAIN, st);
-    gemm_kernel<TA, TB, A_KM, BM, BN, EPI><<<grid, 256, 0, st>>>(A, B, C, M, N, K, lda, ldb, ldc, k_chunk, aux);
-    count_launch();
-    return (int)cudaGetLastError();
-}
 
 // ------------------------------------------------------------------------------------------
 // loss + backward through tanh, fc2 and fc1's ReLU; one warp per position (grid-stride).  Writes
@@ -179,28 +83,6 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
     }
 }
 
-// column sums of a [rows][cols] fp32 matrix (bias gradients), cols <= 256
-__global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* __restrict__ out) {
-    const int c = threadIdx.x % cols, sub = threadIdx.x / cols, nsub = 256 / cols;
-    if (sub >= nsub) return;
-    float s = 0.f;
-    for (long long r = (long long)blockIdx.x * nsub + sub; r < rows; r += (long long)gridDim.x * nsub) s += x[r * cols + c];
-    atomicAdd(out + c, s);
-}
-
-// im2col of ReLU(conv1): col1[(b,sq)][tap*32 + ci] = a1[b][sq + tap][ci]  (fp16, zero outside)
-__global__ void im2col_act1_kernel(const __half* __restrict__ a1, long long n, __half* __restrict__ col) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, sq, tap, quarter)
-    if (i >= n * 64 * 9 * 4) return;
-    const int qd = (int)(i & 3), tap = (int)((i >> 2) % 9), sq = (int)((i / 36) & 63);
-    const long long b = i / (36 * 64);
-    const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < 8 && x >= 0 && x < 8) v = *reinterpret_cast<const uint4*>(a1 + (b * 64 + y * 8 + x) * 32 + qd * 8);
-    *reinterpret_cast<uint4*>(col + (b * 64 + sq) * 288 + tap * 32 + qd * 8) = v;
-}
-
 // conv1 weight + bias gradient.  The input is one-hot, so the GEMM collapses to a scatter:
 // dW1[co][p][tap] += dz1c[b][sq][co] for the piece p standing on square sq+tap.  One warp per board
 // (lane = output channel), per-warp accumulators [9 taps][12 pieces][32] in shared memory (the
@@ -250,24 +132,6 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
     }
 }
 
-// col2im + ReLU mask: dz1c[b][sq][ci] = a1 > 0 ? sum_tap dcol[b][sq - tap][ci*9 + tap] : 0
-__global__ void fold_conv2_dgrad_kernel(const float* __restrict__ dcol, const __half* __restrict__ a1, long long n,
-                                        float* __restrict__ dz) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, sq, ci)
-    if (i >= n * 64 * 32) return;
-    const int ci = (int)(i & 31), sq = (int)((i >> 5) & 63);
-    const long long b = i >> 11;
-    float s = 0.f;
-    if (__half2float(a1[i]) > 0.f) {
-#pragma unroll
-        for (int tap = 0; tap < 9; tap++) {
-            const int y = (sq >> 3) - (tap / 3 - 1), x = (sq & 7) - (tap % 3 - 1);   // output square that read us
-            if (y >= 0 && y < 8 && x >= 0 && x < 8) s += dcol[(b * 64 + y * 8 + x) * 288 + ci * 9 + tap];
-        }
-    }
-    dz[i] = s;
-}
-
 // Adam (torch.optim.Adam defaults: no weight decay, no amsgrad); grads are pre-multiplied by grad_scale
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
@@ -296,24 +160,24 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
-    __half* act2_tiles; __half* act1; __half* dz1h; float* hidden; float* q; float* qn; float* dz2c;
-    __half* col1; float* dcol1; float* dz1c;
+    __half* act2_tiles; __half* dz1h; __half* a1_boards; __half* dz2_boards; float* hidden; float* q; float* qn; float* dz1c;
+    size_t zero_from, zero_bytes;   // [a1_boards, dz2_boards]: borders must be zero, cleared every step
     size_t total;
 };
 static TrainWs carve(void* base, long long n) {
     TrainWs w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base ? (uint8_t*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
-    const long long tiles = (n + 127) / 128;
+    const long long tiles = (n + 127) / 128, groups = tiles * 16;
     w.act2_tiles = (__half*)take((size_t)tiles << 20);
-    w.act1 = (__half*)take((size_t)n * 64 * 32 * 2);
     w.dz1h = (__half*)take((size_t)tiles << 16);
+    w.zero_from = off;
+    w.a1_boards = (__half*)take((size_t)groups * 51200);
+    w.dz2_boards = (__half*)take((size_t)groups * 102400);
+    w.zero_bytes = off - w.zero_from;
     w.hidden = (float*)take((size_t)n * 256 * 4);
     w.q = (float*)take((size_t)n * 4);
     w.qn = (float*)take((size_t)n * 4);
-    w.dz2c = (float*)take((size_t)n * 4096 * 4);
-    w.col1 = (__half*)take((size_t)n * 64 * 288 * 2);
-    w.dcol1 = (float*)take((size_t)n * 64 * 288 * 4);
     w.dz1c = (float*)take((size_t)n * 64 * 32 * 4);
     w.total = off;
     return w;
@@ -326,13 +190,14 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
                   cudaStream_t st) {
     TrainWs ws = carve(ws_base, n);
     int e;
+    CDQ_CUDA(cudaMemsetAsync((uint8_t*)ws_base + ws.zero_from, 0, ws.zero_bytes, st));
     // ---- forward: target value of next_states (inference), then q of states keeping activations
     if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_tiles, nullptr, st))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, target->p, ws.qn, nullptr, nullptr, nullptr, st))) return e;
-    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, ws.act1, st))) return e;
+    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
-    // ---- loss, tanh, fc2, fc1 bias; then fc1 weight and data gradients on tcgen05 (fc_bwd_kernel.cu)
-    const float scale = 64.f * (float)n;      // power-of-two-ish lift into fp16's normal range; undone in the epilogues
+    // ---- loss, tanh, fc2, fc1 bias
+    const float scale = 64.f * (float)n;      // lift into fp16's normal range; undone in the fp32 epilogues
     {
         ProfileScope ps(KK_TRAIN, st);
         const long long n_pad = ((n + 127) >> 7) << 7;
@@ -341,29 +206,17 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
                                                 (float*)g.fc2_w, (float*)g.fc2_b, (float*)g.fc1_b, loss);
         count_launch();
     }
+    // ---- fc1 weight and data gradients, conv2 weight/bias/data gradients: tcgen05
     if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, st))) return e;
-    if ((e = launch_fc1_dgrad(ws.dz1h, ws.act2_tiles, net->p.fc1tp, n, 1.f / scale, ws.dz2c, st))) return e;
-    GemmAux aux{nullptr};
-    // ---- conv2: bias, weight gradient over im2col(ReLU(conv1)), data gradient via col2im
-    const long long rows = n * 64;
-    const int ks = (int)(rows / 2048 < 1 ? 1 : (rows / 2048 > 512 ? 512 : rows / 2048));
+    if ((e = launch_fc1_dgrad(ws.dz1h, ws.act2_tiles, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
+    if ((e = launch_conv2_bwd(ws.dz2_boards, ws.a1_boards, net->p.w2tp, n, 1.f / scale, (float*)g.conv2_w, (float*)g.conv2_b,
+                              ws.dz1c, st))) return e;
     {
-        ProfileScope ps(KK_TRAIN, st);
-        colsum_kernel<<<296, 256, 0, st>>>(ws.dz2c, rows, 64, (float*)g.conv2_b);
-        im2col_act1_kernel<<<(unsigned)((rows * 36 + 255) / 256), 256, 0, st>>>(ws.act1, n, ws.col1);
-        count_launch(2);
-    }
-    if ((e = run_gemm<float, __half, true, 64, 128, EPI_CONV2_WGRAD>(ws.dz2c, ws.col1, (float*)g.conv2_w, 64, 288, rows, 64, 288, 288, ks, aux, st)))
-        return e;
-    if ((e = run_gemm<float, float, false, 128, 128, EPI_STORE>(ws.dz2c, w.conv2_w, ws.dcol1, (int)rows, 288, 64, 64, 288, 288, 1, aux, st)))
-        return e;
-    {
-        ProfileScope ps(KK_TRAIN, st);
-        fold_conv2_dgrad_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(ws.dcol1, ws.act1, n, ws.dz1c);
         // ---- conv1: weight + bias gradient by scatter over the one-hot input
+        ProfileScope ps(KK_TRAIN, st);
         const unsigned blocks = (unsigned)((n + C1W_WARPS - 1) / C1W_WARPS < 1184 ? (n + C1W_WARPS - 1) / C1W_WARPS : 1184);
         conv1_wgrad_kernel<<<blocks, C1W_WARPS * 32, C1W_WARPS * 109 * 32 * 4, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
-        count_launch(2);
+        count_launch();
     }
     return (int)cudaGetLastError();
 }
