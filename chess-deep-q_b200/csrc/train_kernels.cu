@@ -88,39 +88,51 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
 // (lane = output channel), per-warp accumulators [9 taps][12 pieces][32] in shared memory (the
 // (tap, piece) index is warp-uniform, the lane is the bank: no conflicts, no atomics), one global
 // atomicAdd per accumulator cell per CTA at the end.
-constexpr int C1W_WARPS = 2;   // 2 x 13.6 KB of accumulators: under the 48 KB default
+constexpr int C1W_WARPS = 4;
+constexpr int C1W_SMEM = C1W_WARPS * (109 * 32 * 4 + 64);
 __global__ void __launch_bounds__(C1W_WARPS * 32)
 conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
                    float* __restrict__ g_w, float* __restrict__ g_b) {
-    extern __shared__ float acc_all[];                 // [warps][9*12 + 1][32]
+    extern __shared__ float acc_all[];                 // [warps][9*12 + 1][32] floats, then [warps][64] piece codes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* acc = acc_all + warp * (109 * 32);
+    unsigned char* codes = reinterpret_cast<unsigned char*>(acc_all + C1W_WARPS * 109 * 32) + warp * 64;
     for (int i = 0; i < 109; i++) acc[i * 32 + lane] = 0.f;
     __syncwarp();
     for (long long b = (long long)blockIdx.x * C1W_WARPS + warp; b < n; b += (long long)gridDim.x * C1W_WARPS) {
         const unsigned long long* r = reinterpret_cast<const unsigned long long*>(boards) + b * 9;
-        // lanes 0..31 and a second pass: piece code of every square (12 = empty)
-        unsigned long long bb[8];
+        // piece code (0..11, 12 = empty) of squares lane and lane + 32
 #pragma unroll
-        for (int k = 0; k < 8; k++) bb[k] = __ldg(r + k);
+        for (int h = 0; h < 2; h++) {
+            const int s = lane + 32 * h;
+            int t = -1;
+#pragma unroll
+            for (int k = 0; k < 6; k++) if ((__ldg(r + k) >> s) & 1) t = k;
+            const bool isw = (__ldg(r + 6) >> s) & 1, isb = (__ldg(r + 7) >> s) & 1;
+            codes[s] = (t >= 0 && (isw || isb)) ? (isw ? t : t + 6) : 12;
+        }
+        __syncwarp();
         float bias = 0.f;
-        for (int sq = 0; sq < 64; sq++) {
-            const float gval = dz1c[(b * 64 + sq) * 32 + lane];
-            bias += gval;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            float gv[16];
 #pragma unroll
-            for (int tap = 0; tap < 9; tap++) {
-                const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
-                if (y < 0 || y > 7 || x < 0 || x > 7) continue;          // warp-uniform
-                const int s = y * 8 + x;
-                int t = -1;
+            for (int i = 0; i < 16; i++) gv[i] = dz1c[(b * 64 + c * 16 + i) * 32 + lane];   // 16 loads in flight
 #pragma unroll
-                for (int k = 0; k < 6; k++) if ((bb[k] >> s) & 1) t = k;
-                if (t < 0) continue;                                      // empty square (warp-uniform)
-                const int p = ((bb[6] >> s) & 1) ? t : t + 6;
-                acc[(tap * 12 + p) * 32 + lane] += gval;
+            for (int i = 0; i < 16; i++) {
+                const int sq = c * 16 + i;
+                bias += gv[i];
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    const int y = (sq >> 3) + tap / 3 - 1, x = (sq & 7) + tap % 3 - 1;
+                    if (y < 0 || y > 7 || x < 0 || x > 7) continue;          // compile-time after unrolling
+                    const int p = codes[y * 8 + x];                            // warp-uniform
+                    if (p < 12) acc[(tap * 12 + p) * 32 + lane] += gv[i];
+                }
             }
         }
         acc[108 * 32 + lane] += bias;
+        __syncwarp();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 109 * 32; i += C1W_WARPS * 32) {
@@ -214,8 +226,13 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     {
         // ---- conv1: weight + bias gradient by scatter over the one-hot input
         ProfileScope ps(KK_TRAIN, st);
-        const unsigned blocks = (unsigned)((n + C1W_WARPS - 1) / C1W_WARPS < 1184 ? (n + C1W_WARPS - 1) / C1W_WARPS : 1184);
-        conv1_wgrad_kernel<<<blocks, C1W_WARPS * 32, C1W_WARPS * 109 * 32 * 4, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM);
+            attr_set = true;
+        }
+        const unsigned blocks = (unsigned)((n + C1W_WARPS - 1) / C1W_WARPS < 592 ? (n + C1W_WARPS - 1) / C1W_WARPS : 592);
+        conv1_wgrad_kernel<<<blocks, C1W_WARPS * 32, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
         count_launch();
     }
     return (int)cudaGetLastError();
