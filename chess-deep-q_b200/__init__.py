@@ -9,6 +9,7 @@ from . import _lib  # noqa: F401
 from .board_utils import BOARD_DTYPE, pack_board, pack_boards, board_to_tensor, boards_to_tensor_batch  # noqa: F401
 from .evaluation import fast_evaluate_position, evaluate_batch, PIECE_VALUES  # noqa: F401
 from .neural_network import ChessQNetwork, DQNAgent  # noqa: F401
-from .mcts import evaluate_position, evaluate_positions, LeafEvaluator  # noqa: F401
+from .mcts import (evaluate_position, evaluate_positions, LeafEvaluator, BatchedRussianDollMCTS,  # noqa: F401
+                   self_play_game, move_from_records, move_uci)
 
 __version__ = "0.1.0"
