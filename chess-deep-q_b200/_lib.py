@@ -14,6 +14,7 @@ SIGNATURES = {
     "cdq_version": (c_int, []),
     "cdq_error_string": (ctypes.c_char_p, [c_int]),
     "cdq_eval_terms": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cdq_attack_maps": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cdq_encode_planes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cdq_net_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "cdq_net_load": (c_int, [c_void_p, c_void_p, c_void_p]),

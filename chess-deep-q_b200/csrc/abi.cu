@@ -89,6 +89,12 @@ int cdq_eval_terms(const CdqBoard* d_boards, int64_t n, int ignore_checkmate, in
     return launch_eval_terms(d_boards, n, ignore_checkmate, d_terms, d_score, d_flags, (cudaStream_t)stream);
 }
 
+int cdq_attack_maps(const CdqBoard* d_boards, int64_t n, uint64_t* d_maps, void* stream) {
+    if (n < 0 || (n > 0 && (!d_boards || !d_maps))) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_attack_maps(d_boards, n, (unsigned long long*)d_maps, (cudaStream_t)stream);
+}
+
 int cdq_encode_planes(const CdqBoard* d_boards, int64_t n, float* d_planes, void* stream) {
     if (n < 0 || (n > 0 && (!d_boards || !d_planes))) return CDQ_E_BADARG;
     if (int e = check_device()) return e;

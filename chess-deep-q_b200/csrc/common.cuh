@@ -26,6 +26,7 @@ struct ProfileScope {
 // launchers implemented in the .cu files
 int launch_eval_terms(const CdqBoard* boards, long long n, int ignore_checkmate, int* terms, double* score,
                       unsigned* flags, cudaStream_t st);
+int launch_attack_maps(const CdqBoard* boards, long long n, unsigned long long* maps, cudaStream_t st);
 int launch_encode_planes(const CdqBoard* boards, long long n, float* planes, cudaStream_t st);
 int launch_random_playouts(CdqBoard* boards, long long n, unsigned long long seed, int max_plies, cudaStream_t st);
 

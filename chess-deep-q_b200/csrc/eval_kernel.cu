@@ -190,6 +190,53 @@ encode_planes_kernel(const CdqBoard* __restrict__ boards, long long n, float* __
     }
 }
 
+// the maps behind find_threatened_squares / find_guarded_squares /
+// calculate_attack_range / calculate_movement_range (evaluation.py:368-428): per position
+// [attacked by white, attacked by black, legal destinations of white, legal destinations of black]
+// (turn forced, castling = the king's destination, en passant = the ep square).
+struct DestVisitor {
+    u64 d = 0;
+    bool white;
+    template <int D> __device__ __forceinline__ void slide(u64 t) { d |= t; }
+    template <int J> __device__ __forceinline__ void knight(u64 t) { d |= t; }
+    __device__ __forceinline__ void king(u64 t) { d |= t; }
+    __device__ __forceinline__ void pawn_push(u64 s, u64 dd) { d |= s | dd; }
+    template <int D> __device__ __forceinline__ void pawn_cap(u64 t) { d |= t; }
+    __device__ __forceinline__ void castle(bool k, bool q) {
+        const int sh = white ? 0 : 56;
+        if (k) d |= 0x40ull << sh;
+        if (q) d |= 0x04ull << sh;
+    }
+    __device__ __forceinline__ void ep(u64 caps, int epsq) { if (caps) d |= 1ull << epsq; }
+};
+
+__global__ void __launch_bounds__(EVAL_THREADS)
+attack_maps_kernel(const CdqBoard* __restrict__ boards, long long n, u64* __restrict__ maps) {
+    __shared__ __align__(16) u64 srec[EVAL_THREADS * 9];
+    const long long base = (long long)blockIdx.x * EVAL_THREADS;
+    stage_records<EVAL_THREADS>(boards, n, base, srec);
+    const long long i = base + threadIdx.x;
+    if (i >= n) return;
+    const Pos p = load_pos(srec + threadIdx.x * 9);
+    const Props q = make_props(~(p.co[0] | p.co[1]));
+    const u64 att_w = attack_map<1>(p, q), att_b = attack_map<0>(p, q);
+    DestVisitor vw, vb;
+    vw.white = true; vb.white = false;
+    gen_side<1>(p, q, att_b, vw);
+    gen_side<0>(p, q, att_w, vb);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(maps + i * 4);
+    o[0] = make_ulonglong2(att_w, att_b);
+    o[1] = make_ulonglong2(vw.d, vb.d);
+}
+
+int launch_attack_maps(const CdqBoard* boards, long long n, unsigned long long* maps, cudaStream_t st) {
+    if (n == 0) return 0;
+    ProfileScope ps(KK_EVAL, st);
+    attack_maps_kernel<<<(unsigned)((n + EVAL_THREADS - 1) / EVAL_THREADS), EVAL_THREADS, 0, st>>>(boards, n, maps);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int launch_eval_terms(const CdqBoard* boards, long long n, int ignore_checkmate, int* terms, double* score,
                       unsigned* flags, cudaStream_t st) {
     if (n == 0) return 0;

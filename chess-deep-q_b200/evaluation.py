@@ -38,3 +38,49 @@ def fast_evaluate_position(board, ignore_checkmate=False):
     if int(flags[0].item()) & F_BADBOARD:
         raise _lib.CdqError("malformed board record")
     return float(score[0].item())
+
+
+# ------------------------------------------------------------------ attack / movement maps (evaluation.py:368-428)
+def attack_maps(boards):
+    """-> int64 CUDA tensor [n,4]: bitboards {attacked by white, attacked by black, legal
+    destinations of white, legal destinations of black} (bit i = square i)."""
+    import torch
+    d = to_device(boards)
+    out = torch.empty((d.shape[0], 4), dtype=torch.int64, device=d.device)
+    _lib.check(_lib.lib().cdq_attack_maps(d.data_ptr(), d.shape[0], out.data_ptr(), _lib.stream_ptr()))
+    return out
+
+
+def _squares(bits):
+    bits &= (1 << 64) - 1
+    return {s for s in range(64) if (bits >> s) & 1}
+
+
+def _maps_of(board):
+    m = attack_maps(board)[0].tolist()
+    return [x & ((1 << 64) - 1) for x in m]
+
+
+def _turn_of(board):
+    from .board_utils import as_records
+    return bool(int(as_records(board)[0]["meta"]) & 1)
+
+
+def calculate_attack_range(board, color):
+    """evaluation.py:402-413"""
+    return _squares(_maps_of(board)[0 if color else 1])
+
+
+def calculate_movement_range(board, color):
+    """evaluation.py:417-428"""
+    return _squares(_maps_of(board)[2 if color else 3])
+
+
+def find_threatened_squares(board):
+    """evaluation.py:368-382: squares attacked by the opponent of the side to move"""
+    return calculate_attack_range(board, not _turn_of(board))
+
+
+def find_guarded_squares(board):
+    """evaluation.py:384-398: squares attacked by the side to move"""
+    return calculate_attack_range(board, _turn_of(board))

@@ -120,6 +120,11 @@ int cdq_eval_terms(const CdqBoard* d_boards, int64_t n, int ignore_checkmate,
                    int32_t* d_terms /*[n][24]*/, double* d_score /*[n]*/,
                    uint32_t* d_flags /*[n]*/, void* stream);
 
+/* Replaces find_threatened_squares / find_guarded_squares / calculate_attack_range /
+ * calculate_movement_range (evaluation.py:368-428) for a batch: d_maps[i] = { squares attacked by
+ * white, attacked by black, legal destination squares of white, of black (turn forced) }. */
+int cdq_attack_maps(const CdqBoard* d_boards, int64_t n, uint64_t* d_maps /*[n][4]*/, void* stream);
+
 /* Replaces board_utils.board_to_tensor (board_utils.py:12-40) /
  * archive boards_to_tensor_batch (archive/board_utils.py:2-10): fp32 planes [n,12,8,8]. */
 int cdq_encode_planes(const CdqBoard* d_boards, int64_t n, float* d_planes, void* stream);

@@ -706,6 +706,26 @@ void cdq_oracle_eval(const CdqBoard* boards, int64_t n, int ignore_checkmate, in
     parallel_for(n, nthreads, eval_slice, &a);
 }
 
+/* evaluation.py:368-428: per position {attacked by white, attacked by black, legal destination
+ * squares of white, of black (turn forced)} */
+void cdq_oracle_maps(const CdqBoard* boards, int64_t n, uint64_t* out) {
+    cdq_oracle_init();
+    for (int64_t i = 0; i < n; i++) {
+        Pos p; unpack(&boards[i], &p);
+        u64 a[2] = {0, 0}, d[2] = {0, 0};
+        for (int s = 0; s < 64; s++) {
+            if (is_attacked_by(&p, WHITE, s)) a[0] |= BB(s);
+            if (is_attacked_by(&p, BLACK, s)) a[1] |= BB(s);
+        }
+        for (int c = 0; c < 2; c++) {
+            Pos q = p; q.turn = c == 0 ? WHITE : BLACK;
+            MoveList l; gen_legal(&q, &l);
+            for (int k = 0; k < l.n; k++) d[c] |= BB(MV_TO(l.m[k]));
+        }
+        out[i * 4 + 0] = a[0]; out[i * 4 + 1] = a[1]; out[i * 4 + 2] = d[0]; out[i * 4 + 3] = d[1];
+    }
+}
+
 /* board_to_tensor (board_utils.py:12-40) for a batch: planes [n][12][8][8] */
 void cdq_oracle_encode_planes(const CdqBoard* boards, int64_t n, float* planes) {
     for (int64_t i = 0; i < n; i++) {

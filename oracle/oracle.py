@@ -54,6 +54,7 @@ def lib():
         L.cdq_oracle_eval.argtypes = [vp, i64, i32, vp, vp, vp, i32]
         L.cdq_oracle_encode_planes.argtypes = [vp, i64, vp]
         L.cdq_oracle_playouts.argtypes = [u64, i64, i32, vp]
+        L.cdq_oracle_maps.argtypes = [vp, i64, vp]
         L.cdq_oracle_init()
         _lib = L
     return _lib
@@ -120,6 +121,14 @@ def encode_planes(boards):
     boards = np.ascontiguousarray(boards)
     out = np.zeros((len(boards), 12, 8, 8), np.float32)
     lib().cdq_oracle_encode_planes(_ptr(boards), len(boards), _ptr(out))
+    return out
+
+
+def attack_maps(boards):
+    """evaluation.py:368-428 -> uint64 [n,4]: attacked by white / black, legal destinations of white / black."""
+    boards = np.ascontiguousarray(boards)
+    out = np.zeros((len(boards), 4), np.uint64)
+    lib().cdq_oracle_maps(_ptr(boards), len(boards), _ptr(out))
     return out
 
 

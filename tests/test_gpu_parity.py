@@ -278,3 +278,19 @@ def test_full_size_properties_1m(cdq, oracle):
     # (4) ranges
     assert float(out["leaf"].abs().max()) <= 1.0
     assert bool(torch.isfinite(out["score"]).all())
+
+
+def test_attack_and_movement_maps(cdq, oracle, eval_golden):
+    """find_threatened_squares / find_guarded_squares / calculate_attack_range /
+    calculate_movement_range (evaluation.py:368-428) from the eval kernel's bitboards."""
+    boards = np.concatenate([eval_golden["boards"][:40], oracle.playouts(20000, seed=17)])
+    ref = oracle.attack_maps(boards)
+    got = _np(cdq.evaluation.attack_maps(boards)).view(np.uint64)
+    assert np.array_equal(got, ref)
+    b = boards[5:6]
+    white = bool(int(b["meta"][0]) & 1)
+    sq = lambda bits: {s for s in range(64) if (int(bits) >> s) & 1}   # noqa: E731
+    assert cdq.evaluation.calculate_attack_range(b, True) == sq(ref[5, 0])
+    assert cdq.evaluation.calculate_movement_range(b, False) == sq(ref[5, 3])
+    assert cdq.evaluation.find_threatened_squares(b) == sq(ref[5, 1 if white else 0])
+    assert cdq.evaluation.find_guarded_squares(b) == sq(ref[5, 0 if white else 1])
