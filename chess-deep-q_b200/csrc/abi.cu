@@ -111,7 +111,14 @@ int cdq_expand(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* 
                void* stream) {
     if (n < 0 || max_children < 0 || (n > 0 && (!d_boards || !d_children || !d_counts))) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
-    return launch_expand(d_boards, n, max_children, d_children, d_counts, (cudaStream_t)stream);
+    return launch_expand(d_boards, n, max_children, d_children, d_counts, nullptr, (cudaStream_t)stream);
+}
+
+int cdq_expand_weighted(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* d_children, int32_t* d_counts,
+                        uint8_t* d_weights, void* stream) {
+    if (n < 0 || max_children < 0 || (n > 0 && (!d_boards || !d_children || !d_counts || !d_weights))) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_expand(d_boards, n, max_children, d_children, d_counts, d_weights, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ network handle

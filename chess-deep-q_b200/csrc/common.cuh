@@ -31,6 +31,6 @@ int launch_encode_planes(const CdqBoard* boards, long long n, float* planes, cud
 int launch_random_playouts(CdqBoard* boards, long long n, unsigned long long seed, int max_plies, cudaStream_t st);
 
 int launch_expand(const CdqBoard* boards, long long n, int max_children, CdqBoard* children, int* counts,
-                  cudaStream_t st);
+                  unsigned char* weights, cudaStream_t st);
 
 } // namespace cdq

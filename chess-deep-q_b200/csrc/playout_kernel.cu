@@ -170,12 +170,50 @@ random_playouts_kernel(CdqBoard* __restrict__ boards, long long n, u64 seed, int
     store_pos(p, reinterpret_cast<u64*>(boards) + i * 9);
 }
 
+// Sampling weight of a move, categorize_moves (evaluation.py:232-339): first matching category of
+// capture of a more valuable piece 10, gives check 9, equal capture 8, moves a threatened piece 7,
+// develops a minor piece 6, capture of a less valuable piece 5, to d4/e4/d5/e5 4, castling or a king
+// move from its back rank 3, pawn move 2, other 1.  (An en-passant capture lands on an empty square
+// and is therefore not a "capture" there.)
+__device__ __forceinline__ int piece_value_at(const Pos& p, u64 b) {
+    if (p.P & b) return 1;
+    if ((p.N | p.B) & b) return 3;
+    if (p.R & b) return 5;
+    if (p.Q & b) return 9;
+    return 0;   // king (PIECE_VALUES, evaluation.py:8-15)
+}
+__device__ __forceinline__ int move_category_weight(const Pos& p, const Pos& child, const SelectVisitor& m, u64 att_opp, bool white) {
+    const u64 fb = 1ull << m.from, tb = 1ull << m.to;
+    const u64 occ = p.co[0] | p.co[1];
+    if (occ & tb) {
+        const int vt = piece_value_at(p, tb), vf = piece_value_at(p, fb);
+        return vt > vf ? 10 : (vt == vf ? 8 : 5);
+    }
+    {   // gives check: the child's side to move is attacked on its king square
+        const u64 cocc = child.co[0] | child.co[1];
+        const Props cq = make_props(~cocc);
+        const u64 att_us = white ? attack_map<1>(child, cq) : attack_map<0>(child, cq);
+        if (att_us & child.K & child.co[white ? 0 : 1]) return 9;
+    }
+    if (att_opp & fb) return 7;
+    const int fr = m.from >> 3, ff = m.from & 7;
+    if (((p.N | p.B) & fb) && fr == (white ? 0 : 7) && (ff == 1 || ff == 2 || ff == 5 || ff == 6)) return 6;
+    if (tb & 0x0000001818000000ull) return 4;
+    if (p.K & fb) {
+        const int d = ff - (m.to & 7);
+        if (d > 1 || d < -1) return 3;
+        if (fr == (white ? 0 : 7)) return 3;
+    }
+    if (p.P & fb) return 2;
+    return 1;
+}
+
 // All legal successors of each position (side to move), the building block of a batched tree
 // expansion (mcts.py:166-194 calls list(board.legal_moves) + push per child).  children is
 // [n][max_children]; counts[i] = number of legal moves (children beyond max_children are dropped).
 __global__ void __launch_bounds__(128)
 expand_kernel(const CdqBoard* __restrict__ boards, long long n, int max_children,
-              CdqBoard* __restrict__ children, int* __restrict__ counts) {
+              CdqBoard* __restrict__ children, int* __restrict__ counts, unsigned char* __restrict__ weights) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Pos p = load_pos(reinterpret_cast<const u64*>(boards) + i * 9);
@@ -194,14 +232,15 @@ expand_kernel(const CdqBoard* __restrict__ boards, long long n, int max_children
         Pos c = p;
         apply_move(c, sv);
         store_pos(c, reinterpret_cast<u64*>(children) + (i * max_children + r) * 9);
+        if (weights) weights[i * max_children + r] = (unsigned char)move_category_weight(p, c, sv, att_opp, white);
     }
 }
 
 int launch_expand(const CdqBoard* boards, long long n, int max_children, CdqBoard* children, int* counts,
-                  cudaStream_t st) {
+                  unsigned char* weights, cudaStream_t st) {
     if (n == 0) return 0;
     ProfileScope ps(KK_PLAYOUT, st);
-    expand_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(boards, n, max_children, children, counts);
+    expand_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(boards, n, max_children, children, counts, weights);
     count_launch();
     return (int)cudaGetLastError();
 }

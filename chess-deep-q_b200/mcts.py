@@ -78,9 +78,9 @@ def evaluate_position(board, neural_net, device=None):
 # simulations advance level by level in waves of `num_workers` (the reference's thread count): every
 # level of a wave costs one device expansion (cdq_expand) and the wave's leaves cost one
 # cdq_leaf_eval, instead of one batch-1 network call per simulation under the GIL.
-# Differences, stated: children are sampled uniformly (the tactical move categoriser,
-# evaluation.py:232-366, is row f2 and not built); nodes are keyed by their 72-byte record instead
-# of a FEN; positions inside a search carry no move history (rep3 = 0).
+# Children are sampled like select_weighted_moves does, with the tactical weights of categorize_moves
+# computed on the device (cdq_expand_weighted, row f2).  Differences, stated: nodes are keyed by
+# their 72-byte record instead of a FEN; positions inside a search carry no move history (rep3 = 0).
 import math
 import random as _random
 
@@ -140,11 +140,13 @@ class BatchedRussianDollMCTS:
         kids = torch.empty((n, maxc, 9), dtype=torch.int64, device=d.device)
         counts = torch.empty(n, dtype=torch.int32, device=d.device)
         flags = torch.empty(n, dtype=torch.int32, device=d.device)
+        wts = torch.empty((n, maxc), dtype=torch.uint8, device=d.device)
         L = _lib.lib()
-        _lib.check(L.cdq_expand(d.data_ptr(), n, maxc, kids.data_ptr(), counts.data_ptr(), _lib.stream_ptr()))
+        _lib.check(L.cdq_expand_weighted(d.data_ptr(), n, maxc, kids.data_ptr(), counts.data_ptr(), wts.data_ptr(),
+                                         _lib.stream_ptr()))
         _lib.check(L.cdq_eval_terms(d.data_ptr(), n, 0, None, None, flags.data_ptr(), _lib.stream_ptr()))
         kids_h = kids.cpu().numpy().view(np.uint64).reshape(n, maxc, 9)
-        counts_h, flags_h = counts.cpu().numpy(), flags.cpu().numpy()
+        counts_h, flags_h, wts_h = counts.cpu().numpy(), flags.cpu().numpy(), wts.cpu().numpy()
         width = self.samples_per_level[0]
         for i, key in enumerate(uniq):
             c = min(int(counts_h[i]), maxc)
@@ -153,7 +155,17 @@ class BatchedRussianDollMCTS:
             else:
                 idx = list(range(c))
                 if c > width:
-                    idx = self.rng.sample(idx, width)
+                    # select_weighted_moves (evaluation.py:342-366): `width` draws without replacement,
+                    # probability proportional to the tactical weight of the move
+                    pool, w, idx = idx, [float(x) for x in wts_h[i, :c]], []
+                    for _ in range(width):
+                        r, acc = self.rng.random() * sum(w), 0.0
+                        for k, wk in enumerate(w):
+                            acc += wk
+                            if r < acc:
+                                break
+                        idx.append(pool.pop(k))
+                        w.pop(k)
                 sel = np.ascontiguousarray(kids_h[i, idx]).view(BOARD_DTYPE).reshape(-1)
             self.children[key] = sel
             self.N[key] = np.zeros(len(sel), np.int64)

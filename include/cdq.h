@@ -181,6 +181,11 @@ int cdq_random_playouts(CdqBoard* d_boards, int64_t n, uint64_t seed, int max_pl
 int cdq_expand(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* d_children,
                int32_t* d_counts, void* stream);
 
+/* Same, plus the tactical sampling weight (10..1) of every child's move as categorize_moves assigns
+ * it (evaluation.py:232-339); select_weighted_moves (evaluation.py:342-366) samples with them. */
+int cdq_expand_weighted(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* d_children,
+                        int32_t* d_counts, uint8_t* d_weights /*[n][max_children]*/, void* stream);
+
 /* Kernel launch counter (all cdq_* kernels launched by this process), for bench gpu_launches. */
 uint64_t cdq_launch_count(void);
 

@@ -706,6 +706,35 @@ void cdq_oracle_eval(const CdqBoard* boards, int64_t n, int ignore_checkmate, in
     parallel_for(n, nthreads, eval_slice, &a);
 }
 
+/* categorize_moves (evaluation.py:232-339): sampling weight of every legal move, in the order of
+ * cdq_oracle_legal_moves. */
+int cdq_oracle_categorize(const CdqBoard* b, uint16_t* moves, int* weights) {
+    Pos p; cdq_oracle_init(); unpack(b, &p);
+    MoveList l; gen_legal(&p, &l);
+    for (int i = 0; i < l.n; i++) {
+        Move m = l.m[i];
+        int f = MV_FROM(m), t = MV_TO(m), w;
+        int ft = type_at(&p, f), tt = type_at(&p, t);
+        int fr = sq_rank(f), ff = sq_file(f), tf = sq_file(t);
+        if (tt >= 0) {
+            int vt = PIECE_VALUE[tt], vf = PIECE_VALUE[ft];
+            w = vt > vf ? 10 : (vt == vf ? 8 : 5);
+        } else {
+            Pos q = p; push(&q, m);
+            if (in_check(&q)) w = 9;
+            else if (is_attacked_by(&p, !p.turn, f)) w = 7;
+            else if ((ft == KNIGHT || ft == BISHOP) && fr == (p.turn == WHITE ? 0 : 7) && (ff == 1 || ff == 2 || ff == 5 || ff == 6)) w = 6;
+            else if (t == SQ(3, 3) || t == SQ(4, 3) || t == SQ(3, 4) || t == SQ(4, 4)) w = 4;
+            else if (ft == KING && (ff - tf > 1 || tf - ff > 1 || fr == (p.turn == WHITE ? 0 : 7))) w = 3;
+            else if (ft == PAWN) w = 2;
+            else w = 1;
+        }
+        if (moves) moves[i] = m;
+        weights[i] = w;
+    }
+    return l.n;
+}
+
 /* evaluation.py:368-428: per position {attacked by white, attacked by black, legal destination
  * squares of white, of black (turn forced)} */
 void cdq_oracle_maps(const CdqBoard* boards, int64_t n, uint64_t* out) {

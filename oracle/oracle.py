@@ -55,6 +55,8 @@ def lib():
         L.cdq_oracle_encode_planes.argtypes = [vp, i64, vp]
         L.cdq_oracle_playouts.argtypes = [u64, i64, i32, vp]
         L.cdq_oracle_maps.argtypes = [vp, i64, vp]
+        L.cdq_oracle_categorize.argtypes = [vp, vp, vp]
+        L.cdq_oracle_categorize.restype = i32
         L.cdq_oracle_init()
         _lib = L
     return _lib
@@ -122,6 +124,14 @@ def encode_planes(boards):
     out = np.zeros((len(boards), 12, 8, 8), np.float32)
     lib().cdq_oracle_encode_planes(_ptr(boards), len(boards), _ptr(out))
     return out
+
+
+def categorize(board):
+    """categorize_moves (evaluation.py:232-339) -> (moves uint16 [k], sampling weights int32 [k])."""
+    mv = np.zeros(512, np.uint16)
+    w = np.zeros(512, np.int32)
+    k = lib().cdq_oracle_categorize(_ptr(np.ascontiguousarray(board)), _ptr(mv), _ptr(w))
+    return mv[:k].copy(), w[:k].copy()
 
 
 def attack_maps(boards):

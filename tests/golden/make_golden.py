@@ -207,6 +207,27 @@ def make_eval_golden():
     return boards, planes
 
 
+def make_policy_golden(boards):
+    """categorize_moves (evaluation.py:232-339) of the reference itself: sampling weight per legal move."""
+    weights = {"captures_high_value": 10, "checks": 9, "captures_equal_value": 8, "threatened_piece_moves": 7,
+               "developing_moves": 6, "captures_low_value": 5, "center_control": 4, "king_safety": 3,
+               "pawn_structure": 2, "other_moves": 1}
+    idx, mv, wt = [], [], []
+    pick = list(range(0, 29)) + list(range(29, 29 + 220))
+    for i in pick:
+        b = unpack_board(boards[i])
+        cats, cw = ref_evaluation.categorize_moves(b)
+        assert cw == weights
+        for name, moves in cats.items():
+            for m in moves:
+                idx.append(i)
+                mv.append(m.from_square | (m.to_square << 6) | (((m.promotion - 1) if m.promotion else 0) << 12))
+                wt.append(cw[name])
+    np.savez_compressed(os.path.join(HERE, "policy_golden.npz"), boards=boards, pos=np.array(idx, np.int32),
+                        move=np.array(mv, np.uint16), weight=np.array(wt, np.int8), picked=np.array(pick, np.int32))
+    print("policy golden:", len(pick), "positions,", len(mv), "moves")
+
+
 def load_params(module, params):
     module.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()})
 
@@ -271,5 +292,6 @@ def make_train_golden(boards, planes):
 
 if __name__ == "__main__":
     b, pl = make_eval_golden()
+    make_policy_golden(b)
     make_net_golden(b, pl)
     make_train_golden(b, pl)

@@ -60,15 +60,22 @@ def test_search_returns_legal_move_and_exact_leaf_values(cdq, oracle):
     assert cdq.move_uci(root[0], child[0])[:4] == "abcdefgh"[frm & 7] + str((frm >> 3) + 1) + "abcdefgh"[to & 7] + str((to >> 3) + 1)
 
 
-def test_search_prefers_mate_in_one_for_white(cdq, oracle):
+def test_mate_in_one_backs_up_the_exact_terminal_value(cdq, oracle):
+    """Ra8# for white: the mated leaf is worth exactly +1 (mcts.py:202-203, white-centric) and the
+    running mean of that edge stays +1; with the reference's UCB (which divides the mean by N once
+    more, mcts.py:61-62) that edge is visited at least as often as the average edge."""
     import random
     net, _ = _net(cdq, oracle, scale=1.0)
-    root = oracle.from_fen("6k1/5ppp/8/8/8/8/8/R5K1 w - - 0 1")       # Ra8#
+    root = oracle.from_fen("6k1/5ppp/8/8/8/8/8/R5K1 w - - 0 1")
     tree = cdq.BatchedRussianDollMCTS(root, iterations=200, rng=random.Random(3))
-    child, move = tree.search(net)
-    assert move[:2] == (0, 56)
-    _, _, f = oracle.evaluate(child)
-    assert f[0] & 0x10
+    tree.search(net)
+    key = root[0].tobytes()
+    kids = tree.children[key]
+    mate = [i for i, k in enumerate(kids) if oracle.evaluate(np.array([k], dtype=oracle.BOARD_DTYPE))[2][0] & 0x10]
+    assert len(mate) == 1 and cdq.move_from_records(root[0], kids[mate[0]])[:2] == (0, 56)
+    assert tree.Q[key][mate[0]] == 1.0
+    assert tree.N[key][mate[0]] >= tree.N[key].mean()
+    assert int(tree.N[key].sum()) == 200
 
 
 def test_terminal_root(cdq, oracle):
@@ -90,3 +97,45 @@ def test_self_play_game_with_batched_leaf_evaluation(cdq, oracle):
     assert np.array_equal(np.array(scores), s_ref)                     # reward-shaping scores are the bit-exact eval
     again, _ = cdq.self_play_game(net, max_moves=24, iterations=50, seed=42)
     assert np.array_equal(again, positions)                           # seeded -> reproducible
+
+
+def test_expand_weights_match_categorize_moves(cdq, oracle, eval_golden):
+    """the device move categoriser (sampling weights 10..1) against the oracle, which is
+    itself pinned to the reference's categorize_moves (tests/test_oracle.py)."""
+    boards = np.concatenate([eval_golden["boards"][:250], oracle.playouts(750, seed=9)])
+    d = cdq.board_utils.to_device(boards)
+    n, maxc = len(boards), 128
+    kids = torch.zeros((n, maxc, 9), dtype=torch.int64, device="cuda")
+    counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    wts = torch.zeros((n, maxc), dtype=torch.uint8, device="cuda")
+    L = cdq._lib.lib()
+    cdq._lib.check(L.cdq_expand_weighted(d.data_ptr(), n, maxc, kids.data_ptr(), counts.data_ptr(), wts.data_ptr(),
+                                         cdq._lib.stream_ptr()))
+    kh, ch, wh = kids.cpu().numpy().view(np.uint64), counts.cpu().numpy(), wts.cpu().numpy()
+    for i in range(n):
+        mv, w = oracle.categorize(boards[i:i + 1])
+        want = {oracle.push(boards[i:i + 1], m)[0].tobytes(): int(x) for m, x in zip(mv, w)}
+        # under-promotions to the same square give distinct children, so the map is one-to-one
+        got = {kh[i, k].tobytes(): int(wh[i, k]) for k in range(ch[i])}
+        assert got == want, i
+
+
+def test_weighted_child_sampling_prefers_tactical_moves(cdq, oracle):
+    """exd5 wins a queen with a pawn (weight 10, evaluation.py:253); with 5 weighted draws out of ~31
+    moves it must be sampled far more often than the ~16 % a uniform sampler would give."""
+    import random
+    net, _ = _net(cdq, oracle)
+    root = oracle.from_fen("rnb1kbnr/ppp1pppp/8/3q4/4P3/8/PPPP1PPP/RNBQKBNR w KQkq - 0 1")
+    mv, w = oracle.categorize(root)
+    best = [int(m) for m, x in zip(mv, w) if x == 10]
+    assert len(best) == 1
+    target = oracle.push(root, best[0])[0].tobytes()
+    hits = 0
+    for seed in range(40):
+        tree = cdq.BatchedRussianDollMCTS(root, iterations=1, samples_per_level=[5], rng=random.Random(seed))
+        tree.search(net)
+        kids = tree.children[root[0].tobytes()]
+        assert len(kids) == 5 and len({k.tobytes() for k in kids}) == 5
+        hits += any(k.tobytes() == target for k in kids)
+    expected = 1.0 - np.prod([1.0 - 10.0 / (w.sum() - 2.0 * i) for i in range(5)])    # rough lower estimate
+    assert hits >= 0.6 * 40 * expected and hits > 40 * 5 / len(mv) * 1.8

@@ -101,3 +101,19 @@ def test_net_oracle_matches_reference_class(oracle, eval_golden, net_golden):
 def test_empty_batch(oracle):
     t, s, f = oracle.evaluate(np.zeros(0, oracle.BOARD_DTYPE))
     assert t.shape == (0, 24) and s.shape == (0,) and f.shape == (0,)
+
+
+def test_move_categories_match_reference_categorize_moves(oracle):
+    """oracle.categorize == the reference's own categorize_moves (evaluation.py:232-339) run over the
+    shim, move for move (tests/golden/policy_golden.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "policy_golden.npz"))
+    boards, pos, move, weight = g["boards"], g["pos"], g["move"], g["weight"]
+    checked = 0
+    for i in g["picked"]:
+        mv, w = oracle.categorize(boards[i:i + 1])
+        want = {int(m): int(x) for m, x in zip(move[pos == i], weight[pos == i])}
+        got = {int(m): int(x) for m, x in zip(mv, w)}
+        assert got == want, i
+        checked += len(got)
+    assert checked > 6000
