@@ -207,6 +207,25 @@ def make_eval_golden():
     return boards, planes
 
 
+def make_arbitrary_golden():
+    """fast_evaluate_position of the reference on arbitrary (mostly unreachable) positions."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from randboards import random_boards
+    boards = random_boards(400, seed=2024).astype(O.BOARD_DTYPE)
+    n = len(boards)
+    score = np.zeros(n)
+    terms = np.full((n, O.NTERMS), -999, np.int32)
+    has = np.zeros(n, bool)
+    for i in range(n):
+        b = unpack_board(boards[i])
+        assert (pack_board(b) == boards[i:i + 1]).all(), i      # castling bits are clean, ep preserved
+        score[i], T = reference_eval(b, False)
+        if T is not None:
+            terms[i], has[i] = T, True
+    np.savez_compressed(os.path.join(HERE, "arbitrary_golden.npz"), boards=boards, score=score, terms=terms, has_terms=has)
+    print("arbitrary golden:", n, "positions;", int(has.sum()), "with integer terms")
+
+
 def make_policy_golden(boards):
     """categorize_moves (evaluation.py:232-339) of the reference itself: sampling weight per legal move."""
     weights = {"captures_high_value": 10, "checks": 9, "captures_equal_value": 8, "threatened_piece_moves": 7,
@@ -293,5 +312,6 @@ def make_train_golden(boards, planes):
 if __name__ == "__main__":
     b, pl = make_eval_golden()
     make_policy_golden(b)
+    make_arbitrary_golden()
     make_net_golden(b, pl)
     make_train_golden(b, pl)

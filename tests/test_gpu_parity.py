@@ -294,3 +294,29 @@ def test_attack_and_movement_maps(cdq, oracle, eval_golden):
     assert cdq.evaluation.calculate_movement_range(b, False) == sq(ref[5, 3])
     assert cdq.evaluation.find_threatened_squares(b) == sq(ref[5, 1 if white else 0])
     assert cdq.evaluation.find_guarded_squares(b) == sq(ref[5, 0 if white else 1])
+
+
+from randboards import random_boards as _random_boards  # noqa: E402
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_eval_matches_oracle_on_arbitrary_positions(cdq, oracle, seed):
+    boards = _random_boards(60_000, seed).astype(oracle.BOARD_DTYPE)
+    t_ref, s_ref, f_ref = oracle.evaluate(boards, nthreads=0)
+    terms, score, flags = _eval_gpu(cdq, boards)
+    bad = np.nonzero((terms != t_ref).any(1))[0]
+    assert bad.size == 0, "first of %d mismatches, board %s meta %x: gpu %s oracle %s" % (
+        bad.size, [hex(int(x)) for x in boards["bb"][bad[0]]], int(boards["meta"][bad[0]]), terms[bad[0]], t_ref[bad[0]])
+    assert np.array_equal(score, s_ref)
+    assert np.array_equal(flags & 0xFFFF, f_ref & 0xFFFF)
+    assert np.array_equal(_np(cdq.evaluation.attack_maps(boards)).view(np.uint64), oracle.attack_maps(boards[:60_000]))
+
+
+def test_eval_matches_reference_on_arbitrary_golden(cdq):
+    """The reference's own evaluation.py on 400 arbitrary positions (tests/golden/arbitrary_golden.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "arbitrary_golden.npz"))
+    terms, score, flags = _eval_gpu(cdq, g["boards"])
+    assert np.array_equal(score, g["score"])
+    has = g["has_terms"]
+    assert np.array_equal(terms[has][:, :23], g["terms"][has][:, :23])

@@ -117,3 +117,15 @@ def test_move_categories_match_reference_categorize_moves(oracle):
         assert got == want, i
         checked += len(got)
     assert checked > 6000
+
+
+def test_eval_matches_reference_on_arbitrary_positions(oracle):
+    """Oracle vs the reference's own evaluation.py (over the shim) on 400 arbitrary positions:
+    multiple checkers, pins while in check, many sliders, kings in corners, ep squares."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "arbitrary_golden.npz"))
+    terms, score, _ = oracle.evaluate(g["boards"])
+    assert np.array_equal(score, g["score"])
+    has = g["has_terms"]
+    assert has.sum() > 200
+    assert np.array_equal(terms[has][:, :23], g["terms"][has][:, :23])
