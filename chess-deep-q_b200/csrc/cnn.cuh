@@ -29,6 +29,8 @@ int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __
 int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float inv_scale, float* g_fc1_w, cudaStream_t st);
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                       cudaStream_t st, __half* act1_boards = nullptr);
+int launch_conv_stack_v1(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
+                         cudaStream_t st, __half* act1_boards);
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
                    float* leaf, float* hidden, cudaStream_t st);
 

@@ -316,8 +316,9 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
-                      cudaStream_t st, __half* act1_boards) {
+// first formulation (one MMA per 3x3 tap); kept for A/B runs: CDQ_CONV_V1=1 selects it in launch_conv_stack
+int launch_conv_stack_v1(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
+                         cudaStream_t st, __half* act1_boards) {
     if (n == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {

@@ -1,0 +1,415 @@
+// conv_stream_kernel.cu -- K2a, second formulation: boards -> ReLU(conv2(ReLU(conv1(one-hot planes))))
+// as fp16 in fc1's A-operand tile order (neural_network.py:22-23,30-31), streamed FILE BY FILE.
+//
+// Why: a tcgen05.mma (M=128, K=16) costs max(N/2, 40 + 0.22 N) cycles -- it fetches its 4 KB A
+// operand and 32 N bytes of B from shared memory for every instruction (tests/cuda/umma_bw_probe.cu).
+// The first kernel (conv_kernel.cu) used one N=64 MMA per 3x3 tap, each on its own shifted A:
+// 54 cycles for 32 cycles of math.  Here one A operand feeds the three taps of a kernel row:
+//
+//   tile      = 16 positions; GEMM rows m = (rank y, position p), p fastest -> M = 128
+//   A operand = one FILE x of those 16 boards: shared-memory slab [K/8 chunks][10 padded ranks]
+//               [16 positions][16 B], K-major no-swizzle with SBO = 128 B and LBO = 2 560 B; every
+//               core matrix is 128 contiguous, 128-byte-aligned bytes and the vertical tap dy is
+//               a +-256 B start address
+//   scatter   = source file x contributes to output files x+1, x, x-1 through taps dx = -1, 0, +1:
+//               three MMAs (N = 64 each for conv2, 32 for conv1) on the SAME A with
+//               collector::a::fill/use/lastuse, each accumulating into the TMEM slot of its
+//               output file.  3 x 32 cycles of math per 4 KB A + 6 KB B fetched (96-cycle floor met).
+//
+// The kernel is a stream over file steps g = 8 * tile + x with ring buffers everywhere:
+//   planes slabs (8 x 5 KB), act1 slabs (8 x 10 KB), conv1 TMEM slots (4 x 32 columns), conv2 TMEM
+//   slots (6 x 64 columns); an output file is complete once source files x-1, x, x+1 have been
+//   issued.  Warp roles (all hand-overs by mbarriers):
+//     warp 0, 1     MMA issuers: conv1(g) and conv2(g), each paced only by its own barriers
+//     warps 2-5     plane encoder: thread = (rank, position), one square per step
+//     warps 6-9     epilogue 1: conv1 slot -> ReLU -> fp16 -> act1 slab (+ optional training copies)
+//     warps 10-13   epilogue 2: conv2 slot -> +bias -> ReLU -> fp16 -> global, fc1 tile order
+//
+// Algorithmic work: 2 801 664 FLOP/position (dense convention);
+// traffic 72 B in + 8 192 B out per position.
+#include <cstdlib>
+#include "umma.cuh"
+#include "common.cuh"
+#include "cnn.cuh"
+
+namespace cdq {
+namespace cs {
+
+typedef unsigned long long u64;
+
+constexpr int TILE_POS = 16;                      // positions per tile
+constexpr int CELL = 16;                          // bytes per (square, 8-channel chunk)
+constexpr int RANK_B = TILE_POS * CELL;           // 256 B: one rank of the 16 boards (two core matrices)
+constexpr int CHUNK_B = 10 * RANK_B;              // 2 560 B: 10 padded ranks (= LBO)
+constexpr int PL_SLAB = 2 * CHUNK_B;              // 16 input channels of one file
+constexpr int A1_SLAB = 4 * CHUNK_B;              // 32 channels of one file
+constexpr int RP = 8, RA = 8;                     // slab rings
+constexpr int S1 = 4, S2 = 6;                     // TMEM slot rings
+constexpr int W1_TAP_BYTES = 32 * 16 * 2;
+constexpr int W2_TAP_BYTES = 64 * 32 * 2;
+constexpr int W1_BYTES = 9 * W1_TAP_BYTES;
+constexpr int W2_BYTES = 9 * W2_TAP_BYTES;
+
+constexpr int OFF_PLANES = 0;
+constexpr int OFF_ACT1 = OFF_PLANES + RP * PL_SLAB;
+constexpr int OFF_W1 = OFF_ACT1 + RA * A1_SLAB;
+constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
+constexpr int OFF_B2 = OFF_W2 + W2_BYTES;         // conv2 bias, 64 floats
+constexpr int OFF_BAR = OFF_B2 + 256;
+enum { B_W = 0, B_PL_FULL = 1, B_PL_EMPTY = B_PL_FULL + RP, B_C1_FULL = B_PL_EMPTY + RP, B_C1_EMPTY = B_C1_FULL + S1,
+       B_A1_FULL = B_C1_EMPTY + S1, B_A1_EMPTY = B_A1_FULL + RA, B_C2_FULL = B_A1_EMPTY + RA, B_C2_EMPTY = B_C2_FULL + S2,
+       B_COUNT = B_C2_EMPTY + S2 };
+constexpr int SMEM = OFF_BAR + B_COUNT * 8 + 16;
+static_assert(SMEM <= 227 * 1024, "conv stream kernel shared memory");
+static_assert(OFF_BAR % 8 == 0 && OFF_W1 % 128 == 0 && OFF_ACT1 % 128 == 0, "alignment");
+
+constexpr int THREADS = 14 * 32;
+constexpr int TM_C2 = 0;            // conv2 slot s: columns TM_C2 + 64 s
+constexpr int TM_C1 = 64 * S2;      // conv1 slot s: columns TM_C1 + 32 s
+static_assert(TM_C1 + 32 * S1 <= 512, "TMEM columns");
+
+// layout of the training copy of ReLU(conv1) (consumed by conv_bwd_kernel.cu): zero-bordered boards
+// per group of 8 positions, [4 chunks][10 ranks][8 positions][10 files][16 B]
+constexpr int TB_ROW = 160, TB_RANK = 8 * TB_ROW, TB_CHUNK = 10 * TB_RANK, TB_GROUP = 4 * TB_CHUNK;
+
+// ---------------------------------------------------------------- MMA issue of one source file step
+// A source file feeds output files x-1, x, x+1 (dx blocks 0, 1, 2 of the re-ordered weights) whose
+// TMEM slots d0, d1, d2 are consecutive except where the slot ring wraps.  The three taps of a kernel
+// row go out as ONE MMA of N = 3 BLK, or, at a wrap, as two MMAs on the same A (collector fill /
+// lastuse: 96 cycles either way, tests/cuda/umma_bw_probe.cu).  The first row of a step is also
+// split where "accumulate" changes: a slot touched for the first time starts from zero.
+//   FC   0 = first file of the tile (blocks 1, 2), 1 = middle, 2 = last file (blocks 0, 1)
+//   WRAP 0 = none, 1 = ring wraps between d0 and d1, 2 = between d1 and d2
+template <int BLK, int FC, int WRAP, bool FIRST>
+__device__ __forceinline__ void issue_row(uint32_t d0, uint32_t d1, uint32_t d2, uint64_t a, uint64_t b) {
+    constexpr uint64_t T = (BLK * 16) >> 4;      // one dx block of B in descriptor units
+    constexpr uint32_t I1 = make_idesc_f16(128, BLK), I2 = make_idesc_f16(128, 2 * BLK), I3 = make_idesc_f16(128, 3 * BLK);
+    if (FC == 0) {
+        if (WRAP != 2) umma_f16(d1, a, b + T, I2, !FIRST);
+        else { umma_f16_ca<0>(d1, a, b + T, I1, !FIRST); umma_f16_ca<2>(d2, a, b + 2 * T, I1, !FIRST); }
+    } else if (FC == 2) {
+        if (WRAP != 1) umma_f16(d0, a, b, I2, true);
+        else { umma_f16_ca<0>(d0, a, b, I1, true); umma_f16_ca<2>(d1, a, b + T, I1, true); }
+    } else if (FIRST) {
+        if (WRAP != 1) { umma_f16_ca<0>(d0, a, b, I2, true); umma_f16_ca<2>(d2, a, b + 2 * T, I1, false); }
+        else { umma_f16_ca<0>(d0, a, b, I1, true); umma_f16_ca<1>(d1, a, b + T, I1, true); umma_f16_ca<2>(d2, a, b + 2 * T, I1, false); }
+    } else {
+        if (WRAP == 0) umma_f16(d0, a, b, I3, true);
+        else if (WRAP == 1) { umma_f16_ca<0>(d0, a, b, I1, true); umma_f16_ca<2>(d1, a, b + T, I2, true); }
+        else { umma_f16_ca<0>(d0, a, b, I2, true); umma_f16_ca<2>(d2, a, b + 2 * T, I1, true); }
+    }
+}
+// all kernel rows of a step: 3 dy x NK K-slices of 16 channels
+template <int BLK, int NK, int FC, int WRAP>
+__device__ __forceinline__ void issue_rows(uint32_t d0, uint32_t d1, uint32_t d2, uint64_t a_base, uint64_t w_desc) {
+#pragma unroll
+    for (int dyi = 0; dyi < 3; dyi++) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            const uint64_t a = a_base + (uint64_t)((dyi * RANK_B + k * 2 * CHUNK_B) >> 4);
+            const uint64_t b = w_desc + (uint64_t)((dyi * NK * 2 * 3 * BLK * 16 + k * 2 * 3 * BLK * 16) >> 4);
+            if (dyi == 0 && k == 0) issue_row<BLK, FC, WRAP, true>(d0, d1, d2, a, b);
+            else issue_row<BLK, FC, WRAP, false>(d0, d1, d2, a, b);
+        }
+    }
+}
+template <int BLK, int NK>
+__device__ __forceinline__ void issue_step(int fc, int wrap, uint32_t d0, uint32_t d1, uint32_t d2, uint64_t a_base,
+                                           uint64_t w_desc) {
+    switch (fc * 3 + wrap) {
+        case 0: issue_rows<BLK, NK, 0, 0>(d0, d1, d2, a_base, w_desc); break;
+        case 1: issue_rows<BLK, NK, 0, 1>(d0, d1, d2, a_base, w_desc); break;
+        case 2: issue_rows<BLK, NK, 0, 2>(d0, d1, d2, a_base, w_desc); break;
+        case 3: issue_rows<BLK, NK, 1, 0>(d0, d1, d2, a_base, w_desc); break;
+        case 4: issue_rows<BLK, NK, 1, 1>(d0, d1, d2, a_base, w_desc); break;
+        case 5: issue_rows<BLK, NK, 1, 2>(d0, d1, d2, a_base, w_desc); break;
+        case 6: issue_rows<BLK, NK, 2, 0>(d0, d1, d2, a_base, w_desc); break;
+        case 7: issue_rows<BLK, NK, 2, 1>(d0, d1, d2, a_base, w_desc); break;
+        default: issue_rows<BLK, NK, 2, 2>(d0, d1, d2, a_base, w_desc); break;
+    }
+}
+
+#ifdef CDQ_TRACE
+// timeline study build (python chess-deep-q_b200/build.py -DCDQ_TRACE --out=libcdq_trace.so):
+// clock64 stamps of CTA 0, steps [TR_FROM, TR_FROM + 32), layout [role 4][step 32][tag 8]
+__device__ long long* g_trace;
+constexpr int TR_FROM = 96;
+#define TR(role, step, tag)                                                                             \
+    do {                                                                                                \
+        if (tr_buf && lane == 0 && (step) >= TR_FROM && (step) < TR_FROM + 32)                            \
+            tr_buf[((role) * 32 + (step) - TR_FROM) * 8 + (tag)] = clock64();                            \
+    } while (0)
+#else
+#define TR(role, step, tag) do {} while (0)
+#endif
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const PackedNet net,
+                   __half* __restrict__ act2, __half* __restrict__ dbg_act1, __half* __restrict__ act1_boards) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef CDQ_TRACE
+    long long* const tr_buf = blockIdx.x == 0 ? g_trace : nullptr;
+#endif
+
+    // ---- one-time setup: zero both slab rings (rank borders stay zero forever), barriers, weights
+    for (int i = tid; i < OFF_W1 / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 64) reinterpret_cast<float*>(smem + OFF_B2)[tid] = net.conv2_b[tid];
+    if (tid == 0) {
+        mbar_init(bars + B_W, 1);
+        for (int b = 0; b < RP; b++) { mbar_init(bars + B_PL_FULL + b, 4); mbar_init(bars + B_PL_EMPTY + b, 1); }
+        for (int b = 0; b < RA; b++) { mbar_init(bars + B_A1_FULL + b, 4); mbar_init(bars + B_A1_EMPTY + b, 1); }
+        for (int b = 0; b < S1; b++) { mbar_init(bars + B_C1_FULL + b, 1); mbar_init(bars + B_C1_EMPTY + b, 4); }
+        for (int b = 0; b < S2; b++) { mbar_init(bars + B_C2_FULL + b, 1); mbar_init(bars + B_C2_EMPTY + b, 4); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // weights: global order [tap = 3(dy+1) + (dx+1)][K chunk][n groups] -> shared memory order
+        // [dy][K chunk][dx = +1, 0, -1][n groups], so that the taps of one kernel row form ONE
+        // B operand of N = 3 x 64 (3 x 32) rows whose row order matches ascending output files
+        mbar_arrive_expect_tx(bars + B_W, W1_BYTES + W2_BYTES);
+        for (int dyi = 0; dyi < 3; dyi++)
+            for (int dxb = 0; dxb < 3; dxb++) {
+                const int tap = dyi * 3 + (2 - dxb);
+                for (int c = 0; c < 2; c++)
+                    bulk_g2s(smem + OFF_W1 + ((dyi * 2 + c) * 3 + dxb) * 512,
+                             reinterpret_cast<const uint8_t*>(net.w1p) + tap * W1_TAP_BYTES + c * 512, 512, bars + B_W);
+                for (int c = 0; c < 4; c++)
+                    bulk_g2s(smem + OFF_W2 + ((dyi * 4 + c) * 3 + dxb) * 1024,
+                             reinterpret_cast<const uint8_t*>(net.w2p) + tap * W2_TAP_BYTES + c * 1024, 1024, bars + B_W);
+            }
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // whole 128-position fc1 tiles are always written (missing boards count as empty boards)
+    const long long n_tiles = ((n + 127) >> 7) * (128 / TILE_POS);
+    const int n_local = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
+    const int G = 8 * n_local;                                                        // file steps of this CTA
+
+    if (warp <= 1) {
+        // =============================== MMA issuers: warp 0 conv1, warp 1 conv2 (warp-uniform control, one
+        // elected lane issues; two warps so that one's barrier waits overlap the other's queued MMAs)
+        mbar_wait_warp(lane, bars + B_W, 0);
+        const uint32_t smem_a = smem_u32(smem);
+        constexpr uint64_t A_HI = ((uint64_t)(128 >> 4) << 32) | (1ull << 46) | ((uint64_t)(CHUNK_B >> 4) << 16);
+        constexpr uint64_t B_HI = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+        // B operands: LBO = one K chunk of all three dx blocks
+        const uint64_t w1_desc = B_HI | ((uint64_t)(1536 >> 4) << 16) | (uint64_t)(((smem_a + OFF_W1) >> 4) & 0x3fff);
+        const uint64_t w2_desc = B_HI | ((uint64_t)(3072 >> 4) << 16) | (uint64_t)(((smem_a + OFF_W2) >> 4) & 0x3fff);
+
+        auto issue_c1 = [&](int g) {
+            const int f = g & 7, slab = g % RP;
+            TR(0, g, 0);
+            mbar_wait_warp(lane, bars + B_PL_FULL + slab, (g / RP) & 1);
+            TR(0, g, 1);
+            if (f == 0) mbar_wait_warp(lane, bars + B_C1_EMPTY + (g % S1), ((g / S1) & 1) ^ 1);
+            if (f < 7) mbar_wait_warp(lane, bars + B_C1_EMPTY + ((g + 1) % S1), (((g + 1) / S1) & 1) ^ 1);
+            tc_fence_after();
+            TR(0, g, 2);
+            if (elect_one_sync()) {
+                const uint64_t a_base = A_HI | (uint64_t)(((smem_a + OFF_PLANES + slab * PL_SLAB) >> 4) & 0x3fff);
+                const int s1 = g % S1;
+                issue_step<32, 1>(f == 0 ? 0 : f == 7 ? 2 : 1, s1 == 0 ? 1 : s1 == S1 - 1 ? 2 : 0,
+                                  tmem + TM_C1 + 32 * ((g + S1 - 1) % S1), tmem + TM_C1 + 32 * s1,
+                                  tmem + TM_C1 + 32 * ((g + 1) % S1), a_base, w1_desc);
+                umma_commit(bars + B_PL_EMPTY + slab);
+                if (f > 0) umma_commit(bars + B_C1_FULL + ((g - 1) % S1));
+                if (f == 7) umma_commit(bars + B_C1_FULL + (g % S1));
+            }
+            __syncwarp();
+        };
+        auto issue_c2 = [&](int g) {
+            const int f = g & 7, slab = g % RA;
+            TR(0, g, 3);
+            mbar_wait_warp(lane, bars + B_A1_FULL + slab, (g / RA) & 1);
+            TR(0, g, 4);
+            if (f == 0) mbar_wait_warp(lane, bars + B_C2_EMPTY + (g % S2), ((g / S2) & 1) ^ 1);
+            if (f < 7) mbar_wait_warp(lane, bars + B_C2_EMPTY + ((g + 1) % S2), (((g + 1) / S2) & 1) ^ 1);
+            tc_fence_after();
+            TR(0, g, 5);
+            if (elect_one_sync()) {
+                const uint64_t a_base = A_HI | (uint64_t)(((smem_a + OFF_ACT1 + slab * A1_SLAB) >> 4) & 0x3fff);
+                const int s1 = g % S2;
+                issue_step<64, 2>(f == 0 ? 0 : f == 7 ? 2 : 1, s1 == 0 ? 1 : s1 == S2 - 1 ? 2 : 0,
+                                  tmem + TM_C2 + 64 * ((g + S2 - 1) % S2), tmem + TM_C2 + 64 * s1,
+                                  tmem + TM_C2 + 64 * ((g + 1) % S2), a_base, w2_desc);
+                umma_commit(bars + B_A1_EMPTY + slab);
+                if (f > 0) umma_commit(bars + B_C2_FULL + ((g - 1) % S2));
+                if (f == 7) umma_commit(bars + B_C2_FULL + (g % S2));
+            }
+            __syncwarp();
+            TR(0, g, 6);
+        };
+        if (warp == 0) for (int g = 0; g < G; g++) issue_c1(g);
+        else for (int g = 0; g < G; g++) issue_c2(g);
+    } else if (warp <= 5) {
+        // =============================== plane encoder: thread = (rank r, position p)
+        const int e = tid - 64, r = e >> 4, p = e & 15;
+        const uint8_t* gb = reinterpret_cast<const uint8_t*>(boards);
+        // rank byte r of the 8 bitboards of one board, as channel-pair words: bit x of byte 0 /
+        // byte 2 = channel 2j / 2j+1 present on file x (channel = type + 6*black, board_utils.py:17-30)
+        auto fetch = [&](int i, unsigned (&pair)[6]) {
+            const long long pos = (blockIdx.x + (long long)i * gridDim.x) * TILE_POS + p;
+            unsigned b[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) b[t] = (i < n_local && pos < n) ? (unsigned)__ldg(gb + pos * 72 + t * 8 + r) : 0u;
+            const unsigned w = b[6], k = b[7] & ~b[6];
+            pair[0] = (b[0] & w) | ((b[1] & w) << 16);
+            pair[1] = (b[2] & w) | ((b[3] & w) << 16);
+            pair[2] = (b[4] & w) | ((b[5] & w) << 16);
+            pair[3] = (b[0] & k) | ((b[1] & k) << 16);
+            pair[4] = (b[2] & k) | ((b[3] & k) << 16);
+            pair[5] = (b[4] & k) | ((b[5] & k) << 16);
+        };
+        unsigned cur[6], nxt[6];
+        fetch(0, nxt);
+        uint8_t* dst0 = smem + OFF_PLANES + (r + 1) * RANK_B + p * CELL;
+        for (int i = 0; i < n_local; i++) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) cur[j] = nxt[j];
+            fetch(i + 1, nxt);                       // in flight during this tile's eight steps
+#pragma unroll 1
+            for (int f = 0; f < 8; f++) {
+                const int g = i * 8 + f, slab = g % RP;
+                TR(1, g, 0);
+                mbar_wait_warp(lane, bars + B_PL_EMPTY + slab, ((g / RP) & 1) ^ 1);
+                TR(1, g, 1);
+                unsigned w[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) w[j] = ((cur[j] >> f) & 0x00010001u) * 0x3C00u;   // fp16 1.0 per present channel
+                uint8_t* dst = dst0 + slab * PL_SLAB;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(dst + CHUNK_B) = make_uint4(w[4], w[5], 0x3C00u, 0u);   // channel 12: constant one
+                TR(1, g, 2);
+                fence_proxy_async();
+                __syncwarp();
+                TR(1, g, 3);
+                if (lane == 0) mbar_arrive(bars + B_PL_FULL + slab);
+            }
+        }
+    } else if (warp <= 9) {
+        // =============================== epilogue 1: conv1 slot -> act1 slab
+        const int q = warp & 3;
+        const int y = 2 * q + (lane >> 4), p = lane & 15;      // TMEM lane 32q + lane = row (rank y, position p)
+        uint8_t* dst0 = smem + OFF_ACT1 + (y + 1) * RANK_B + p * CELL;
+#pragma unroll 1
+        for (int o = 0; o < G; o++) {
+            const int slot = o % S1, slab = o % RA, f = o & 7;
+            TR(2, o, 0);
+            mbar_wait_warp(lane, bars + B_C1_FULL + slot, (o / S1) & 1);
+            tc_fence_after();
+            TR(2, o, 1);
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_C1 + 32 * slot, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + B_C1_EMPTY + slot);
+            TR(2, o, 2);
+            mbar_wait_warp(lane, bars + B_A1_EMPTY + slab, ((o / RA) & 1) ^ 1);   // conv2 has read this slab's last use
+            TR(2, o, 3);
+            uint8_t* dst = dst0 + slab * A1_SLAB;
+            const long long pos = (blockIdx.x + (long long)(o >> 3) * gridDim.x) * TILE_POS + p;
+#pragma unroll
+            for (int kc = 0; kc < 4; kc++) {
+                uint4 u;
+                u.x = relu_pack_f16(__uint_as_float(v[kc * 8 + 0]), __uint_as_float(v[kc * 8 + 1]));
+                u.y = relu_pack_f16(__uint_as_float(v[kc * 8 + 2]), __uint_as_float(v[kc * 8 + 3]));
+                u.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]), __uint_as_float(v[kc * 8 + 5]));
+                u.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]), __uint_as_float(v[kc * 8 + 7]));
+                *reinterpret_cast<uint4*>(dst + kc * CHUNK_B) = u;
+                if (act1_boards)   // training: ReLU(conv1) as zero-bordered boards for conv2's backward pass
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 3) * TB_GROUP + kc * TB_CHUNK +
+                                              (y + 1) * TB_RANK + (int)(pos & 7) * TB_ROW + (f + 1) * CELL) = u;
+                if (dbg_act1 && pos < n)
+                    *reinterpret_cast<uint4*>(dbg_act1 + (pos * 64 + y * 8 + f) * 32 + kc * 8) = u;
+            }
+            TR(2, o, 4);
+            fence_proxy_async();
+            __syncwarp();
+            TR(2, o, 5);
+            if (lane == 0) mbar_arrive(bars + B_A1_FULL + slab);
+        }
+    } else {
+        // =============================== epilogue 2: conv2 slot -> global (fc1 A-tile order)
+        const int q = warp & 3;
+        const int y = 2 * q + (lane >> 4), p = lane & 15;
+        float4 b2r[16];   // conv2 bias, kept in registers for the whole kernel
+#pragma unroll
+        for (int k = 0; k < 16; k++) b2r[k] = reinterpret_cast<const float4*>(smem + OFF_B2)[k];
+#pragma unroll 1
+        for (int o = 0; o < G; o++) {
+            const int slot = o % S2, f = o & 7;
+            TR(3, o, 0);
+            mbar_wait_warp(lane, bars + B_C2_FULL + slot, (o / S2) & 1);
+            tc_fence_after();
+            TR(3, o, 1);
+            uint32_t v0[32], v1[32];
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + 64 * slot;
+            tmem_ld32(ta, v0);
+            tmem_ld32(ta + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + B_C2_EMPTY + slot);
+            TR(3, o, 2);
+            const long long pos = (blockIdx.x + (long long)(o >> 3) * gridDim.x) * TILE_POS + p;
+            const int pr = (int)(pos & 127);
+            // 16 KB block per (128-position tile, square): [8 channel chunks][16 row groups][8 rows][8 halfs]
+            uint8_t* dst = reinterpret_cast<uint8_t*>(act2) + ((pos >> 7) << 20) + ((long long)(y * 8 + f) << 14) +
+                           (pr >> 3) * 128 + (pr & 7) * 16;
+#pragma unroll
+            for (int kc = 0; kc < 8; kc++) {
+                const uint32_t* v = kc < 4 ? v0 + kc * 8 : v1 + (kc - 4) * 8;
+                const float4 ba = b2r[kc * 2], bb = b2r[kc * 2 + 1];
+                uint4 u;
+                u.x = relu_pack_f16(__uint_as_float(v[0]) + ba.x, __uint_as_float(v[1]) + ba.y);
+                u.y = relu_pack_f16(__uint_as_float(v[2]) + ba.z, __uint_as_float(v[3]) + ba.w);
+                u.z = relu_pack_f16(__uint_as_float(v[4]) + bb.x, __uint_as_float(v[5]) + bb.y);
+                u.w = relu_pack_f16(__uint_as_float(v[6]) + bb.z, __uint_as_float(v[7]) + bb.w);
+                *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
+            }
+            TR(3, o, 3);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+} // namespace cs
+
+#ifdef CDQ_TRACE
+extern "C" int cdq_debug_set_trace(long long* d_buf) {
+    return (int)cudaMemcpyToSymbol(cs::g_trace, &d_buf, sizeof(d_buf));
+}
+#endif
+
+int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
+                      cudaStream_t st, __half* act1_boards) {
+    if (n == 0) return 0;
+    static const bool use_v1 = getenv("CDQ_CONV_V1") != nullptr;   // A/B switch, see conv_kernel.cu
+    if (use_v1) return launch_conv_stack_v1(boards, n, net, act2, dbg_act1, st, act1_boards);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(cs::conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cs::SMEM);
+        attr_set = true;
+    }
+    const long long tiles = ((n + 127) >> 7) * (128 / cs::TILE_POS);
+    const int sms = device_sm_count();
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    ProfileScope ps(KK_CONV, st);
+    cs::conv_stream_kernel<<<grid, cs::THREADS, cs::SMEM, st>>>(boards, n, net, act2, dbg_act1, act1_boards);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+} // namespace cdq

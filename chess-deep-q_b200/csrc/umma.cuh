@@ -114,6 +114,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// A-collector form: consecutive MMAs that read the SAME A operand keep it in the collector
+// instead of fetching it from shared memory again.  MODE 0 = fill, 1 = use, 2 = lastuse.
+// Measured (tests/cuda/umma_bw_probe.cu): N=64 + N=128 on one A cost 96 cycles with
+// fill/lastuse (= one N=192 MMA, the math floor) against 112 without the hint.
+template <int MODE>
+__device__ __forceinline__ void umma_f16_ca(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+#define CDQ_CA_ASM(M)                                                                                    \
+    asm volatile(                                                                                        \
+        "{\n\t.reg .pred p;\n\t"                                                                         \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                                      \
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::" M " [%0], %1, %2, %3, p;\n\t}"               \
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory")
+    if (MODE == 0) CDQ_CA_ASM("fill");
+    else if (MODE == 1) CDQ_CA_ASM("use");
+    else CDQ_CA_ASM("lastuse");
+#undef CDQ_CA_ASM
+}
 // Weight-stationary form: B is held in collector buffer b0 across MMAs.  MODE 0 = fill (read B
 // from shared memory and keep it), 1 = use (reuse the kept B), 2 = lastuse, 3 = discard.
 template <int MODE>
