@@ -23,7 +23,7 @@
 //     warp 0, 1     MMA issuers: conv1(g) and conv2(g), each paced only by its own barriers
 //     warps 2-5     plane encoder: thread = (rank, position), one square per step
 //     warps 6-9     epilogue 1: conv1 slot -> ReLU -> fp16 -> act1 slab (+ optional training copies)
-//     warps 10-13   epilogue 2: conv2 slot -> +bias -> ReLU -> fp16 -> global, fc1 tile order
+//     warps 10-17   epilogue 2 (two groups of four, one per half of the output channels): conv2 slot -> +bias -> ReLU -> fp16 -> global, fc1 tile order
 //
 // Algorithmic work: 2 801 664 FLOP/position (dense convention);
 // traffic 72 B in + 8 192 B out per position.
@@ -63,7 +63,7 @@ constexpr int SMEM = OFF_BAR + B_COUNT * 8 + 16;
 static_assert(SMEM <= 227 * 1024, "conv stream kernel shared memory");
 static_assert(OFF_BAR % 8 == 0 && OFF_W1 % 128 == 0 && OFF_ACT1 % 128 == 0, "alignment");
 
-constexpr int THREADS = 14 * 32;
+constexpr int THREADS = 18 * 32;
 constexpr int TM_C2 = 0;            // conv2 slot s: columns TM_C2 + 64 s
 constexpr int TM_C1 = 64 * S2;      // conv1 slot s: columns TM_C1 + 32 s
 static_assert(TM_C1 + 32 * S1 <= 512, "TMEM columns");
@@ -100,12 +100,13 @@ __device__ __forceinline__ void issue_row(uint32_t d0, uint32_t d1, uint32_t d2,
     }
 }
 // all kernel rows of a step: 3 dy x NK K-slices of 16 channels
-template <int BLK, int NK, int FC, int WRAP>
+template <int BLK, int NK, int FC, int WRAP, int R0, int R1>
 __device__ __forceinline__ void issue_rows(uint32_t d0, uint32_t d1, uint32_t d2, uint64_t a_base, uint64_t w_desc) {
 #pragma unroll
     for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
         for (int k = 0; k < NK; k++) {
+            if (dyi * NK + k < R0 || dyi * NK + k >= R1) continue;   // rows [R0, R1) of the step
             const uint64_t a = a_base + (uint64_t)((dyi * RANK_B + k * 2 * CHUNK_B) >> 4);
             const uint64_t b = w_desc + (uint64_t)((dyi * NK * 2 * 3 * BLK * 16 + k * 2 * 3 * BLK * 16) >> 4);
             if (dyi == 0 && k == 0) issue_row<BLK, FC, WRAP, true>(d0, d1, d2, a, b);
@@ -113,20 +114,78 @@ __device__ __forceinline__ void issue_rows(uint32_t d0, uint32_t d1, uint32_t d2
         }
     }
 }
-template <int BLK, int NK>
-__device__ __forceinline__ void issue_step(int fc, int wrap, uint32_t d0, uint32_t d1, uint32_t d2, uint64_t a_base,
-                                           uint64_t w_desc) {
-    switch (fc * 3 + wrap) {
-        case 0: issue_rows<BLK, NK, 0, 0>(d0, d1, d2, a_base, w_desc); break;
-        case 1: issue_rows<BLK, NK, 0, 1>(d0, d1, d2, a_base, w_desc); break;
-        case 2: issue_rows<BLK, NK, 0, 2>(d0, d1, d2, a_base, w_desc); break;
-        case 3: issue_rows<BLK, NK, 1, 0>(d0, d1, d2, a_base, w_desc); break;
-        case 4: issue_rows<BLK, NK, 1, 1>(d0, d1, d2, a_base, w_desc); break;
-        case 5: issue_rows<BLK, NK, 1, 2>(d0, d1, d2, a_base, w_desc); break;
-        case 6: issue_rows<BLK, NK, 2, 0>(d0, d1, d2, a_base, w_desc); break;
-        case 7: issue_rows<BLK, NK, 2, 1>(d0, d1, d2, a_base, w_desc); break;
-        default: issue_rows<BLK, NK, 2, 2>(d0, d1, d2, a_base, w_desc); break;
+// ---------------------------------------------------------------- one file step of an issuer, all indices
+// compile-time.  The issuers' control flow repeats with period lcm(8 files, ring sizes): 8 steps
+// for conv1 (slabs 8, slots 4), 24 steps for conv2 (slabs 8, slots 6).  J is the step inside that
+// period, so barrier numbers, TMEM slots, operand offsets and the MMA segmentation are immediates
+// and a step costs a few dozen instructions.  (A first version computed them at run time --
+// g % 6, a 9-way switch, descriptors through R2UR -- and the issuing warps, not the tensor pipe,
+// set the pace: 1 650 cycles per step for 760 cycles of MMAs, ncu tensor pipe 48 %.)
+struct IssueCtx {
+    uint64_t* bars;
+    uint32_t tmem;
+    uint64_t a1_desc, a2_desc, w1_desc, w2_desc;   // descriptors of planes slab 0 / act1 slab 0 / re-ordered weights
+    int lane;
+};
+__device__ __forceinline__ void wait_bar(const IssueCtx& c, int bar, uint32_t parity) { mbar_wait_warp(c.lane, c.bars + bar, parity); }
+
+// conv1: J = file of the tile; `odd` = parity of the tile index (the planes ring turns once per tile)
+template <int J>
+__device__ __forceinline__ void c1_ready(const IssueCtx& c, uint32_t odd) {
+    wait_bar(c, B_PL_FULL + J, odd);
+    if (J == 0) wait_bar(c, B_C1_EMPTY + 0, 1);                      // output file 0 of a tile: slot 0, an even use
+    if (J < 7) wait_bar(c, B_C1_EMPTY + (J + 1) % S1, (((J + 1) / S1) & 1) ^ 1);
+    tc_fence_after();
+}
+template <int J>
+__device__ __forceinline__ void c1_step(const IssueCtx& c, uint32_t odd, bool more) {
+    static_assert(RP == 8 && S1 == 4, "conv1 issuer period");
+    constexpr int FC = J == 0 ? 0 : J == 7 ? 2 : 1, SL = J % S1, WR = SL == 0 ? 1 : SL == S1 - 1 ? 2 : 0;
+    const uint64_t a = c.a1_desc + (uint64_t)((J * PL_SLAB) >> 4);
+    const uint32_t d0 = c.tmem + TM_C1 + 32 * ((J + S1 - 1) % S1), d1 = c.tmem + TM_C1 + 32 * SL, d2 = c.tmem + TM_C1 + 32 * ((J + 1) % S1);
+    if (elect_one_sync()) issue_rows<32, 1, FC, WR, 0, 2>(d0, d1, d2, a, c.w1_desc);
+    __syncwarp();
+    if (J < 7) c1_ready<(J + 1) & 7>(c, odd);
+    else if (more) c1_ready<0>(c, odd ^ 1);
+    if (elect_one_sync()) {
+        issue_rows<32, 1, FC, WR, 2, 3>(d0, d1, d2, a, c.w1_desc);
+        umma_commit(c.bars + B_PL_EMPTY + J);
+        if (J > 0) umma_commit(c.bars + B_C1_FULL + (J - 1) % S1);
+        if (J == 7) umma_commit(c.bars + B_C1_FULL + SL);
     }
+    __syncwarp();
+}
+// conv2: J = step inside three tiles; `odd` = parity of the three-tile group index
+template <int J>
+__device__ __forceinline__ void c2_ready(const IssueCtx& c, uint32_t odd) {
+    wait_bar(c, B_A1_FULL + (J & 7), odd ^ ((J >> 3) & 1));          // act1 ring: use = 3 group + J/8
+    if ((J & 7) == 0) wait_bar(c, B_C2_EMPTY + J % S2, ((J / S2) & 1) ^ 1);   // slot ring: use = 4 group + J/6
+    if ((J & 7) < 7) wait_bar(c, B_C2_EMPTY + (J + 1) % S2, (((J + 1) / S2) & 1) ^ 1);
+    tc_fence_after();
+}
+template <int J>
+__device__ __forceinline__ void c2_step(const IssueCtx& c, uint32_t odd, bool more) {
+    static_assert(RA == 8 && S2 == 6, "conv2 issuer period");
+    constexpr int F = J & 7, FC = F == 0 ? 0 : F == 7 ? 2 : 1, SL = J % S2, WR = SL == 0 ? 1 : SL == S2 - 1 ? 2 : 0;
+    const uint64_t a = c.a2_desc + (uint64_t)((F * A1_SLAB) >> 4);
+    const uint32_t d0 = c.tmem + TM_C2 + 64 * ((J + S2 - 1) % S2), d1 = c.tmem + TM_C2 + 64 * SL, d2 = c.tmem + TM_C2 + 64 * ((J + 1) % S2);
+    if (elect_one_sync()) issue_rows<64, 2, FC, WR, 0, 4>(d0, d1, d2, a, c.w2_desc);
+    __syncwarp();
+    if (F < 7) c2_ready<(J + 1) % 24>(c, odd);
+    else if (more) c2_ready<(J + 1) % 24>(c, J == 23 ? odd ^ 1 : odd);
+    if (elect_one_sync()) {
+        issue_rows<64, 2, FC, WR, 4, 6>(d0, d1, d2, a, c.w2_desc);
+        umma_commit(c.bars + B_A1_EMPTY + F);
+        if (F > 0) umma_commit(c.bars + B_C2_FULL + (J + S2 - 1) % S2);
+        if (F == 7) umma_commit(c.bars + B_C2_FULL + SL);
+    }
+    __syncwarp();
+}
+template <int T>   // the eight steps of tile T (0..2) of a three-tile group
+__device__ __forceinline__ void c2_tile(const IssueCtx& c, uint32_t odd, bool more) {
+    c2_step<8 * T + 0>(c, odd, true); c2_step<8 * T + 1>(c, odd, true); c2_step<8 * T + 2>(c, odd, true);
+    c2_step<8 * T + 3>(c, odd, true); c2_step<8 * T + 4>(c, odd, true); c2_step<8 * T + 5>(c, odd, true);
+    c2_step<8 * T + 6>(c, odd, true); c2_step<8 * T + 7>(c, odd, more);
 }
 
 #ifdef CDQ_TRACE
@@ -162,7 +221,7 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
         for (int b = 0; b < RP; b++) { mbar_init(bars + B_PL_FULL + b, 4); mbar_init(bars + B_PL_EMPTY + b, 1); }
         for (int b = 0; b < RA; b++) { mbar_init(bars + B_A1_FULL + b, 4); mbar_init(bars + B_A1_EMPTY + b, 1); }
         for (int b = 0; b < S1; b++) { mbar_init(bars + B_C1_FULL + b, 1); mbar_init(bars + B_C1_EMPTY + b, 4); }
-        for (int b = 0; b < S2; b++) { mbar_init(bars + B_C2_FULL + b, 1); mbar_init(bars + B_C2_EMPTY + b, 4); }
+        for (int b = 0; b < S2; b++) { mbar_init(bars + B_C2_FULL + b, 1); mbar_init(bars + B_C2_EMPTY + b, 8); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -201,55 +260,36 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
         const uint32_t smem_a = smem_u32(smem);
         constexpr uint64_t A_HI = ((uint64_t)(128 >> 4) << 32) | (1ull << 46) | ((uint64_t)(CHUNK_B >> 4) << 16);
         constexpr uint64_t B_HI = ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+        IssueCtx c;
+        c.bars = bars; c.tmem = tmem; c.lane = lane;
+        c.a1_desc = A_HI | (uint64_t)(((smem_a + OFF_PLANES) >> 4) & 0x3fff);
+        c.a2_desc = A_HI | (uint64_t)(((smem_a + OFF_ACT1) >> 4) & 0x3fff);
         // B operands: LBO = one K chunk of all three dx blocks
-        const uint64_t w1_desc = B_HI | ((uint64_t)(1536 >> 4) << 16) | (uint64_t)(((smem_a + OFF_W1) >> 4) & 0x3fff);
-        const uint64_t w2_desc = B_HI | ((uint64_t)(3072 >> 4) << 16) | (uint64_t)(((smem_a + OFF_W2) >> 4) & 0x3fff);
-
-        auto issue_c1 = [&](int g) {
-            const int f = g & 7, slab = g % RP;
-            TR(0, g, 0);
-            mbar_wait_warp(lane, bars + B_PL_FULL + slab, (g / RP) & 1);
-            TR(0, g, 1);
-            if (f == 0) mbar_wait_warp(lane, bars + B_C1_EMPTY + (g % S1), ((g / S1) & 1) ^ 1);
-            if (f < 7) mbar_wait_warp(lane, bars + B_C1_EMPTY + ((g + 1) % S1), (((g + 1) / S1) & 1) ^ 1);
-            tc_fence_after();
-            TR(0, g, 2);
-            if (elect_one_sync()) {
-                const uint64_t a_base = A_HI | (uint64_t)(((smem_a + OFF_PLANES + slab * PL_SLAB) >> 4) & 0x3fff);
-                const int s1 = g % S1;
-                issue_step<32, 1>(f == 0 ? 0 : f == 7 ? 2 : 1, s1 == 0 ? 1 : s1 == S1 - 1 ? 2 : 0,
-                                  tmem + TM_C1 + 32 * ((g + S1 - 1) % S1), tmem + TM_C1 + 32 * s1,
-                                  tmem + TM_C1 + 32 * ((g + 1) % S1), a_base, w1_desc);
-                umma_commit(bars + B_PL_EMPTY + slab);
-                if (f > 0) umma_commit(bars + B_C1_FULL + ((g - 1) % S1));
-                if (f == 7) umma_commit(bars + B_C1_FULL + (g % S1));
+        c.w1_desc = B_HI | ((uint64_t)(1536 >> 4) << 16) | (uint64_t)(((smem_a + OFF_W1) >> 4) & 0x3fff);
+        c.w2_desc = B_HI | ((uint64_t)(3072 >> 4) << 16) | (uint64_t)(((smem_a + OFF_W2) >> 4) & 0x3fff);
+        // Both issuers take the barrier waits of step g+1 in the MIDDLE of step g's MMAs, so the
+        // tensor pipe always has queued work while the issuing thread waits.
+        if (warp == 0) {
+            if (n_local > 0) c1_ready<0>(c, 0);
+            for (int i = 0; i < n_local; i++) {
+                const uint32_t odd = i & 1;
+                TR(0, 8 * i, 0);
+                c1_step<0>(c, odd, true); c1_step<1>(c, odd, true); c1_step<2>(c, odd, true); c1_step<3>(c, odd, true);
+                c1_step<4>(c, odd, true); c1_step<5>(c, odd, true); c1_step<6>(c, odd, true);
+                c1_step<7>(c, odd, i + 1 < n_local);
             }
-            __syncwarp();
-        };
-        auto issue_c2 = [&](int g) {
-            const int f = g & 7, slab = g % RA;
-            TR(0, g, 3);
-            mbar_wait_warp(lane, bars + B_A1_FULL + slab, (g / RA) & 1);
-            TR(0, g, 4);
-            if (f == 0) mbar_wait_warp(lane, bars + B_C2_EMPTY + (g % S2), ((g / S2) & 1) ^ 1);
-            if (f < 7) mbar_wait_warp(lane, bars + B_C2_EMPTY + ((g + 1) % S2), (((g + 1) / S2) & 1) ^ 1);
-            tc_fence_after();
-            TR(0, g, 5);
-            if (elect_one_sync()) {
-                const uint64_t a_base = A_HI | (uint64_t)(((smem_a + OFF_ACT1 + slab * A1_SLAB) >> 4) & 0x3fff);
-                const int s1 = g % S2;
-                issue_step<64, 2>(f == 0 ? 0 : f == 7 ? 2 : 1, s1 == 0 ? 1 : s1 == S2 - 1 ? 2 : 0,
-                                  tmem + TM_C2 + 64 * ((g + S2 - 1) % S2), tmem + TM_C2 + 64 * s1,
-                                  tmem + TM_C2 + 64 * ((g + 1) % S2), a_base, w2_desc);
-                umma_commit(bars + B_A1_EMPTY + slab);
-                if (f > 0) umma_commit(bars + B_C2_FULL + ((g - 1) % S2));
-                if (f == 7) umma_commit(bars + B_C2_FULL + (g % S2));
+        } else {
+            if (n_local > 0) c2_ready<0>(c, 0);
+            for (int i = 0, grp = 0; i < n_local; i += 3, grp++) {
+                const uint32_t odd = grp & 1;
+                TR(0, 8 * i, 3);
+                c2_tile<0>(c, odd, i + 1 < n_local);
+                TR(0, 8 * i + 8, 3);
+                if (i + 1 < n_local) c2_tile<1>(c, odd, i + 2 < n_local);
+                TR(0, 8 * i + 16, 3);
+                if (i + 2 < n_local) c2_tile<2>(c, odd, i + 3 < n_local);
             }
-            __syncwarp();
-            TR(0, g, 6);
-        };
-        if (warp == 0) for (int g = 0; g < G; g++) issue_c1(g);
-        else for (int g = 0; g < G; g++) issue_c2(g);
+        }
     } else if (warp <= 5) {
         // =============================== plane encoder: thread = (rank r, position p)
         const int e = tid - 64, r = e >> 4, p = e & 15;
@@ -339,12 +379,13 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
             if (lane == 0) mbar_arrive(bars + B_A1_FULL + slab);
         }
     } else {
-        // =============================== epilogue 2: conv2 slot -> global (fc1 A-tile order)
-        const int q = warp & 3;
+        // =============================== epilogue 2: conv2 slot -> global (fc1 A-tile order); eight warps,
+        // warps 10-13 take output channels 0-31, warps 14-17 channels 32-63 of every output file
+        const int q = warp & 3, hh = (warp - 10) >> 2;
         const int y = 2 * q + (lane >> 4), p = lane & 15;
-        float4 b2r[16];   // conv2 bias, kept in registers for the whole kernel
+        float4 b2r[8];    // this half's conv2 bias, kept in registers for the whole kernel
 #pragma unroll
-        for (int k = 0; k < 16; k++) b2r[k] = reinterpret_cast<const float4*>(smem + OFF_B2)[k];
+        for (int k = 0; k < 8; k++) b2r[k] = reinterpret_cast<const float4*>(smem + OFF_B2)[hh * 8 + k];
 #pragma unroll 1
         for (int o = 0; o < G; o++) {
             const int slot = o % S2, f = o & 7;
@@ -352,10 +393,8 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
             mbar_wait_warp(lane, bars + B_C2_FULL + slot, (o / S2) & 1);
             tc_fence_after();
             TR(3, o, 1);
-            uint32_t v0[32], v1[32];
-            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + 64 * slot;
-            tmem_ld32(ta, v0);
-            tmem_ld32(ta + 32, v1);
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + 64 * slot + 32 * hh, v);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -365,17 +404,20 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
             const int pr = (int)(pos & 127);
             // 16 KB block per (128-position tile, square): [8 channel chunks][16 row groups][8 rows][8 halfs]
             uint8_t* dst = reinterpret_cast<uint8_t*>(act2) + ((pos >> 7) << 20) + ((long long)(y * 8 + f) << 14) +
-                           (pr >> 3) * 128 + (pr & 7) * 16;
+                           (pr >> 3) * 128 + (pr & 7) * 16 + hh * 4 * 2048;
 #pragma unroll
-            for (int kc = 0; kc < 8; kc++) {
-                const uint32_t* v = kc < 4 ? v0 + kc * 8 : v1 + (kc - 4) * 8;
+            for (int kc = 0; kc < 4; kc++) {
                 const float4 ba = b2r[kc * 2], bb = b2r[kc * 2 + 1];
                 uint4 u;
-                u.x = relu_pack_f16(__uint_as_float(v[0]) + ba.x, __uint_as_float(v[1]) + ba.y);
-                u.y = relu_pack_f16(__uint_as_float(v[2]) + ba.z, __uint_as_float(v[3]) + ba.w);
-                u.z = relu_pack_f16(__uint_as_float(v[4]) + bb.x, __uint_as_float(v[5]) + bb.y);
-                u.w = relu_pack_f16(__uint_as_float(v[6]) + bb.z, __uint_as_float(v[7]) + bb.w);
+                u.x = relu_pack_f16(__uint_as_float(v[kc * 8 + 0]) + ba.x, __uint_as_float(v[kc * 8 + 1]) + ba.y);
+                u.y = relu_pack_f16(__uint_as_float(v[kc * 8 + 2]) + ba.z, __uint_as_float(v[kc * 8 + 3]) + ba.w);
+                u.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]) + bb.x, __uint_as_float(v[kc * 8 + 5]) + bb.y);
+                u.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]) + bb.z, __uint_as_float(v[kc * 8 + 7]) + bb.w);
+#ifndef CDQ_EXP_NOSTORE   // A/B experiment only: how much of the kernel time is the act2 write stream
                 *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
+#else
+                if (u.x == 0x12345678u) *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
+#endif
             }
             TR(3, o, 3);
         }

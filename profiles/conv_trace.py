@@ -37,7 +37,7 @@ for it in range(3):
 t = trace.cpu().numpy().reshape(4, 32, 8)
 t0 = t[t > 0].min()
 rel = np.where(t > 0, t - t0, -1)
-names = ["MMA   0 c1.wait 1 planes.ok 2 c1.slots.ok(issue c1) 3 c2.wait 4 act1.ok 5 c2.slots.ok(issue c2) 6 issued",
+names = ["MMA   c1: 0 step 1 rows0-1.issued 2 next.ready / c2: 3 step 4 rows0-3.issued 5 next.ready 6 rest.issued",
          "ENC   0 wait 1 slab.free 2 stored 3 fenced",
          "EPI1  0 wait 1 c1.full 2 loaded 3 slab.free 4 stored 5 fenced",
          "EPI2  0 wait 1 c2.full 2 loaded 3 stored"]
@@ -47,8 +47,7 @@ for r in range(4):
         row = rel[r, s]
         if (row >= 0).sum() == 0:
             continue
-        d = [int(row[k + 1] - row[k]) if row[k + 1] >= 0 and row[k] >= 0 else -1 for k in range(7)]
-        print("  step %3d  start %7d  deltas %s" % (s, int(row[0]), " ".join("%5d" % x for x in d if x != -1)))
+        print("  step %3d  abs %s" % (s, " ".join("%7d" % x for x in row)))
     starts = rel[r, :, 0]
     ok = starts[starts >= 0]
     if len(ok) > 1:
