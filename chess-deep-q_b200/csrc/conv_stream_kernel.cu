@@ -22,8 +22,9 @@
 //   issued.  Warp roles (all hand-overs by mbarriers):
 //     warp 0, 1     MMA issuers: conv1(g) and conv2(g), each paced only by its own barriers
 //     warps 2-5     plane encoder: thread = (rank, position), one square per step
-//     warps 6-9     epilogue 1: conv1 slot -> ReLU -> fp16 -> act1 slab (+ optional training copies)
-//     warps 10-17   epilogue 2 (two groups of four, one per half of the output channels): conv2 slot -> +bias -> ReLU -> fp16 -> global, fc1 tile order
+//     warps 6-13    epilogue 1 (two groups of four, alternating output files): conv1 slot -> ReLU ->
+//                   fp16 -> act1 slab (+ optional training copies)
+//     warps 14-21   epilogue 2 (two groups of four, one per half of the output channels): conv2 slot -> +bias -> ReLU -> fp16 -> global, fc1 tile order
 //
 // Algorithmic work: 2 801 664 FLOP/position (dense convention);
 // traffic 72 B in + 8 192 B out per position.
@@ -63,7 +64,7 @@ constexpr int SMEM = OFF_BAR + B_COUNT * 8 + 16;
 static_assert(SMEM <= 227 * 1024, "conv stream kernel shared memory");
 static_assert(OFF_BAR % 8 == 0 && OFF_W1 % 128 == 0 && OFF_ACT1 % 128 == 0, "alignment");
 
-constexpr int THREADS = 18 * 32;
+constexpr int THREADS = 22 * 32;
 constexpr int TM_C2 = 0;            // conv2 slot s: columns TM_C2 + 64 s
 constexpr int TM_C1 = 64 * S2;      // conv1 slot s: columns TM_C1 + 32 s
 static_assert(TM_C1 + 32 * S1 <= 512, "TMEM columns");
@@ -335,13 +336,15 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
                 if (lane == 0) mbar_arrive(bars + B_PL_FULL + slab);
             }
         }
-    } else if (warp <= 9) {
-        // =============================== epilogue 1: conv1 slot -> act1 slab
+    } else if (warp <= 13) {
+        // =============================== epilogue 1: conv1 slot -> act1 slab; two groups of four warps,
+        // warps 6-9 take the even output files, warps 10-13 the odd ones (a step's fixed latencies --
+        // barrier polls, tcgen05.ld, proxy fence -- add up to more than the 760-cycle MMA budget)
         const int q = warp & 3;
         const int y = 2 * q + (lane >> 4), p = lane & 15;      // TMEM lane 32q + lane = row (rank y, position p)
         uint8_t* dst0 = smem + OFF_ACT1 + (y + 1) * RANK_B + p * CELL;
 #pragma unroll 1
-        for (int o = 0; o < G; o++) {
+        for (int o = (warp - 6) >> 2; o < G; o += 2) {
             const int slot = o % S1, slab = o % RA, f = o & 7;
             TR(2, o, 0);
             mbar_wait_warp(lane, bars + B_C1_FULL + slot, (o / S1) & 1);
@@ -380,8 +383,8 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
         }
     } else {
         // =============================== epilogue 2: conv2 slot -> global (fc1 A-tile order); eight warps,
-        // warps 10-13 take output channels 0-31, warps 14-17 channels 32-63 of every output file
-        const int q = warp & 3, hh = (warp - 10) >> 2;
+        // warps 14-17 take output channels 0-31, warps 18-21 channels 32-63 of every output file
+        const int q = warp & 3, hh = (warp - 14) >> 2;
         const int y = 2 * q + (lane >> 4), p = lane & 15;
         float4 b2r[8];    // this half's conv2 bias, kept in registers for the whole kernel
 #pragma unroll
