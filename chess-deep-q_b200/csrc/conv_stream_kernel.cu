@@ -360,7 +360,8 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
             mbar_wait_warp(lane, bars + B_A1_EMPTY + slab, ((o / RA) & 1) ^ 1);   // conv2 has read this slab's last use
             TR(2, o, 3);
             uint8_t* dst = dst0 + slab * A1_SLAB;
-            const long long pos = (blockIdx.x + (long long)(o >> 3) * gridDim.x) * TILE_POS + p;
+            long long pos = 0;
+            if (act1_boards || dbg_act1) pos = (blockIdx.x + (long long)(o >> 3) * gridDim.x) * TILE_POS + p;
 #pragma unroll
             for (int kc = 0; kc < 4; kc++) {
                 uint4 u;
@@ -389,40 +390,46 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
         float4 b2r[8];    // this half's conv2 bias, kept in registers for the whole kernel
 #pragma unroll
         for (int k = 0; k < 8; k++) b2r[k] = reinterpret_cast<const float4*>(smem + OFF_B2)[hh * 8 + k];
+        int slot = 0;            // ring position and phase parity of the next output file
+        uint32_t phase = 0;
 #pragma unroll 1
-        for (int o = 0; o < G; o++) {
-            const int slot = o % S2, f = o & 7;
-            TR(3, o, 0);
-            mbar_wait_warp(lane, bars + B_C2_FULL + slot, (o / S2) & 1);
-            tc_fence_after();
-            TR(3, o, 1);
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + 64 * slot + 32 * hh, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + B_C2_EMPTY + slot);
-            TR(3, o, 2);
-            const long long pos = (blockIdx.x + (long long)(o >> 3) * gridDim.x) * TILE_POS + p;
+        for (int i = 0; i < n_local; i++) {
+            const long long pos = (blockIdx.x + (long long)i * gridDim.x) * TILE_POS + p;
             const int pr = (int)(pos & 127);
             // 16 KB block per (128-position tile, square): [8 channel chunks][16 row groups][8 rows][8 halfs]
-            uint8_t* dst = reinterpret_cast<uint8_t*>(act2) + ((pos >> 7) << 20) + ((long long)(y * 8 + f) << 14) +
+            uint8_t* dst = reinterpret_cast<uint8_t*>(act2) + ((pos >> 7) << 20) + ((long long)(y * 8) << 14) +
                            (pr >> 3) * 128 + (pr & 7) * 16 + hh * 4 * 2048;
+#pragma unroll 1
+            for (int f = 0; f < 8; f++, dst += 1 << 14) {
+                const int o = 8 * i + f;
+                TR(3, o, 0);
+                mbar_wait_warp(lane, bars + B_C2_FULL + slot, phase);
+                tc_fence_after();
+                TR(3, o, 1);
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + 64 * slot + 32 * hh, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + B_C2_EMPTY + slot);
+                TR(3, o, 2);
+                if (++slot == S2) { slot = 0; phase ^= 1; }
 #pragma unroll
-            for (int kc = 0; kc < 4; kc++) {
-                const float4 ba = b2r[kc * 2], bb = b2r[kc * 2 + 1];
-                uint4 u;
-                u.x = relu_pack_f16(__uint_as_float(v[kc * 8 + 0]) + ba.x, __uint_as_float(v[kc * 8 + 1]) + ba.y);
-                u.y = relu_pack_f16(__uint_as_float(v[kc * 8 + 2]) + ba.z, __uint_as_float(v[kc * 8 + 3]) + ba.w);
-                u.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]) + bb.x, __uint_as_float(v[kc * 8 + 5]) + bb.y);
-                u.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]) + bb.z, __uint_as_float(v[kc * 8 + 7]) + bb.w);
+                for (int kc = 0; kc < 4; kc++) {
+                    const float4 ba = b2r[kc * 2], bb = b2r[kc * 2 + 1];
+                    uint4 u;
+                    u.x = relu_pack_f16(__uint_as_float(v[kc * 8 + 0]) + ba.x, __uint_as_float(v[kc * 8 + 1]) + ba.y);
+                    u.y = relu_pack_f16(__uint_as_float(v[kc * 8 + 2]) + ba.z, __uint_as_float(v[kc * 8 + 3]) + ba.w);
+                    u.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]) + bb.x, __uint_as_float(v[kc * 8 + 5]) + bb.y);
+                    u.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]) + bb.z, __uint_as_float(v[kc * 8 + 7]) + bb.w);
 #ifndef CDQ_EXP_NOSTORE   // A/B experiment only: how much of the kernel time is the act2 write stream
-                *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
+                    *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
 #else
-                if (u.x == 0x12345678u) *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
+                    if (u.x == 0x12345678u) *reinterpret_cast<uint4*>(dst + kc * 2048) = u;
 #endif
+                }
+                TR(3, o, 3);
             }
-            TR(3, o, 3);
         }
     }
     tc_fence_before();
