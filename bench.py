@@ -222,26 +222,32 @@ def main():
     #      (strong scaling), one NCCL all-reduce of the flat gradient per step
     dqn = None
     if not args.no_dqn:
-        from chess_deep_q_b200.train import FusedAdam, dqn_train_step, shard_range
+        from chess_deep_q_b200.train import FusedAdam, GraphedDQNStep, shard_range
         B = 4096
         lo, hi = shard_range(B, rank, world)
         tgt = cdq.ChessQNetwork().cuda()
         tgt.load_state_dict(net.state_dict())
-        opt = FusedAdam(net, lr=1e-3)
+        # parameters + gradients in CUDA-IPC peer memory: the optimizer step is ONE kernel that
+        # reduce-scatters the gradients over NVLink, runs Adam on the rank's slice and all-gathers
+        # the parameters; the whole step is one CUDA graph per rank (no NCCL call in the loop)
+        opt = FusedAdam(net, lr=1e-3, peer_group=(world > 1))
         s_b, ns_b = boards[lo:hi].contiguous(), boards[lo + 1:hi + 1].contiguous()
         sc, fl = cdq.evaluate_batch(ns_b)
         rew = (0.01 * torch.tanh(sc / 10.0)).float()                  # chess_ai.py:183
         dn = ((fl & 7) != 0).float()
+        gstep = GraphedDQNStep(net, tgt, opt, batch=hi - lo, gamma=0.99)
+        gstep.load(s_b, ns_b, rew, dn)
         for _ in range(3):
-            dqn_train_step(net, tgt, opt, s_b, ns_b, rew, dn, 0.99)
+            gstep.run()
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
+        l0 = L.cdq_launch_count()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
-        dsteps = 20
+        dsteps = 50
         for _ in range(dsteps):
-            dloss = dqn_train_step(net, tgt, opt, s_b, ns_b, rew, dn, 0.99)
+            gstep.run()
         t1e.record()
         torch.cuda.synchronize()
         dms = t0e.elapsed_time(t1e)
@@ -249,9 +255,16 @@ def main():
             t = torch.tensor([dms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dms = float(t.item())
+        dloss = gstep.global_loss()
         dqn = {"metric": "DQN samples/sec", "value": B * dsteps / (dms * 1e-3), "unit": "samples/s", "global_batch": B,
                "ms_per_step": dms / dsteps, "scaling": "strong", "loss": float(dloss.item()),
-               "parallelism": "dp%d, one NCCL all-reduce of 1 071 073 fp32 grads per step" % world if world > 1 else "single GPU"}
+               "parallelism": ("dp%d: one CUDA graph per rank; gradients reduce-scattered, Adam and parameter all-gather "
+                               "in one kernel over NVLink peer memory" % world) if world > 1 else
+                              "single GPU, whole step as one CUDA graph"}
+        if opt.region is not None:
+            if dist:
+                dist.barrier()
+            opt.region.close()
 
     if rank != 0:
         if dist:
@@ -260,7 +273,7 @@ def main():
 
     # ---- roofline of the dominant kernel (tensor bound)
     peaks = measured_peaks()
-    kinds = {0: ("eval_terms_kernel", None), 1: ("conv_stack_kernel", FLOP_CONV), 2: ("fc_head_kernel", FLOP_FC)}
+    kinds = {0: ("eval_terms_kernel", None), 1: ("conv_stream_kernel", FLOP_CONV), 2: ("fc_head_kernel", FLOP_FC)}
     dom = max((1, 2), key=lambda k: kms[k])
     per_launch_pos = n * args.steps / max(1, kcnt[dom])
     avg_ms = kms[dom] / max(1, kcnt[dom])

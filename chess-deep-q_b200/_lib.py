@@ -29,6 +29,12 @@ SIGNATURES = {
                                   ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdq_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.c_float, ctypes.c_float,
                               ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
+    "cdq_dp_adam_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_float,
+                                 ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
+    "cdq_ipc_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    "cdq_ipc_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "cdq_ipc_close": (c_int, [c_void_p]),
+    "cdq_ipc_free": (c_int, [c_void_p]),
     "cdq_random_playouts": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
     "cdq_expand": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "cdq_expand_weighted": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -41,6 +47,13 @@ SIGNATURES = {
 
 class CdqWeights(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+MAX_RANKS = 8
+
+
+class CdqDpPeers(ctypes.Structure):
+    _fields_ = [("params", c_void_p * MAX_RANKS), ("grads", c_void_p * MAX_RANKS), ("flags", c_void_p * MAX_RANKS)]
 
 
 class CdqError(RuntimeError):

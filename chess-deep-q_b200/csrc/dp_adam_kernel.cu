@@ -1,0 +1,171 @@
+// dp_adam_kernel.cu -- the optimizer step of the DQN replay trainer (torch.optim.Adam defaults,
+// neural_network.py:65) fused with its data-parallel collective: ONE kernel per rank does
+//
+//     reduce-scatter of the gradients  ->  Adam on the rank's own slice  ->  all-gather of the parameters
+//
+// over NVLink peer memory (CUDA IPC mappings of every rank's buffers), instead of
+// ncclAllReduce(4.28 MB) followed by a full-size Adam on every rank:
+//   * rank r owns chunks [C r / W, C (r+1) / W) of the flat parameter vector (C = chunks of 4 floats);
+//   * it sums that slice of every rank's gradient buffer with 16-byte peer loads in rank order
+//     0..W-1 (each element is summed by exactly one rank, so all replicas receive identical bits),
+//     scales by 1/W, updates ITS slice of exp_avg / exp_avg_sq (optimizer state is sharded,
+//     28 -> 28/W bytes of state traffic per parameter) and stores the new parameters into every
+//     rank's parameter buffer;
+//   * the gradient slice it has just consumed is zeroed on every rank, so the next step needs no
+//     zero_grad pass;
+//   * cross-GPU ordering uses two epoch flags per (rank, peer) written with system-scope release
+//     stores: "my gradients are complete" before the reduction, "my stores have landed" after it.
+// With W = 1 the same kernel is the plain fused Adam step with a device-side step counter, which
+// is what lets the whole training step live in one CUDA graph (no host-computed bias correction).
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+#include "cnn.cuh"
+
+namespace cdq {
+
+constexpr int DP_THREADS = 512;
+#ifndef CDQ_DP_SPIN_LIMIT
+#define CDQ_DP_SPIN_LIMIT (1u << 24)   // a peer that never arrives traps this rank instead of hanging the GPU
+#endif
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// every CTA waits until all W ranks have published `epoch` in this rank's flag row
+__device__ __forceinline__ void wait_peers(const unsigned* my_flags, int world, unsigned epoch) {
+    if (threadIdx.x < world) {
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {
+            if (++spins > CDQ_DP_SPIN_LIMIT) __trap();
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DP_THREADS)
+dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ m, float* __restrict__ v,
+               long long n_chunks, int* __restrict__ d_step, unsigned* __restrict__ grid_bar, float lr, float b1, float b2,
+               float eps) {
+    __shared__ float s_bc[2];
+    // both counters are read by every thread before block 0 bumps them at the very end
+    const int step = *d_step + 1;                      // Adam's t (bias correction); reset by load_state_dict
+    const unsigned gen = grid_bar[1] + 1u;             // launch generation of this group: never reset
+    const unsigned epoch = 2u * gen;
+    if (threadIdx.x == 0) {
+        s_bc[0] = (float)(1.0 - pow((double)b1, (double)step));
+        s_bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
+    }
+    // ---- A: this rank's gradients are complete (stream order); tell every peer, wait for all of them
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch - 1);
+    wait_peers(peers.flags[rank], world, epoch - 1);
+    const float bc1 = s_bc[0], bc2_sqrt = s_bc[1], inv_world = 1.f / (float)world;
+
+    // ---- reduce-scatter + Adam + all-gather on this rank's slice
+    const long long lo = n_chunks * rank / world, hi = n_chunks * (rank + 1) / world;
+    for (long long c = lo + (long long)blockIdx.x * DP_THREADS + threadIdx.x; c < hi; c += (long long)gridDim.x * DP_THREADS) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; p++) {
+            const float4 x = reinterpret_cast<const float4*>(peers.grads[p])[c];
+            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+        }
+        float4 mi = reinterpret_cast<float4*>(m)[c], vi = reinterpret_cast<float4*>(v)[c];
+        float4 pi = reinterpret_cast<const float4*>(peers.params[rank])[c];
+#define CDQ_ADAM1(F)                                                                    \
+        {                                                                               \
+            const float gi = g.F * inv_world;                                           \
+            mi.F = b1 * mi.F + (1.f - b1) * gi;                                         \
+            vi.F = b2 * vi.F + (1.f - b2) * gi * gi;                                    \
+            /* torch: denom = sqrt(v)/sqrt(bc2) + eps ; p -= (lr / bc1) * m / denom */  \
+            pi.F -= (lr / bc1) * (mi.F / (sqrtf(vi.F) / bc2_sqrt + eps));               \
+        }
+        CDQ_ADAM1(x) CDQ_ADAM1(y) CDQ_ADAM1(z) CDQ_ADAM1(w)
+#undef CDQ_ADAM1
+        reinterpret_cast<float4*>(m)[c] = mi;
+        reinterpret_cast<float4*>(v)[c] = vi;
+        for (int p = 0; p < world; p++) {
+            reinterpret_cast<float4*>(peers.params[p])[c] = pi;
+            reinterpret_cast<float4*>(peers.grads[p])[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+
+    // ---- B: all CTAs of this rank have stored; publish, then wait until every peer's stores have landed here
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned target = gen * gridDim.x;                 // grid_bar[0] is never reset
+        atomicAdd(grid_bar, 1u);
+        if (blockIdx.x == 0) {
+            unsigned spins = 0;
+            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) {
+                if (++spins > CDQ_DP_SPIN_LIMIT) __trap();
+            }
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
+    wait_peers(peers.flags[rank], world, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *d_step = step; grid_bar[1] = gen; }
+}
+
+int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float* v, long long n_padded, int* d_step,
+                   unsigned* grid_bar, float lr, float b1, float b2, float eps, cudaStream_t st) {
+    const long long n_chunks = n_padded / 4;
+    const long long slice = (n_chunks + world - 1) / world;
+    int grid = (int)((slice + DP_THREADS - 1) / DP_THREADS);
+    const int sms = device_sm_count();
+    if (grid > sms) grid = sms;          // all CTAs must be co-resident: block 0 waits for the others
+    if (grid < 1) grid = 1;
+    ProfileScope ps(KK_TRAIN, st);
+    void* args[] = {(void*)&peers, &rank, &world, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)dp_adam_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
+    count_launch();
+    return (int)e;
+}
+
+} // namespace cdq
+
+using namespace cdq;
+
+extern "C" {
+
+int cdq_ipc_alloc(size_t bytes, void** d_ptr, void* handle64) {
+    if (!d_ptr || !handle64 || bytes == 0) return CDQ_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CDQ_CUDA(cudaMalloc(d_ptr, bytes));
+    CDQ_CUDA(cudaMemset(*d_ptr, 0, bytes));
+    CDQ_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, *d_ptr));
+    return 0;
+}
+int cdq_ipc_open(const void* handle64, void** d_ptr) {
+    if (!d_ptr || !handle64) return CDQ_E_BADARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CDQ_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int cdq_ipc_close(void* d_ptr) { return d_ptr ? (int)cudaIpcCloseMemHandle(d_ptr) : 0; }
+int cdq_ipc_free(void* d_ptr) { return d_ptr ? (int)cudaFree(d_ptr) : 0; }
+
+int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, float* d_v, int64_t n_params_padded,
+                     int32_t* d_step, uint32_t* d_grid_bar, float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!peers || world < 1 || world > CDQ_MAX_RANKS || rank < 0 || rank >= world || !d_m || !d_v || !d_step || !d_grid_bar ||
+        n_params_padded <= 0 || (n_params_padded & 3))
+        return CDQ_E_BADARG;
+    for (int p = 0; p < world; p++)
+        if (!peers->params[p] || !peers->grads[p] || !peers->flags[p]) return CDQ_E_BADARG;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return CDQ_E_NODEVICE; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return CDQ_E_NODEVICE;
+    return launch_dp_adam(*peers, rank, world, d_m, d_v, n_params_padded, d_step, d_grid_bar, lr, beta1, beta2, eps,
+                          (cudaStream_t)stream);
+}
+
+} // extern "C"

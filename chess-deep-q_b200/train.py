@@ -15,6 +15,7 @@ PARAM_SIZES = tuple(int(torch.Size(s).numel()) for s in PARAM_SHAPES)
 PARAM_OFFSETS = tuple(sum(PARAM_SIZES[:i]) for i in range(len(PARAM_SIZES)))
 NPARAMS = sum(PARAM_SIZES)
 assert NPARAMS == 1071073
+NPARAMS_PAD = (NPARAMS + 3) // 4 * 4      # flat buffers are padded to whole 16-byte chunks (padding stays 0)
 
 LOSS_MSE, LOSS_HUBER = 0, 1
 
@@ -39,12 +40,74 @@ def allreduce_mean_scale(flat_grad, group=None):
     return 1.0 / world
 
 
-def flatten_parameters(network):
+class _DevicePtr:
+    """Zero-copy torch view of raw device memory (a CUDA IPC region) via __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerRegion:
+    """One device region per rank -- [flat parameters | flat gradients | flag row] -- exported with
+    CUDA IPC and mapped by every other rank of the data-parallel group, for cdq_dp_adam_step (the
+    fused reduce-scatter + Adam + all-gather kernel).  world = 1 needs no mapping at all."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        dev = _lib.require_cuda()
+        L = _lib.lib()
+        self.rank, self.world = 0, 1
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_RANKS:
+            raise _lib.CdqError("cdq_dp_adam_step supports at most %d ranks" % _lib.MAX_RANKS)
+        nbytes = 2 * NPARAMS_PAD * 4 + self.FLAG_BYTES
+        base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _lib.check(L.cdq_ipc_alloc(nbytes, ctypes.byref(base), handle))
+        self._base, self._mapped = base, []
+        raw = torch.as_tensor(_DevicePtr(base.value, nbytes), device=dev)
+        self.params = raw[:NPARAMS_PAD * 4].view(torch.float32)
+        self.grads = raw[NPARAMS_PAD * 4:2 * NPARAMS_PAD * 4].view(torch.float32)
+        bases = [None] * self.world
+        bases[self.rank] = base.value
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                ptr = ctypes.c_void_p()
+                _lib.check(L.cdq_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(ptr)))
+                self._mapped.append(ptr)
+                bases[r] = ptr.value
+            dist.barrier(group=group)
+        self.peers = _lib.CdqDpPeers()
+        for r in range(self.world):
+            self.peers.params[r] = bases[r]
+            self.peers.grads[r] = bases[r] + NPARAMS_PAD * 4
+            self.peers.flags[r] = bases[r] + 2 * NPARAMS_PAD * 4
+
+    def close(self):
+        L = _lib.lib()
+        torch.cuda.synchronize()
+        for ptr in self._mapped:
+            L.cdq_ipc_close(ptr)
+        self._mapped = []
+        if self._base is not None:
+            self.params = self.grads = None
+            L.cdq_ipc_free(self._base)
+            self._base = None
+
+
+def flatten_parameters(network, flat=None):
     """Re-home the network's eight parameters as views into one contiguous fp32 buffer (so the
-    gradient all-reduce and the Adam update are one call each).  Returns the flat buffer."""
+    gradient reduction and the Adam update are one call each).  Returns the flat buffer."""
     params = dict(network.named_parameters())
     first = params[PARAM_ORDER[0]]
-    flat = torch.empty(NPARAMS, dtype=torch.float32, device=first.device)
+    if flat is None:
+        flat = torch.zeros(NPARAMS_PAD, dtype=torch.float32, device=first.device)
     for name, off, size, shape in zip(PARAM_ORDER, PARAM_OFFSETS, PARAM_SIZES, PARAM_SHAPES):
         p = params[name]
         assert tuple(p.shape) == shape, (name, tuple(p.shape))
@@ -60,14 +123,26 @@ class FusedAdam:
     state_dict()/load_state_dict() use torch.optim.Adam's format so reference checkpoints
     (chess_ai.py:459,483) round-trip."""
 
-    def __init__(self, network, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        _lib.require_cuda()
+    def __init__(self, network, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, peer_group=False):
+        """peer_group: False = plain buffers (single GPU, or NCCL all-reduce through step(grad_scale));
+        True / a ProcessGroup = parameters and gradients live in a CUDA-IPC PeerRegion so that
+        step_fused() runs the one-kernel reduce-scatter + Adam + all-gather over NVLink."""
+        dev = _lib.require_cuda()
         self.network = network
-        self.flat = flatten_parameters(network)
-        self.grad = torch.zeros_like(self.flat)
+        self.region = None
+        if peer_group is not False:
+            self.region = PeerRegion(None if peer_group is True else peer_group)
+            self.flat = flatten_parameters(network, self.region.params)
+            self.grad = self.region.grads
+        else:
+            self.flat = flatten_parameters(network)
+            self.grad = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
+        self._d_step = torch.zeros(1, dtype=torch.int32, device=dev)       # device copy of step_count (step_fused)
+        self._grid_bar = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._flags = torch.zeros(64, dtype=torch.int32, device=dev)        # flag row of the world = 1 case
         self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": 0, "amsgrad": False,
                               "params": list(range(len(PARAM_ORDER)))}]
 
@@ -77,21 +152,65 @@ class FusedAdam:
     def grad_views(self):
         return {n: self.grad[o:o + s].view(sh) for n, o, s, sh in zip(PARAM_ORDER, PARAM_OFFSETS, PARAM_SIZES, PARAM_SHAPES)}
 
+    @property
+    def world(self):
+        return self.region.world if self.region is not None else 1
+
+    def _peers(self):
+        if self.region is not None:
+            return self.region.peers, self.region.rank, self.region.world
+        peers = _lib.CdqDpPeers()
+        peers.params[0], peers.grads[0], peers.flags[0] = self.flat.data_ptr(), self.grad.data_ptr(), self._flags.data_ptr()
+        return peers, 0, 1
+
+    def step_fused(self):
+        """cdq_dp_adam_step: gradient reduction over the peer group (if any), Adam with the step
+        counter on the device, parameter broadcast and gradient zeroing in one kernel.  Safe to
+        capture in a CUDA graph.  Every rank of the group must call it."""
+        g = self.param_groups[0]
+        peers, rank, world = self._peers()
+        self.step_count += 1
+        _lib.check(_lib.lib().cdq_dp_adam_step(ctypes.byref(peers), rank, world, self.exp_avg.data_ptr(),
+                                               self.exp_avg_sq.data_ptr(), NPARAMS_PAD, self._d_step.data_ptr(),
+                                               self._grid_bar.data_ptr(), g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                                               _lib.stream_ptr()))
+        self.network.invalidate_packed()
+
     def step(self, grad_scale=1.0):
         g = self.param_groups[0]
         self.step_count += 1
+        self._d_step.fill_(self.step_count)
         _lib.check(_lib.lib().cdq_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                             self.exp_avg_sq.data_ptr(), NPARAMS, self.step_count, g["lr"],
                                             g["betas"][0], g["betas"][1], g["eps"], grad_scale, _lib.stream_ptr()))
         self.network.invalidate_packed()   # parameters changed behind autograd's back: repack before next forward
 
+    def _gathered_state(self):
+        """exp_avg / exp_avg_sq of all parameters.  Under a peer group each rank only maintains its
+        own slice (the rest of its arrays is zero), so the full state is the sum over ranks."""
+        if self.world == 1:
+            return self.exp_avg, self.exp_avg_sq
+        import torch.distributed as dist
+        m, v = self.exp_avg.clone(), self.exp_avg_sq.clone()
+        dist.all_reduce(m)
+        dist.all_reduce(v)
+        return m, v
+
+    def _owned_mask(self):
+        chunks = NPARAMS_PAD // 4
+        lo, hi = chunks * self.region.rank // self.region.world * 4, chunks * (self.region.rank + 1) // self.region.world * 4
+        mask = torch.zeros(NPARAMS_PAD, dtype=torch.bool, device=self.flat.device)
+        mask[lo:hi] = True
+        return mask
+
     def state_dict(self):
         state = {}
+        exp_avg, exp_avg_sq = self._gathered_state()
         if self.step_count:
             for i, (o, s, sh) in enumerate(zip(PARAM_OFFSETS, PARAM_SIZES, PARAM_SHAPES)):
                 state[i] = {"step": torch.tensor(float(self.step_count)),
-                            "exp_avg": self.exp_avg[o:o + s].view(sh).clone(),
-                            "exp_avg_sq": self.exp_avg_sq[o:o + s].view(sh).clone()}
+                            "exp_avg": exp_avg[o:o + s].view(sh).clone(),
+                            "exp_avg_sq": exp_avg_sq[o:o + s].view(sh).clone()}
         return {"state": state, "param_groups": [dict(self.param_groups[0])]}
 
     def load_state_dict(self, sd):
@@ -107,6 +226,11 @@ class FusedAdam:
             self.exp_avg[o:o + s].copy_(st["exp_avg"].reshape(-1))
             self.exp_avg_sq[o:o + s].copy_(st["exp_avg_sq"].reshape(-1))
             self.step_count = int(float(st["step"]))
+        if self.world > 1:          # keep only the owned slice of the optimizer state
+            mask = self._owned_mask()
+            self.exp_avg.mul_(mask)
+            self.exp_avg_sq.mul_(mask)
+        self._d_step.fill_(self.step_count)
 
 
 class _TrainScratch:
@@ -156,3 +280,75 @@ def dqn_train_step(q_network, target_network, optimizer, states, next_states, re
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
         out *= scale
     return out
+
+
+class GraphedDQNStep:
+    """The whole replay step -- weight repack, q = net(s), q' = target(s'), loss, backward, gradient
+    reduction over the peer group, Adam, parameter broadcast -- as ONE CUDA graph per rank
+    (about 15 kernels; launched eagerly from Python they cost more host time than device time at
+    batch 4 096).  Inputs are copied into static device buffers, so shapes are fixed at construction.
+    Under a peer group (FusedAdam(peer_group=True)) every rank holds `batch` = its shard."""
+
+    def __init__(self, q_network, target_network, optimizer, batch, gamma=0.99, loss_kind=LOSS_MSE):
+        dev = _lib.require_cuda()
+        self.q_network, self.target_network, self.optimizer = q_network, target_network, optimizer
+        self.batch, self.gamma, self.loss_kind = int(batch), float(gamma), int(loss_kind)
+        self.states = torch.zeros((self.batch, 9), dtype=torch.int64, device=dev)
+        self.next_states = torch.zeros((self.batch, 9), dtype=torch.int64, device=dev)
+        self.rewards = torch.zeros(self.batch, dtype=torch.float32, device=dev)
+        self.dones = torch.zeros(self.batch, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)        # mean over THIS rank's shard
+        self.ws = torch.empty(_lib.lib().cdq_train_workspace_bytes(self.batch), dtype=torch.uint8, device=dev)
+        self.graph = None
+        optimizer.zero_grad()
+        target_network.net_handle()       # packed once here; update_target_network() repacks in place
+
+    def _body(self):
+        params = dict(self.q_network.named_parameters())
+        weights = _weights_struct([params[k] for k in PARAM_ORDER])
+        gv = self.optimizer.grad_views()
+        grads = _weights_struct([gv[k] for k in PARAM_ORDER])
+        self.loss.zero_()
+        self.q_network.invalidate_packed()
+        _lib.check(_lib.lib().cdq_train_fwd_bwd(
+            self.q_network.net_handle(), self.target_network.net_handle(), ctypes.byref(weights),
+            self.states.data_ptr(), self.next_states.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
+            self.batch, self.gamma, self.loss_kind, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
+            self.ws.numel(), _lib.stream_ptr()))
+        self.optimizer.step_fused()
+
+    def load(self, states, next_states, rewards, dones):
+        self.states.copy_(states, non_blocking=True)
+        self.next_states.copy_(next_states, non_blocking=True)
+        self.rewards.copy_(rewards, non_blocking=True)
+        self.dones.copy_(dones, non_blocking=True)
+
+    def run(self):
+        """One step on the current contents of the static buffers; returns the local loss tensor."""
+        if self.graph is None:
+            self._body()                       # eager once: function attributes, lazy tables
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+            self.optimizer.step_count -= 1     # capture recorded the launch but did not run it
+        else:
+            self.target_network.net_handle()   # repacks (eagerly, in place) after update_target_network()
+            self.graph.replay()
+            self.optimizer.step_count += 1
+        self.q_network.invalidate_packed()     # eager forwards after this must repack
+        return self.loss
+
+    def __call__(self, states, next_states, rewards, dones):
+        self.load(states, next_states, rewards, dones)
+        return self.run()
+
+    def global_loss(self):
+        """Loss averaged over all ranks of the peer group (equal shards)."""
+        out = self.loss.clone()
+        if self.optimizer.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out)
+            out /= self.optimizer.world
+        return out

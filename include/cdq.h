@@ -171,6 +171,34 @@ int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeig
 int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n_params, int step,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- data-parallel optimizer step: reduce-scatter + Adam + all-gather in ONE kernel -------------
+ * Replaces `ncclAllReduce(grads); optimizer.step()` of a data-parallel DQNAgent.train (the
+ * reference trains on one device only, neural_network.py:218-252).  Every rank maps
+ * every rank's flat parameter buffer, flat gradient buffer and flag row (CUDA IPC, cdq_ipc_*) and
+ * passes the mapped pointers in rank order.  Rank r sums ITS slice of all gradient buffers (rank
+ * order, so all replicas get identical bits), scales by 1/world, updates its slice of d_m / d_v
+ * (optimizer state is sharded: only the owned slice of those arrays is meaningful), writes the new
+ * parameters into every rank's parameter buffer and zeroes the consumed gradients on every rank.
+ * *d_step (device int32, Adam's t) is incremented by the call; d_grid_bar = 2 zero-initialised
+ * device uint32 that belong to this group and are never reset.  n_params_padded = parameter count
+ * rounded up to a multiple of 4 (padding elements stay zero).  world = 1 is the single-GPU fused
+ * Adam step with a device-side step counter (CUDA-graph friendly).  All ranks must call it once
+ * per step; a peer that never arrives traps the waiting kernel (no silent hang). */
+#define CDQ_MAX_RANKS 8
+typedef struct CdqDpPeers {
+    float* params[CDQ_MAX_RANKS];
+    float* grads[CDQ_MAX_RANKS];
+    uint32_t* flags[CDQ_MAX_RANKS];   /* flags[r] = rank r's row of `world` uint32, zero-initialised */
+} CdqDpPeers;
+int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, float* d_v, int64_t n_params_padded,
+                     int32_t* d_step, uint32_t* d_grid_bar, float lr, float beta1, float beta2, float eps, void* stream);
+/* CUDA IPC plumbing for the above: allocate a zeroed device region and export its 64-byte handle;
+ * map a peer's handle; unmap; free. */
+int cdq_ipc_alloc(size_t bytes, void** d_ptr, void* handle64);
+int cdq_ipc_open(const void* handle64, void** d_ptr);
+int cdq_ipc_close(void* d_ptr);
+int cdq_ipc_free(void* d_ptr);
+
 /* Synthetic workload: n random playouts from the start position on the device.
  * Position i plays plies_i = U{0..max_plies} uniformly random legal moves (counter-based RNG
  * keyed by (seed, i, ply)); stops early at no-legal-move / insufficient material. */
