@@ -278,8 +278,16 @@ def main():
     per_launch_pos = n * args.steps / max(1, kcnt[dom])
     avg_ms = kms[dom] / max(1, kcnt[dom])
     achieved = per_launch_pos * kinds[dom][1] / (avg_ms * 1e-3) / 1e12
+    traffic = None        # DRAM bytes per launch of that kernel from the committed ncu capture (same launch size only)
+    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if kinds[dom][0] in tj and int(per_launch_pos) == tj["positions_per_launch"]:
+            traffic = tj[kinds[dom][0]]["traffic_bytes"]
     roofline = {"kernel": kinds[dom][0], "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                "traffic_note": "bytes per launch (131 072 positions), ncu dram read+write, profiles/r1b_kernels.ncu-rep; "
+                                "algorithmic 1.083 GB",
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kind::f16 shares the bf16 rate)",
                 "kernel_ms_per_step": {kinds[k][0]: kms[k] / args.steps for k in kinds},
                 "eval_kernel_hbm": {"achieved_GBps": n * args.steps * 84 / (kms[0] * 1e-3) / 1e9 if kms[0] else None,

@@ -18,13 +18,15 @@ for r in rows[2:]:
             print("  %-95s %-12s %s" % (h, u, v))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[h]; data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
-iS, iSrc, iEx = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
-stall = [i for i, x in enumerate(hdr) if x.startswith("stall_") and "Not Issued" not in x]
-tot = sum(int(r[iS]) for r in data)
-print("total samples", tot, "instructions", len(data))
-for i in sorted(sorted(range(len(data)), key=lambda i: -int(data[i][iS]))[:top]):
-    r = data[i]
-    st = sorted(((int(r[c]), hdr[c]) for c in stall), reverse=True)[:2]
-    print("%5d %6.2f%% exec=%-8s %-60s %s" % (i, 100.0 * int(r[iS]) / max(tot, 1), r[iEx], r[iSrc].strip()[:60], st))
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"] + [len(rows)]
+for sec in range(len(heads) - 1):          # one section per profiled kernel
+    hdr = rows[heads[sec]]
+    data = [r for r in rows[heads[sec] + 1:heads[sec + 1]] if len(r) == len(hdr) and r[0] != "Address"]
+    iS, iSrc, iEx = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
+    stall = [i for i, x in enumerate(hdr) if x.startswith("stall_") and "Not Issued" not in x]
+    tot = sum(int(r[iS]) for r in data)
+    print("-- source section %d: total samples %d, instructions %d" % (sec, tot, len(data)))
+    for i in sorted(sorted(range(len(data)), key=lambda i: -int(data[i][iS]))[:top]):
+        r = data[i]
+        st = sorted(((int(r[c]), hdr[c]) for c in stall), reverse=True)[:2]
+        print("%5d %6.2f%% exec=%-8s %-60s %s" % (i, 100.0 * int(r[iS]) / max(tot, 1), r[iEx], r[iSrc].strip()[:60], st))
