@@ -75,8 +75,10 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_throughput(n_sample, steps=1):
-    """The reference path's CPU port: oracle C evaluation (all host threads) + fp32 torch-CPU CNN."""
+def cpu_port_throughput(n_sample, steps=1, passes=1):
+    """The reference path's CPU port: oracle C evaluation (all host threads) + fp32 torch-CPU CNN.
+    One step = `passes` passes over n_sample unique positions (the port keeps no cache, so every
+    pass is the full work)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
@@ -86,13 +88,15 @@ def cpu_port_throughput(n_sample, steps=1):
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.evaluate(boards, nthreads=0)
-        planes = O.encode_planes(boards)
-        with torch.no_grad():
-            for i in range(0, n_sample, 4096):
-                O.net_forward(params, planes[i:i + 4096])
+        for _ in range(passes):
+            O.evaluate(boards, nthreads=0)
+            planes = O.encode_planes(boards)
+            with torch.no_grad():
+                for i in range(0, n_sample, 4096):
+                    O.net_forward(params, planes[i:i + 4096])
         times.append(time.perf_counter() - t0)
-    return n_sample / (sum(times) / len(times)), sum(times) / len(times), os.cpu_count(), torch.get_num_threads()
+    mean = sum(times) / len(times)
+    return n_sample * passes / mean, mean, os.cpu_count(), torch.get_num_threads()
 
 
 def run_reference(args):
@@ -124,6 +128,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=131072)
     ap.add_argument("--cpu-sample", type=int, default=131072)
+    ap.add_argument("--cpu-passes", type=int, default=10, help="passes over the CPU sample (about 10-15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dqn", action="store_true")
     args = ap.parse_args()
@@ -295,10 +300,10 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, sec, cores, tthreads = cpu_port_throughput(args.cpu_sample)
+        v, sec, cores, tthreads = cpu_port_throughput(args.cpu_sample, passes=args.cpu_passes)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d positions: C oracle eval on %d threads + torch-CPU fp32 CNN (%d threads), %.1f s"
-                         % (args.cpu_sample, cores, tthreads, sec)}
+               "sample": "%d passes over %d random-playout positions: C oracle eval on %d threads + torch-CPU fp32 CNN "
+                         "(%d threads), %.1f s" % (args.cpu_passes, args.cpu_sample, cores, tthreads, sec)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -28,7 +28,9 @@ ProfileScope::~ProfileScope() {
     g_prof.push_back({kind, a, b});
 }
 
-constexpr long long FWD_CHUNK = 128 * 1024; // positions per conv->fc pass (act2 = 1 GiB)
+// positions per conv->fc pass (act2 = 1 036 MiB): 148 SMs x 7 fc tiles of 128 = 148 SMs x 56 conv tiles of 16,
+// so both persistent kernels end their last round with every SM busy
+constexpr long long FWD_CHUNK = 148 * 7 * 128;
 static inline long long tiles_of(long long n) { return (n + 127) / 128; }
 
 static int check_device() {
@@ -224,7 +226,8 @@ int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeig
                       const float* d_done, int64_t n, float gamma, int loss_kind, const CdqWeights* d_grads,
                       float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!net || !target_net || !net->loaded || !target_net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 ||
-        !d_states || !d_next_states || !d_reward || !d_done || !d_workspace || (loss_kind != 0 && loss_kind != 1))
+        !d_states || !d_next_states || !d_reward || !d_done || !d_workspace ||
+        ((loss_kind & 0xff) != 0 && (loss_kind & 0xff) != 1) || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT)))
         return CDQ_E_BADARG;
     if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if (int e = check_device()) return e;
@@ -242,7 +245,7 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
 // ------------------------------------------------------------------ host-buffer path (e2e)
 namespace {
 struct HostPath {
-    static constexpr long long CHUNK = 256 * 1024;
+    static constexpr long long CHUNK = 2 * 148 * 7 * 128;   // two forward chunks
     std::mutex mu;
     bool ready = false;
     cudaStream_t st[2];

@@ -174,7 +174,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
-    __half* act2_tiles; __half* dz1h; __half* a1_boards; __half* dz2_boards; float* hidden; float* q; float* qn; float* dz1c;
+    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_boards; __half* dz2_boards; float* hidden; float* q; float* qn; float* dz1c;
     size_t zero_from, zero_bytes;   // [a1_boards, dz2_boards]: borders must be zero, cleared every step
     size_t total;
 };
@@ -184,6 +184,7 @@ static TrainWs carve(void* base, long long n) {
     auto take = [&](size_t bytes) { void* p = base ? (uint8_t*)base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
     const long long tiles = (n + 127) / 128, groups = tiles * 16;
     w.act2_tiles = (__half*)take((size_t)tiles << 20);
+    w.act2_target = (__half*)take((size_t)tiles << 20);
     w.dz1h = (__half*)take((size_t)tiles << 16);
     w.zero_from = off;
     w.a1_boards = (__half*)take((size_t)groups * 51200);
@@ -198,18 +199,46 @@ static TrainWs carve(void* base, long long n) {
 }
 size_t train_workspace_bytes(long long n) { return n > 0 ? carve(nullptr, n).total : 0; }
 
+// Independent pieces of the step run on a side stream (fork/join with events, which a capturing
+// stream turns into graph edges): the target network's forward next to the online forward, and
+// fc1's weight gradient next to the data-gradient chain.  At batch 4 096 every kernel here fills a
+// fraction of the 148 SMs, so the critical path, not the sum, sets the step time.
+namespace {
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int init() {
+        if (st) return 0;
+        CDQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CDQ_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CDQ_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        return 0;
+    }
+};
+SideStream g_side;
+} // namespace
+
 int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
                   const CdqBoard* next_states, const float* reward, const float* done, long long n, float gamma,
-                  int loss_kind, const CdqWeights& g /* gradient outputs, pre-zeroed */, float* loss, void* ws_base,
+                  int loss_kind_flags, const CdqWeights& g /* gradient outputs, pre-zeroed */, float* loss, void* ws_base,
                   cudaStream_t st) {
     TrainWs ws = carve(ws_base, n);
+    const int loss_kind = loss_kind_flags & 0xff;
     int e;
-    CDQ_CUDA(cudaMemsetAsync((uint8_t*)ws_base + ws.zero_from, 0, ws.zero_bytes, st));
-    // ---- forward: target value of next_states (inference), then q of states keeping activations
-    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_tiles, nullptr, st))) return e;
-    if ((e = launch_fc_head(ws.act2_tiles, n, target->p, ws.qn, nullptr, nullptr, nullptr, st))) return e;
+    if ((e = g_side.init())) return e;
+    cudaStream_t side = g_side.st;
+    // borders of the board-shaped buffers must be zero; their interiors are rewritten every step
+    if (!(loss_kind_flags & CDQ_TRAIN_WS_PERSISTENT))
+        CDQ_CUDA(cudaMemsetAsync((uint8_t*)ws_base + ws.zero_from, 0, ws.zero_bytes, st));
+    // ---- forward: target value of next_states (inference, side stream) next to q of states (keeps activations)
+    CDQ_CUDA(cudaEventRecord(g_side.fork, st));
+    CDQ_CUDA(cudaStreamWaitEvent(side, g_side.fork, 0));
+    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side))) return e;
+    if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
+    CDQ_CUDA(cudaEventRecord(g_side.join, side));
     if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
+    CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // ---- loss, tanh, fc2, fc1 bias
     const float scale = 64.f * (float)n;      // lift into fp16's normal range; undone in the fp32 epilogues
     {
@@ -221,7 +250,10 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
         count_launch();
     }
     // ---- fc1 weight and data gradients, conv2 weight/bias/data gradients: tcgen05
-    if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, st))) return e;
+    CDQ_CUDA(cudaEventRecord(g_side.fork, st));
+    CDQ_CUDA(cudaStreamWaitEvent(side, g_side.fork, 0));
+    if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, side))) return e;
+    CDQ_CUDA(cudaEventRecord(g_side.join, side));
     if ((e = launch_fc1_dgrad(ws.dz1h, ws.act2_tiles, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
     if ((e = launch_conv2_bwd(ws.dz2_boards, ws.a1_boards, net->p.w2tp, n, 1.f / scale, (float*)g.conv2_w, (float*)g.conv2_b,
                               ws.dz1c, st))) return e;
@@ -238,6 +270,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
         conv1_wgrad_kernel<<<blocks, C1W_WARPS * 32, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
         count_launch();
     }
+    CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     return (int)cudaGetLastError();
 }
 

@@ -18,6 +18,7 @@ assert NPARAMS == 1071073
 NPARAMS_PAD = (NPARAMS + 3) // 4 * 4      # flat buffers are padded to whole 16-byte chunks (padding stays 0)
 
 LOSS_MSE, LOSS_HUBER = 0, 1
+WS_PERSISTENT = 0x100      # CDQ_TRAIN_WS_PERSISTENT: the workspace is ours, zero-filled once, reused every step
 
 
 def shard_range(n, rank, world):
@@ -298,7 +299,7 @@ class GraphedDQNStep:
         self.rewards = torch.zeros(self.batch, dtype=torch.float32, device=dev)
         self.dones = torch.zeros(self.batch, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)        # mean over THIS rank's shard
-        self.ws = torch.empty(_lib.lib().cdq_train_workspace_bytes(self.batch), dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(_lib.lib().cdq_train_workspace_bytes(self.batch), dtype=torch.uint8, device=dev)
         self.graph = None
         optimizer.zero_grad()
         target_network.net_handle()       # packed once here; update_target_network() repacks in place
@@ -313,7 +314,7 @@ class GraphedDQNStep:
         _lib.check(_lib.lib().cdq_train_fwd_bwd(
             self.q_network.net_handle(), self.target_network.net_handle(), ctypes.byref(weights),
             self.states.data_ptr(), self.next_states.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
-            self.batch, self.gamma, self.loss_kind, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
+            self.batch, self.gamma, self.loss_kind | WS_PERSISTENT, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
             self.ws.numel(), _lib.stream_ptr()))
         self.optimizer.step_fused()
 

@@ -161,8 +161,13 @@ int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
  * `net` was packed from; d_grads = where to ACCUMULATE the gradients (same layouts; zero them first);
  * *d_loss is accumulated too (zero it first).  A terminal next_state is the all-zero board
  * (neural_network.py:215).  After an N-rank data-parallel step, sum the gradients over ranks and
- * pass grad_scale = 1/N to cdq_adam_step.
+ * pass grad_scale = 1/N to cdq_adam_step.  OR loss_kind with CDQ_TRAIN_WS_PERSISTENT when d_workspace
+ * is the same buffer as in the previous call with the same n AND was zero-filled before its first
+ * use: the call then skips re-zeroing the (never written) borders of its board-shaped buffers.
+ * The target network's forward and fc1's weight gradient run on an internal side stream, forked
+ * from and joined to `stream` with events (graph-capture safe).
  * cdq_adam_step: torch.optim.Adam defaults (neural_network.py:65) over one flat fp32 buffer. */
+#define CDQ_TRAIN_WS_PERSISTENT 0x100
 size_t cdq_train_workspace_bytes(int64_t n);
 int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
                       const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,
