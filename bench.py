@@ -42,37 +42,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, sampled through NVML every 10 ms while the timed
+    region runs (nvidia-smi as a subprocess needs about a second to produce its first line)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h))))
+                time.sleep(0.01)
+        except Exception as e:  # noqa: BLE001 -- reported in the JSON line, never fatal for the benchmark
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2.0)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling failed: %s" % self.err], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, bit in self.BAD.items() if mask & bit), "samples": len(sm)}
 
 
 def cpu_port_throughput(n_sample, steps=1, passes=1):
@@ -82,6 +89,7 @@ def cpu_port_throughput(n_sample, steps=1, passes=1):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
     boards = O.playouts(n_sample, seed=42)
     params = O.init_params(42, 2.0)
     planes = None
@@ -119,6 +127,44 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_sweep(args, cdq, L, ev, rank, world, local, dist):
+    """Per-GPU batch sweep (BASELINE configs[4]): every rank evaluates its own batch, sizes 4K..16M,
+    device-resident, CUDA events, max over ranks; reports positions/s and the tensor-roofline
+    fraction of the whole step (4 899 328 FLOP/position) for every size."""
+    import torch
+    peaks = measured_peaks()
+    rows = []
+    for n in (4096, 16384, 65536, 262144, 1048576, 4194304, 16777216):
+        boards = torch.empty((n, 9), dtype=torch.int64, device="cuda")
+        cdq._lib.check(L.cdq_random_playouts(boards.data_ptr(), n, 42 + rank, 199, cdq._lib.stream_ptr()))
+        steps = max(3, min(200, (8 << 20) // n))
+        for _ in range(3):
+            ev.evaluate_device(boards)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ev.evaluate_device(boards)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        pps = world * n * steps / (ms * 1e-3)
+        rows.append({"positions_per_gpu": n, "steps": steps, "ms_per_step": ms / steps, "positions_per_s": pps,
+                     "tensor_frac_whole_step": pps / world * (FLOP_CONV + FLOP_FC) / 1e12 / peaks["tflops"]})
+        del boards
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "scaling": "weak", "sweep": rows,
+                          "peak_tflops": peaks["tflops"], "data": "synthetic"}))
+    if dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,6 +177,8 @@ def main():
     ap.add_argument("--cpu-passes", type=int, default=10, help="passes over the CPU sample (about 10-15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dqn", action="store_true")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE configs[4]: device-resident throughput for 4K..16M positions per GPU (one JSON line)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -167,6 +215,9 @@ def main():
 
     def step():
         return ev.evaluate_device(boards)
+
+    if args.sweep:
+        return run_sweep(args, cdq, L, ev, rank, world, local, dist)
 
     for _ in range(W):
         out = step()
@@ -299,7 +350,7 @@ def main():
                                     "peak_GBps": peaks["hbm"], "note": "84 B/position; integer-issue bound"}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
         v, sec, cores, tthreads = cpu_port_throughput(args.cpu_sample, passes=args.cpu_passes)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d passes over %d random-playout positions: C oracle eval on %d threads + torch-CPU fp32 CNN "

@@ -197,6 +197,23 @@ def test_value_ragged_batch_sizes(cdq, oracle, n):
     assert np.abs(v - ref).max() <= 1e-3
 
 
+def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle):
+    """The stream conv kernel hands tiles between five warp roles through ~50 mbarriers; a missing
+    fence or a slot reused too early would show up as run-to-run or placement-dependent bits.
+    Twelve repetitions and evaluations of shifted sub-ranges (other tile / CTA assignment, other
+    ring phases) must reproduce every value bit for bit."""
+    n = 200_000
+    d = _dev_playouts(cdq, n, seed=9)
+    net, _ = _make_net(cdq, oracle, 3.0)
+    with torch.no_grad():
+        ref = net.forward_packed(d).reshape(-1).clone()
+        for _ in range(12):
+            assert torch.equal(net.forward_packed(d).reshape(-1), ref)
+        for off, cnt in [(1, 4095), (17, 70_001), (12_345, 132_608), (99_999, 100_001), (3, 16), (5, 1)]:
+            v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
+            assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
+
+
 def test_repack_after_weight_update(cdq, oracle):
     boards = oracle.playouts(64, seed=11)
     net, p = _make_net(cdq, oracle, 1.0)
