@@ -155,11 +155,7 @@ int cdq_net_load(CdqNet* net, const CdqWeights* w, void* stream) {
         !w->fc2_w || !w->fc2_b)
         return CDQ_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int e = launch_pack_weights(*w, (__half*)net->p.w1p, (__half*)net->p.w2p, (__half*)net->p.fc1p, (__half*)net->p.fc1tp, (__half*)net->p.w2tp, st)) return e;
-    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.conv2_b, w->conv2_b, 64 * 4, cudaMemcpyDeviceToDevice, st));
-    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc1_b, w->fc1_b, 256 * 4, cudaMemcpyDeviceToDevice, st));
-    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc2_w, w->fc2_w, 256 * 4, cudaMemcpyDeviceToDevice, st));
-    CDQ_CUDA(cudaMemcpyAsync((void*)net->p.fc2_b, w->fc2_b, 4, cudaMemcpyDeviceToDevice, st));
+    if (int e = launch_pack_weights(*w, net->p, st)) return e;
     net->loaded = 1;
     return 0;
 }
@@ -227,7 +223,7 @@ int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeig
                       float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!net || !target_net || !net->loaded || !target_net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 ||
         !d_states || !d_next_states || !d_reward || !d_done || !d_workspace ||
-        ((loss_kind & 0xff) != 0 && (loss_kind & 0xff) != 1) || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT)))
+        ((loss_kind & 0xff) != 0 && (loss_kind & 0xff) != 1) || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT | CDQ_TRAIN_REPACK)))
         return CDQ_E_BADARG;
     if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if (int e = check_device()) return e;

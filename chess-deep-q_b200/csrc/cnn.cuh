@@ -20,8 +20,7 @@ struct PackedNet {
 };
 
 int device_sm_count();
-int launch_pack_weights(const CdqWeights& w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
-                        cudaStream_t st);
+int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st);   // fp32 parameters -> all of p
 int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, __half* dz2_boards,
                      cudaStream_t st);
 int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,

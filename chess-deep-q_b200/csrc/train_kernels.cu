@@ -85,11 +85,12 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
 
 // conv1 weight + bias gradient.  The input is one-hot, so the GEMM collapses to a gather:
 // dW1[co][p][tap] += dz1c[b][sq][co] for every piece p standing on square sq + tap.  One warp per
-// board, lane = output channel, and the 12 x 9 accumulators of a lane live in REGISTERS: the loop
+// board, lane = output channel, and the 12 x 9 accumulators of a lane live in REGISTERS: the board's
+// 8 KB of gradients are staged in shared memory with 64 independent coalesced loads, then the loop
 // runs over the pieces of the board (bitboard & colour masks from the record, at most 32 set bits)
-// and, per piece, over the nine output squares around it -- 288 independent coalesced 128-byte
-// loads per board instead of 576 dependent shared-memory read-modify-writes (the first version of
-// this kernel took 115 us of the 430 us step).  Warps of a CTA are then summed through shared
+// and, per piece, over the nine output squares around it -- 288 conflict-free shared-memory reads
+// per board instead of 576 dependent read-modify-writes (the first version of this kernel took
+// 115 us of the 430 us step).  Warps of a CTA are then summed through shared
 // memory and each CTA issues one atomicAdd per accumulator cell.
 constexpr int C1W_WARPS = 8;
 constexpr int C1W_SMEM = C1W_WARPS * 109 * 32 * 4;
@@ -104,19 +105,30 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
 #pragma unroll
         for (int t = 0; t < 9; t++) acc[p][t] = 0.f;
     float bias = 0.f;
+    float* stage = acc_all + warp * (109 * 32);        // this warp's board: [64 squares][32 channels] (8 KB of its 13.6 KB)
     for (long long b = (long long)blockIdx.x * C1W_WARPS + warp; b < n; b += (long long)gridDim.x * C1W_WARPS) {
         const unsigned long long* r = reinterpret_cast<const unsigned long long*>(boards) + b * 9;
         const float* g = dz1c + b * 64 * 32 + lane;     // g[sq * 32] = gradient of ReLU(conv1) at (sq, channel lane)
         const unsigned long long white = __ldg(r + 6), black = __ldg(r + 7) & ~white;
-        {   // bias: sum over all 64 squares, 8 loads in flight
+        unsigned long long masks[12];
+#pragma unroll
+        for (int p = 0; p < 12; p++) masks[p] = __ldg(r + (p % 6)) & (p < 6 ? white : black);
+        // stage the board's 8 KB of gradients: 64 independent coalesced loads in flight, bias on the way
+        {
             float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-            for (int sq = 0; sq < 64; sq += 2) { s0 += g[sq * 32]; s1 += g[(sq + 1) * 32]; }
+#pragma unroll
+            for (int sq = 0; sq < 64; sq += 2) {
+                const float a = g[sq * 32], c = g[(sq + 1) * 32];
+                stage[sq * 32 + lane] = a;
+                stage[(sq + 1) * 32 + lane] = c;
+                s0 += a; s1 += c;
+            }
             bias += s0 + s1;
         }
+        __syncwarp();
 #pragma unroll
         for (int p = 0; p < 12; p++) {                  // channel = type + 6 * black (board_utils.py:17-30)
-            unsigned long long m = __ldg(r + (p % 6)) & (p < 6 ? white : black);
+            unsigned long long m = masks[p];
             while (m) {                                 // warp-uniform
                 const int s = __ffsll((long long)m) - 1;
                 m &= m - 1;
@@ -125,11 +137,13 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
                 for (int t = 0; t < 9; t++) {
                     // the piece on (y, x) is read through tap (dy, dx) by output square (y - dy, x - dx)
                     const int oy = y - (t / 3 - 1), ox = x - (t % 3 - 1);
-                    if (oy >= 0 && oy <= 7 && ox >= 0 && ox <= 7) acc[p][t] += g[(oy * 8 + ox) * 32];
+                    if (oy >= 0 && oy <= 7 && ox >= 0 && ox <= 7) acc[p][t] += stage[(oy * 8 + ox) * 32 + lane];
                 }
             }
         }
+        __syncwarp();                                   // the next board overwrites the staging rows
     }
+    __syncthreads();                                    // staging rows become the reduction buffer
     float* mine = acc_all + warp * (109 * 32);
 #pragma unroll
     for (int p = 0; p < 12; p++)
@@ -236,6 +250,8 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side))) return e;
     if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
+    // the online network's fp16 tiles are rebuilt from the fp32 parameters next to the target forward
+    if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st))) return e;
     if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));

@@ -68,6 +68,11 @@ class ChessQNetwork(nn.Module):
             self._packed_key = key
         return self._handle
 
+    def raw_handle(self):
+        """The CdqNet* without the is-it-current check: for callers that re-pack inside their own
+        call (cdq_train_fwd_bwd with CDQ_TRAIN_REPACK)."""
+        return self._handle if self._handle is not None else self.net_handle()
+
     def invalidate_packed(self):
         """Force a repack on the next forward (used after the fused optimizer wrote the flat
         parameter buffer directly, which autograd's version counters do not see)."""

@@ -18,6 +18,7 @@ assert NPARAMS == 1071073
 NPARAMS_PAD = (NPARAMS + 3) // 4 * 4      # flat buffers are padded to whole 16-byte chunks (padding stays 0)
 
 LOSS_MSE, LOSS_HUBER = 0, 1
+REPACK = 0x200             # CDQ_TRAIN_REPACK: the call re-packs the online network from the fp32 parameters
 WS_PERSISTENT = 0x100      # CDQ_TRAIN_WS_PERSISTENT: the workspace is ours, zero-filled once, reused every step
 
 
@@ -310,11 +311,10 @@ class GraphedDQNStep:
         gv = self.optimizer.grad_views()
         grads = _weights_struct([gv[k] for k in PARAM_ORDER])
         self.loss.zero_()
-        self.q_network.invalidate_packed()
         _lib.check(_lib.lib().cdq_train_fwd_bwd(
-            self.q_network.net_handle(), self.target_network.net_handle(), ctypes.byref(weights),
+            self.q_network.raw_handle(), self.target_network.net_handle(), ctypes.byref(weights),
             self.states.data_ptr(), self.next_states.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
-            self.batch, self.gamma, self.loss_kind | WS_PERSISTENT, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
+            self.batch, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
             self.ws.numel(), _lib.stream_ptr()))
         self.optimizer.step_fused()
 
