@@ -10,6 +10,6 @@ from .board_utils import BOARD_DTYPE, pack_board, pack_boards, board_to_tensor, 
 from .evaluation import fast_evaluate_position, evaluate_batch, PIECE_VALUES  # noqa: F401
 from .neural_network import ChessQNetwork, DQNAgent  # noqa: F401
 from .mcts import (evaluate_position, evaluate_positions, LeafEvaluator, BatchedRussianDollMCTS,  # noqa: F401
-                   self_play_game, move_from_records, move_uci)
+                   self_play_game, self_play_games, search_many, move_from_records, move_uci)
 
 __version__ = "0.1.0"

@@ -38,6 +38,8 @@ SIGNATURES = {
     "cdq_random_playouts": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
     "cdq_expand": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "cdq_expand_weighted": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cdq_sample_children": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "cdq_launch_count": (c_uint64, []),
     "cdq_profile_enable": (None, [c_int]),
     "cdq_profile_collect": (c_int, [c_void_p, c_void_p]),

@@ -123,6 +123,17 @@ int cdq_expand_weighted(const CdqBoard* d_boards, int64_t n, int max_children, C
     return launch_expand(d_boards, n, max_children, d_children, d_counts, d_weights, (cudaStream_t)stream);
 }
 
+int cdq_sample_children(const CdqBoard* d_children, const int32_t* d_counts, const uint8_t* d_weights, int64_t n,
+                        int max_children, int width, const uint64_t* d_seeds, CdqBoard* d_selected, int32_t* d_sel_counts,
+                        void* stream) {
+    if (n < 0 || max_children < 1 || max_children > 128 || width < 1 || width > max_children ||
+        (n > 0 && (!d_children || !d_counts || !d_weights || !d_seeds || !d_selected || !d_sel_counts)))
+        return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_sample_children(d_children, d_counts, d_weights, n, max_children, width,
+                                  (const unsigned long long*)d_seeds, d_selected, d_sel_counts, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ network handle
 static const size_t W1P_HALFS = 9 * 32 * 16, W2P_HALFS = 9 * 64 * 32, FC1P_HALFS = 64ull * 256 * 64;
 

@@ -33,4 +33,8 @@ int launch_random_playouts(CdqBoard* boards, long long n, unsigned long long see
 int launch_expand(const CdqBoard* boards, long long n, int max_children, CdqBoard* children, int* counts,
                   unsigned char* weights, cudaStream_t st);
 
+int launch_sample_children(const CdqBoard* children, const int* counts, const unsigned char* weights, long long n,
+                           int max_children, int width, const unsigned long long* seeds, CdqBoard* selected,
+                           int* sel_counts, cudaStream_t st);
+
 } // namespace cdq

@@ -78,8 +78,9 @@ def evaluate_position(board, neural_net, device=None):
 # simulations advance level by level in waves of `num_workers` (the reference's thread count): every
 # level of a wave costs one device expansion (cdq_expand) and the wave's leaves cost one
 # cdq_leaf_eval, instead of one batch-1 network call per simulation under the GIL.
-# Children are sampled like select_weighted_moves does, with the tactical weights of categorize_moves
-# computed on the device (cdq_expand_weighted, row f2).  Differences, stated: nodes are keyed by
+# Children are sampled like select_weighted_moves does, on the device: tactical weights of
+# categorize_moves from cdq_expand_weighted, the weighted draw without replacement from
+# cdq_sample_children (row f2).  Differences, stated: nodes are keyed by
 # their 72-byte record instead of a FEN; positions inside a search carry no move history (rep3 = 0).
 import math
 import random as _random
@@ -128,48 +129,58 @@ class BatchedRussianDollMCTS:
     def _key(rec):
         return rec.tobytes()
 
-    def _expand(self, records):
-        """Expand a batch of not-yet-expanded nodes on the device (mcts.py:166-194)."""
-        todo = [r for r in records if self._key(r) not in self.children]
-        if not todo:
-            return
-        uniq = {self._key(r): r for r in todo}
-        recs = np.array(list(uniq.values()), dtype=BOARD_DTYPE)
+    @staticmethod
+    def _device_expand(recs, seeds, width):
+        """Successors (cdq_expand_weighted), terminal flags (cdq_eval_terms) and the weighted sample of
+        `width` children per node (cdq_sample_children = select_weighted_moves, evaluation.py:342-366)
+        for a batch of nodes of any number of trees: three launches, and only the sampled children
+        (width x 72 B per node instead of 128 x 73 B) come back to the host."""
         d = to_device(recs)
         n, maxc = len(recs), 128
-        kids = torch.empty((n, maxc, 9), dtype=torch.int64, device=d.device)
-        counts = torch.empty(n, dtype=torch.int32, device=d.device)
-        flags = torch.empty(n, dtype=torch.int32, device=d.device)
-        wts = torch.empty((n, maxc), dtype=torch.uint8, device=d.device)
-        L = _lib.lib()
-        _lib.check(L.cdq_expand_weighted(d.data_ptr(), n, maxc, kids.data_ptr(), counts.data_ptr(), wts.data_ptr(),
-                                         _lib.stream_ptr()))
-        _lib.check(L.cdq_eval_terms(d.data_ptr(), n, 0, None, None, flags.data_ptr(), _lib.stream_ptr()))
-        kids_h = kids.cpu().numpy().view(np.uint64).reshape(n, maxc, 9)
-        counts_h, flags_h, wts_h = counts.cpu().numpy(), flags.cpu().numpy(), wts.cpu().numpy()
-        width = self.samples_per_level[0]
-        for i, key in enumerate(uniq):
-            c = min(int(counts_h[i]), maxc)
-            if c == 0 or (int(flags_h[i]) & 0x40):          # no legal move / insufficient material: game over
-                sel = np.zeros(0, BOARD_DTYPE)
-            else:
-                idx = list(range(c))
-                if c > width:
-                    # select_weighted_moves (evaluation.py:342-366): `width` draws without replacement,
-                    # probability proportional to the tactical weight of the move
-                    pool, w, idx = idx, [float(x) for x in wts_h[i, :c]], []
-                    for _ in range(width):
-                        r, acc = self.rng.random() * sum(w), 0.0
-                        for k, wk in enumerate(w):
-                            acc += wk
-                            if r < acc:
-                                break
-                        idx.append(pool.pop(k))
-                        w.pop(k)
-                sel = np.ascontiguousarray(kids_h[i, idx]).view(BOARD_DTYPE).reshape(-1)
-            self.children[key] = sel
-            self.N[key] = np.zeros(len(sel), np.int64)
-            self.Q[key] = np.zeros(len(sel), np.float64)
+        dev = d.device
+        kids = torch.empty((n, maxc, 9), dtype=torch.int64, device=dev)
+        counts = torch.empty(n, dtype=torch.int32, device=dev)
+        flags = torch.empty(n, dtype=torch.int32, device=dev)
+        wts = torch.empty((n, maxc), dtype=torch.uint8, device=dev)
+        sel = torch.empty((n, width, 9), dtype=torch.int64, device=dev)
+        sel_counts = torch.empty(n, dtype=torch.int32, device=dev)
+        d_seeds = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(dev)
+        L, st = _lib.lib(), _lib.stream_ptr()
+        _lib.check(L.cdq_expand_weighted(d.data_ptr(), n, maxc, kids.data_ptr(), counts.data_ptr(), wts.data_ptr(), st))
+        _lib.check(L.cdq_eval_terms(d.data_ptr(), n, 0, None, None, flags.data_ptr(), st))
+        _lib.check(L.cdq_sample_children(kids.data_ptr(), counts.data_ptr(), wts.data_ptr(), n, maxc, width,
+                                         d_seeds.data_ptr(), sel.data_ptr(), sel_counts.data_ptr(), st))
+        sel_h = sel.cpu().numpy().view(np.uint64).reshape(n, width, 9)
+        return sel_h, sel_counts.cpu().numpy(), flags.cpu().numpy()
+
+    @classmethod
+    def _expand_many(cls, requests):
+        """requests: (tree, record) pairs.  Nodes a tree has not expanded yet are expanded and sampled
+        with ONE batch of device calls for all trees; every node gets a 64-bit sampling seed drawn
+        from its own tree's RNG, in request order."""
+        todo, seen = [], set()
+        for tree, rec in requests:
+            key = cls._key(rec)
+            if key in tree.children or (id(tree), key) in seen:
+                continue
+            seen.add((id(tree), key))
+            todo.append((tree, key, rec))
+        if not todo:
+            return
+        width = todo[0][0].samples_per_level[0]
+        assert all(t.samples_per_level[0] == width for t, _, _ in todo), "trees searched together share the child width"
+        seeds = [t.rng.getrandbits(64) for t, _, _ in todo]
+        sel_h, sel_counts, flags = cls._device_expand(np.array([r for _, _, r in todo], dtype=BOARD_DTYPE), seeds, width)
+        for i, (tree, key, _) in enumerate(todo):
+            c = 0 if int(flags[i]) & 0x40 else int(sel_counts[i])      # insufficient material: game over
+            kids = np.ascontiguousarray(sel_h[i, :c]).view(BOARD_DTYPE).reshape(-1).copy()
+            tree.children[key] = kids
+            tree.N[key] = np.zeros(c, np.int64)
+            tree.Q[key] = np.zeros(c, np.float64)
+
+    def _expand(self, records):
+        """Expand a batch of not-yet-expanded nodes on the device (mcts.py:166-194)."""
+        self._expand_many([(self, r) for r in records])
 
     def _select(self, key, pending, training_progress, current_move, max_moves):
         """mcts.py:34-67.  `pending` holds the wave's not-yet-backed-up selections so that
@@ -197,51 +208,127 @@ class BatchedRussianDollMCTS:
                evaluator=None):
         """-> (best child record, (from, to, promotion)) or (None, None) when the root has no move."""
         ev = evaluator or LeafEvaluator(neural_net)
-        root_key = self._key(self.root[0])
-        self._expand([self.root[0]])
-        depth_limit = len(self.samples_per_level)
-        all_leaves, all_values = [], []
-        # The reference runs `num_workers` simulations concurrently (mcts.py:77) and backs each one up
-        # as it finishes; here a wave of `num_workers` simulations descends level by level together and
-        # is backed up before the next wave selects, so UCB sees the same amount of feedback.
-        for first in range(0, self.iterations, self.num_workers):
-            wave = min(self.num_workers, self.iterations - first)
-            sims = [{"rec": self.root[0], "path": [], "alive": True} for _ in range(wave)]
-            pending = {}
-            for depth in range(depth_limit):
-                live = [s for s in sims if s["alive"]]
-                if not live:
-                    break
-                self._expand([s["rec"] for s in live])
-                for s in live:
-                    key = self._key(s["rec"])
-                    a = self._select(key, pending, training_progress, current_move + depth, max_moves)
+        return search_many([self], ev, training_progress, [current_move], max_moves)[0]
+
+
+def search_many(trees, evaluator, training_progress=0.0, current_moves=None, max_moves=200):
+    """Run the searches of several trees (e.g. one per concurrent self-play game) in lockstep: every
+    level of a wave costs ONE device expansion and every wave ONE leaf evaluation for all trees
+    together, so the batch the GPU sees grows with the number of games.  Each tree keeps its own
+    statistics and RNG, so its result is what `tree.search()` alone would have produced."""
+    current_moves = current_moves or [0] * len(trees)
+    BatchedRussianDollMCTS._expand_many([(t, t.root[0]) for t in trees])
+    iterations = max(t.iterations for t in trees)
+    workers = trees[0].num_workers
+    leaves_of, values_of = [[] for _ in trees], [[] for _ in trees]
+    # The reference runs `num_workers` simulations concurrently (mcts.py:77) and backs each one up
+    # as it finishes; here a wave of `num_workers` simulations descends level by level together and
+    # is backed up before the next wave selects, so UCB sees the same amount of feedback.
+    for first in range(0, iterations, workers):
+        waves = []
+        for t in trees:
+            wave = max(0, min(t.num_workers, t.iterations - first))
+            waves.append(([{"rec": t.root[0], "path": [], "alive": True} for _ in range(wave)], {}))
+        depth_limit = max(len(t.samples_per_level) for t in trees)
+        for depth in range(depth_limit):
+            live = [[s for s in sims if s["alive"]] if depth < len(t.samples_per_level) else []
+                    for t, (sims, _) in zip(trees, waves)]
+            if not any(live):
+                break
+            BatchedRussianDollMCTS._expand_many([(t, s["rec"]) for t, ls in zip(trees, live) for s in ls])
+            for t, ls, (_, pending), cm in zip(trees, live, waves, current_moves):
+                for s in ls:
+                    key = t._key(s["rec"])
+                    a = t._select(key, pending, training_progress, cm + depth, max_moves)
                     if a is None:
                         s["alive"] = False
                         continue
-                    p = pending.setdefault(key, np.zeros(len(self.children[key]), np.int64))
+                    p = pending.setdefault(key, np.zeros(len(t.children[key]), np.int64))
                     p[a] += 1
                     s["path"].append((key, a))
-                    s["rec"] = self.children[key][a]
-            leaves = np.array([s["rec"] for s in sims], dtype=BOARD_DTYPE)
-            values = ev.evaluate_host(leaves)["leaf"]
-            self.total_positions_evaluated += len(leaves)
-            all_leaves.append(leaves)
-            all_values.append(values.copy())
-            for s, v in zip(sims, values):                      # mcts.py:158-164
-                value = float(v)
+                    s["rec"] = t.children[key][a]
+        batch = [s["rec"] for sims, _ in waves for s in sims]
+        if not batch:
+            continue
+        values = evaluator.evaluate_host(np.array(batch, dtype=BOARD_DTYPE))["leaf"]
+        pos = 0
+        for ti, (t, (sims, _)) in enumerate(zip(trees, waves)):
+            if not sims:
+                continue
+            v = values[pos:pos + len(sims)]
+            pos += len(sims)
+            t.total_positions_evaluated += len(sims)
+            leaves_of[ti].append(np.array([s["rec"] for s in sims], dtype=BOARD_DTYPE))
+            values_of[ti].append(v.copy())
+            for s, x in zip(sims, v):                           # mcts.py:158-164
+                value = float(x)
                 for key, a in reversed(s["path"]):
-                    self.N[key][a] += 1
-                    self.Q[key][a] += (value - self.Q[key][a]) / self.N[key][a]
+                    t.N[key][a] += 1
+                    t.Q[key][a] += (value - t.Q[key][a]) / t.N[key][a]
                     value = -value
-        self.last_leaves = (np.concatenate(all_leaves), np.concatenate(all_values))
-        kids = self.children[root_key]
+    out = []
+    for ti, t in enumerate(trees):
+        if leaves_of[ti]:
+            t.last_leaves = (np.concatenate(leaves_of[ti]), np.concatenate(values_of[ti]))
+        root_key = t._key(t.root[0])
+        kids = t.children[root_key]
         if len(kids) == 0:
-            return None, None
-        counts = self.N[root_key]
-        best = int(np.argmax(counts)) if counts.any() else self.rng.randrange(len(kids))
+            out.append((None, None))
+            continue
+        counts = t.N[root_key]
+        best = int(np.argmax(counts)) if counts.any() else t.rng.randrange(len(kids))
         child = kids[best:best + 1].copy()
-        return child, move_from_records(self.root[0], child[0])
+        out.append((child, move_from_records(t.root[0], child[0])))
+    return out
+
+
+def _startpos():
+    start = np.zeros(1, BOARD_DTYPE)
+    start["bb"][0] = [0x00ff00000000ff00, 0x4200000000000042, 0x2400000000000024, 0x8100000000000081,
+                      0x0800000000000008, 0x1000000000000010, 0xffff, 0xffff000000000000]
+    start["meta"][0] = 0x1f
+    return start
+
+
+def self_play_games(neural_net, n_games, max_moves=200, iterations=50, samples_per_level=None, seeds=None,
+                    training_progress=0.0):
+    """`n_games` self-play games (chess_ai.py:117-250) advanced ply by ply in lockstep, their searches
+    batched by search_many: one device expansion per tree level and one leaf evaluation per wave for
+    ALL games.  Game i uses RNG seed seeds[i] and is move for move the game self_play_game(seed =
+    seeds[i]) plays alone.  -> list of (positions, scores)."""
+    from .evaluation import evaluate_batch
+    seeds = list(seeds) if seeds is not None else list(range(42, 42 + n_games))
+    rngs = [_random.Random(s) for s in seeds]
+    ev = LeafEvaluator(neural_net)
+    widths = samples_per_level or [21, 13, 8, 5, 3, 2, 1]
+    positions = [[_startpos()] for _ in range(n_games)]
+    scores = [[] for _ in range(n_games)]
+    active = list(range(n_games))
+    for ply in range(max_moves):
+        if not active:
+            break
+        cur = np.concatenate([positions[g][-1] for g in active])
+        score, flags = evaluate_batch(cur)
+        score_h, flags_h = score.cpu().numpy(), flags.cpu().numpy()
+        still, trees = [], []
+        for k, g in enumerate(active):
+            scores[g].append(float(score_h[k]))
+            if int(flags_h[k]) & 0x70:          # checkmate / stalemate / insufficient material
+                continue
+            still.append(g)
+            trees.append(BatchedRussianDollMCTS(positions[g][-1], iterations=iterations, samples_per_level=widths,
+                                                rng=rngs[g]))
+        if not trees:
+            active = []
+            break
+        results = search_many(trees, ev, training_progress, [ply] * len(trees), max_moves)
+        active = []
+        for g, (child, _) in zip(still, results):
+            if child is None:
+                continue
+            positions[g].append(child)
+            active.append(g)
+    return [(np.concatenate(positions[g]), scores[g]) for g in range(n_games)]
 
 
 def self_play_game(neural_net, max_moves=200, iterations=50, samples_per_level=None, seed=42, start=None,
@@ -253,10 +340,7 @@ def self_play_game(neural_net, max_moves=200, iterations=50, samples_per_level=N
     rng = _random.Random(seed)
     ev = LeafEvaluator(neural_net)
     if start is None:
-        start = np.zeros(1, BOARD_DTYPE)
-        start["bb"][0] = [0x00ff00000000ff00, 0x4200000000000042, 0x2400000000000024, 0x8100000000000081,
-                          0x0800000000000008, 0x1000000000000010, 0xffff, 0xffff000000000000]
-        start["meta"][0] = 0x1f
+        start = _startpos()
     positions, scores = [as_records(start)[:1].copy()], []
     widths = samples_per_level or [21, 13, 8, 5, 3, 2, 1]
     for ply in range(max_moves):

@@ -219,6 +219,18 @@ int cdq_expand(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* 
  * it (evaluation.py:232-339); select_weighted_moves (evaluation.py:342-366) samples with them. */
 int cdq_expand_weighted(const CdqBoard* d_boards, int64_t n, int max_children, CdqBoard* d_children,
                         int32_t* d_counts, uint8_t* d_weights /*[n][max_children]*/, void* stream);
+/* Weighted child sampling on the device (replaces select_weighted_moves, evaluation.py:342-366):
+ * for every node, `width` successive draws without replacement from its children, each with
+ * probability proportional to the child's tactical weight (the output of cdq_expand_weighted);
+ * nodes with at most `width` children keep all of them in order.  Draw k of node i uses
+ * z = mix64(d_seeds[i] + (k+1) * 0x9E3779B97F4A7C15) (splitmix64 finalizer), r = (z * W) >> 64 with
+ * W = sum of the remaining weights, and takes the first remaining child in index order whose
+ * running weight sum exceeds r: integer arithmetic only, reproducible on the host.
+ * d_selected is [n][width] records, d_sel_counts[i] = min(count_i, width).  max_children <= 128. */
+int cdq_sample_children(const CdqBoard* d_children, const int32_t* d_counts, const uint8_t* d_weights, int64_t n,
+                        int max_children, int width, const uint64_t* d_seeds, CdqBoard* d_selected,
+                        int32_t* d_sel_counts, void* stream);
+
 
 /* Kernel launch counter (all cdq_* kernels launched by this process), for bench gpu_launches. */
 uint64_t cdq_launch_count(void);
