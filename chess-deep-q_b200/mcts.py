@@ -122,6 +122,7 @@ class BatchedRussianDollMCTS:
         self.children = {}          # key -> BOARD_DTYPE array of sampled children
         self.N = {}                 # key -> visit counts per child
         self.Q = {}                 # key -> running-mean values per child
+        self.U = {}                 # key -> indices of the children no simulation has taken yet
         self.total_positions_evaluated = 0
         self.last_leaves = None     # (records, leaf values) of the last search, for inspection/tests
 
@@ -171,35 +172,40 @@ class BatchedRussianDollMCTS:
         assert all(t.samples_per_level[0] == width for t, _, _ in todo), "trees searched together share the child width"
         seeds = [t.rng.getrandbits(64) for t, _, _ in todo]
         sel_h, sel_counts, flags = cls._device_expand(np.array([r for _, _, r in todo], dtype=BOARD_DTYPE), seeds, width)
+        recs = sel_h.view(BOARD_DTYPE).reshape(len(todo), width)         # views into one batch array, no copies
+        n_all, q_all = np.zeros((len(todo), width), np.int64), np.zeros((len(todo), width), np.float64)
         for i, (tree, key, _) in enumerate(todo):
             c = 0 if int(flags[i]) & 0x40 else int(sel_counts[i])      # insufficient material: game over
-            kids = np.ascontiguousarray(sel_h[i, :c]).view(BOARD_DTYPE).reshape(-1).copy()
-            tree.children[key] = kids
-            tree.N[key] = np.zeros(c, np.int64)
-            tree.Q[key] = np.zeros(c, np.float64)
+            tree.children[key] = recs[i, :c]
+            tree.N[key] = n_all[i, :c]
+            tree.Q[key] = q_all[i, :c]
+            tree.U[key] = list(range(c))
 
     def _expand(self, records):
         """Expand a batch of not-yet-expanded nodes on the device (mcts.py:166-194)."""
         self._expand_many([(self, r) for r in records])
 
-    def _select(self, key, pending, training_progress, current_move, max_moves):
-        """mcts.py:34-67.  `pending` holds the wave's not-yet-backed-up selections so that
-        simultaneous simulations spread over unexplored children like the reference's threads do."""
-        n_children = len(self.children[key])
-        if n_children == 0:
+    def _select(self, key, training_progress, current_move, max_moves):
+        """mcts.py:34-67: a random child that no simulation has taken yet, else the UCB argmax.  The
+        never-taken children of a node are a list that shrinks as simulations claim them (also within
+        a wave, before its back-up), so simultaneous simulations spread over unexplored children like
+        the reference's threads do."""
+        fresh = self.U[key]
+        if fresh:
+            k = self.rng.randrange(len(fresh))
+            fresh[k], fresh[-1] = fresh[-1], fresh[k]
+            return fresh.pop()
+        counts = self.N[key]
+        if len(counts) == 0:
             return None
+        total = int(counts.sum())
+        if total == 0:
+            return self.rng.randrange(len(counts))
         alpha = 1 + training_progress
         beta = current_move / max_moves if max_moves > 0 else 0.5
         eff = self.exploration_weight * (1.0 - 0.5 * alpha * beta)
-        visits = self.N[key] + pending.get(key, 0)
-        unexplored = np.nonzero(visits == 0)[0]
-        if len(unexplored):
-            return int(self.rng.choice(list(unexplored)))
-        total = int(self.N[key].sum())
-        if total == 0:
-            return self.rng.randrange(n_children)
         log_total = math.log(total + 1e-10)
-        nk = self.N[key] + 1e-10
+        nk = counts + 1e-10
         # as written in the reference: the running mean Q is divided by N once more (mcts.py:61-62)
         ucb = self.Q[key] / nk + eff * np.sqrt(log_total / nk)
         return int(np.argmax(ucb))
@@ -228,31 +234,29 @@ def search_many(trees, evaluator, training_progress=0.0, current_moves=None, max
         waves = []
         for t in trees:
             wave = max(0, min(t.num_workers, t.iterations - first))
-            waves.append(([{"rec": t.root[0], "path": [], "alive": True} for _ in range(wave)], {}))
+            waves.append([{"rec": t.root[0], "path": [], "alive": True} for _ in range(wave)])
         depth_limit = max(len(t.samples_per_level) for t in trees)
         for depth in range(depth_limit):
             live = [[s for s in sims if s["alive"]] if depth < len(t.samples_per_level) else []
-                    for t, (sims, _) in zip(trees, waves)]
+                    for t, sims in zip(trees, waves)]
             if not any(live):
                 break
             BatchedRussianDollMCTS._expand_many([(t, s["rec"]) for t, ls in zip(trees, live) for s in ls])
-            for t, ls, (_, pending), cm in zip(trees, live, waves, current_moves):
+            for t, ls, cm in zip(trees, live, current_moves):
                 for s in ls:
                     key = t._key(s["rec"])
-                    a = t._select(key, pending, training_progress, cm + depth, max_moves)
+                    a = t._select(key, training_progress, cm + depth, max_moves)
                     if a is None:
                         s["alive"] = False
                         continue
-                    p = pending.setdefault(key, np.zeros(len(t.children[key]), np.int64))
-                    p[a] += 1
                     s["path"].append((key, a))
                     s["rec"] = t.children[key][a]
-        batch = [s["rec"] for sims, _ in waves for s in sims]
+        batch = [s["rec"] for sims in waves for s in sims]
         if not batch:
             continue
         values = evaluator.evaluate_host(np.array(batch, dtype=BOARD_DTYPE))["leaf"]
         pos = 0
-        for ti, (t, (sims, _)) in enumerate(zip(trees, waves)):
+        for ti, (t, sims) in enumerate(zip(trees, waves)):
             if not sims:
                 continue
             v = values[pos:pos + len(sims)]
