@@ -44,7 +44,9 @@ def measured_peaks():
 class ClockSampler:
     """SM clock and throttle reasons of one GPU, sampled through NVML every 10 ms while the timed
     region runs (nvidia-smi as a subprocess needs about a second to produce its first line)."""
-    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+    BITS = {"gpu_idle": 0x1, "applications_clocks_setting": 0x2, "sw_power_cap": 0x4, "hw_slowdown": 0x8,
+            "sync_boost": 0x10, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80,
+            "display_clock_setting": 0x100}
 
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
@@ -59,7 +61,8 @@ class ClockSampler:
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop_flag:
-                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h))))
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h)),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
                 time.sleep(0.01)
         except Exception as e:  # noqa: BLE001 -- reported in the JSON line, never fatal for the benchmark
             self.err = repr(e)
@@ -78,8 +81,10 @@ class ClockSampler:
         mask = 0
         for r in self.rows:
             mask |= r[1]
+        watts = sorted(r[2] for r in self.rows)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(k for k, bit in self.BAD.items() if mask & bit), "samples": len(sm)}
+                "reasons": sorted(k for k, bit in self.BITS.items() if mask & bit and k != "gpu_idle"),
+                "reasons_mask": mask, "power_w_median": watts[len(watts) // 2], "power_w_max": watts[-1], "samples": len(sm)}
 
 
 def cpu_port_throughput(n_sample, steps=1, passes=1):
