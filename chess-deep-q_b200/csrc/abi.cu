@@ -141,7 +141,7 @@ int cdq_net_create(CdqNet** out) {
     if (!out) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
     CdqNet* net = new CdqNet();
-    const size_t halfs = W1P_HALFS + 2 * W2P_HALFS + 2 * FC1P_HALFS;
+    const size_t halfs = 2 * W1P_HALFS + 3 * W2P_HALFS + 2 * FC1P_HALFS;
     const size_t bytes = halfs * 2 + (64 + 256 + 256 + 4) * 4;
     cudaError_t e = cudaMalloc(&net->blob, bytes);
     if (e != cudaSuccess) { delete net; return (int)e; }
@@ -152,6 +152,7 @@ int cdq_net_create(CdqNet** out) {
     net->p.fc1p = h + W1P_HALFS + W2P_HALFS;
     net->p.fc1tp = h + W1P_HALFS + W2P_HALFS + FC1P_HALFS;
     net->p.w2tp = h + W1P_HALFS + W2P_HALFS + 2 * FC1P_HALFS;
+    net->p.wss = h + W1P_HALFS + 2 * W2P_HALFS + 2 * FC1P_HALFS;
     net->p.conv2_b = f;
     net->p.fc1_b = f + 64;
     net->p.fc2_w = f + 64 + 256;

@@ -227,20 +227,11 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
     }
     __syncthreads();
     if (tid == 0) {
-        // weights: global order [tap = 3(dy+1) + (dx+1)][K chunk][n groups] -> shared memory order
-        // [dy][K chunk][dx = +1, 0, -1][n groups], so that the taps of one kernel row form ONE
-        // B operand of N = 3 x 64 (3 x 32) rows whose row order matches ascending output files
+        // weights, already in this kernel's order (PackedNet::wss, written by pack_weights_kernel):
+        // [dy][K chunk][dx = +1, 0, -1][n groups], so that the taps of one kernel row form ONE B operand of
+        // N = 3 x 64 (3 x 32) rows whose row order matches ascending output files
         mbar_arrive_expect_tx(bars + B_W, W1_BYTES + W2_BYTES);
-        for (int dyi = 0; dyi < 3; dyi++)
-            for (int dxb = 0; dxb < 3; dxb++) {
-                const int tap = dyi * 3 + (2 - dxb);
-                for (int c = 0; c < 2; c++)
-                    bulk_g2s(smem + OFF_W1 + ((dyi * 2 + c) * 3 + dxb) * 512,
-                             reinterpret_cast<const uint8_t*>(net.w1p) + tap * W1_TAP_BYTES + c * 512, 512, bars + B_W);
-                for (int c = 0; c < 4; c++)
-                    bulk_g2s(smem + OFF_W2 + ((dyi * 4 + c) * 3 + dxb) * 1024,
-                             reinterpret_cast<const uint8_t*>(net.w2p) + tap * W2_TAP_BYTES + c * 1024, 1024, bars + B_W);
-            }
+        bulk_g2s(smem + OFF_W1, net.wss, W1_BYTES + W2_BYTES, bars + B_W);
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     fence_proxy_async();

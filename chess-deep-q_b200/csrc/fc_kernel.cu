@@ -144,7 +144,7 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
 // ------------------------------------------------------------------------------------------
 // weight repacking: fp32 PyTorch layouts -> fp16 UMMA K-major no-swizzle tiles
 __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
-                                    float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b) {
+                                    __half* wss, float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N1 = 9 * 32 * 16, N2 = 9 * 64 * 32, N3 = 64ll * 256 * 64;
     if (i < N1) {
@@ -179,9 +179,26 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
         const int co8 = j & 7, ci8 = (j >> 3) & 7, ng = (j >> 6) & 3, kc = (j >> 8) & 7, u = (int)(j >> 11);
         const int co = kc * 8 + co8, ci = ng * 8 + ci8;
         w2tp[j] = __float2half_rn(w.conv2_w[(co * 32 + ci) * 9 + (8 - u)]);
+    } else if (i < 2 * N1 + 2 * N2 + 2 * N3) {
+        // wss, first part: conv1 in the stream kernel's order [dy 3][kc 2][dx = +1, 0, -1][ng 4][n8][k8]
+        const long long j = i - N1 - 2 * N2 - 2 * N3;
+        const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 3, blk = (int)(j >> 8);
+        const int dxb = blk % 3, kc = (blk / 3) % 2, dyi = blk / 6, tap = dyi * 3 + (2 - dxb);
+        const int nn = ng * 8 + n8, k = kc * 8 + k8;
+        float v = 0.f;
+        if (k < 12) v = w.conv1_w[(nn * 12 + k) * 9 + tap];
+        else if (k == 12 && tap == 4) v = w.conv1_b[nn];
+        wss[j] = __float2half_rn(v);
+    } else if (i < 2 * N1 + 3 * N2 + 2 * N3) {
+        // wss, second part: conv2 as [dy 3][kc 4][dx = +1, 0, -1][ng 8][n8][k8]
+        const long long j = i - 2 * N1 - 2 * N2 - 2 * N3;
+        const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 7, blk = (int)(j >> 9);
+        const int dxb = blk % 3, kc = (blk / 3) % 4, dyi = blk / 12, tap = dyi * 3 + (2 - dxb);
+        const int nn = ng * 8 + n8, k = kc * 8 + k8;
+        wss[N1 + j] = __float2half_rn(w.conv2_w[(nn * 32 + k) * 9 + tap]);
     } else {
         // the fp32 vectors the kernels read directly: conv2 bias, fc1 bias, fc2 weight, fc2 bias
-        const long long j = i - N1 - 2 * N2 - 2 * N3;
+        const long long j = i - 2 * N1 - 3 * N2 - 2 * N3;
         if (j < 64) conv2_b[j] = w.conv2_b[j];
         else if (j < 320) fc1_b[j - 64] = w.fc1_b[j - 64];
         else if (j < 576) fc2_w[j - 320] = w.fc2_w[j - 320];
@@ -190,10 +207,10 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
 }
 
 int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st) {
-    const long long total = 9 * 32 * 16 + 2 * 9 * 64 * 32 + 2 * 64ll * 256 * 64 + 577;
+    const long long total = 2 * 9 * 32 * 16 + 3 * 9 * 64 * 32 + 2 * 64ll * 256 * 64 + 577;
     ProfileScope ps(KK_PACK, st);
     pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        w, (__half*)p.w1p, (__half*)p.w2p, (__half*)p.fc1p, (__half*)p.fc1tp, (__half*)p.w2tp, (float*)p.conv2_b,
+        w, (__half*)p.w1p, (__half*)p.w2p, (__half*)p.fc1p, (__half*)p.fc1tp, (__half*)p.w2tp, (__half*)p.wss, (float*)p.conv2_b,
         (float*)p.fc1_b, (float*)p.fc2_w, (float*)p.fc2_b);
     count_launch();
     return (int)cudaGetLastError();
