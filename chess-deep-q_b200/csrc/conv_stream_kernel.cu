@@ -68,6 +68,7 @@ constexpr int THREADS = 22 * 32;
 constexpr int TM_C2 = 0;            // conv2 slot s: columns TM_C2 + 64 s
 constexpr int TM_C1 = 64 * S2;      // conv1 slot s: columns TM_C1 + 32 s
 static_assert(TM_C1 + 32 * S1 <= 512, "TMEM columns");
+static_assert(RP == 8, "the plane encoder addresses slab = file");
 
 // layout of the training copy of ReLU(conv1) (consumed by conv_bwd_kernel.cu): zero-bordered boards
 // per group of 8 positions, [4 chunks][10 ranks][8 positions][10 files][16 B]
@@ -286,45 +287,54 @@ conv_stream_kernel(const CdqBoard* __restrict__ boards, long long n, const Packe
         // =============================== plane encoder: thread = (rank r, position p)
         const int e = tid - 64, r = e >> 4, p = e & 15;
         const uint8_t* gb = reinterpret_cast<const uint8_t*>(boards);
-        // rank byte r of the 8 bitboards of one board, as channel-pair words: bit x of byte 0 /
-        // byte 2 = channel 2j / 2j+1 present on file x (channel = type + 6*black, board_utils.py:17-30)
-        auto fetch = [&](int i, unsigned (&pair)[6]) {
+        // rank byte r of the 8 bitboards of one board.  The bytes of tile i+1 are requested at the start of
+        // tile i and stay RAW in registers until tile i+1 begins: nothing depends on them before that, so
+        // the loads (DRAM latency) really are in flight during the tile's eight steps.  (With the
+        // channel-pair words computed at once the warp stalled on them and every tile began with a
+        // ~2 800-cycle bubble for all roles.)
+        auto fetch = [&](int i, unsigned (&b)[8]) {
             const long long pos = (blockIdx.x + (long long)i * gridDim.x) * TILE_POS + p;
-            unsigned b[8];
+            const bool ok = i < n_local && pos < n;
 #pragma unroll
-            for (int t = 0; t < 8; t++) b[t] = (i < n_local && pos < n) ? (unsigned)__ldg(gb + pos * 72 + t * 8 + r) : 0u;
-            const unsigned w = b[6], k = b[7] & ~b[6];
-            pair[0] = (b[0] & w) | ((b[1] & w) << 16);
-            pair[1] = (b[2] & w) | ((b[3] & w) << 16);
-            pair[2] = (b[4] & w) | ((b[5] & w) << 16);
-            pair[3] = (b[0] & k) | ((b[1] & k) << 16);
-            pair[4] = (b[2] & k) | ((b[3] & k) << 16);
-            pair[5] = (b[4] & k) | ((b[5] & k) << 16);
+            for (int t = 0; t < 8; t++) b[t] = ok ? (unsigned)__ldg(gb + pos * 72 + t * 8 + r) : 0u;
         };
-        unsigned cur[6], nxt[6];
-        fetch(0, nxt);
+        unsigned raw[8], cur[6];
+        fetch(0, raw);
         uint8_t* dst0 = smem + OFF_PLANES + (r + 1) * RANK_B + p * CELL;
         for (int i = 0; i < n_local; i++) {
-#pragma unroll
-            for (int j = 0; j < 6; j++) cur[j] = nxt[j];
-            fetch(i + 1, nxt);                       // in flight during this tile's eight steps
+            // channel-pair words: bit x of byte 0 / byte 2 = channel 2j / 2j+1 present on file x
+            // (channel = type + 6*black, board_utils.py:17-30)
+            const unsigned w = raw[6], k = raw[7] & ~raw[6];
+            cur[0] = (raw[0] & w) | ((raw[1] & w) << 16);
+            cur[1] = (raw[2] & w) | ((raw[3] & w) << 16);
+            cur[2] = (raw[4] & w) | ((raw[5] & w) << 16);
+            cur[3] = (raw[0] & k) | ((raw[1] & k) << 16);
+            cur[4] = (raw[2] & k) | ((raw[3] & k) << 16);
+            cur[5] = (raw[4] & k) | ((raw[5] & k) << 16);
+            fetch(i + 1, raw);
+            // two files per iteration: one proxy fence and one round of barrier latencies per pair
 #pragma unroll 1
-            for (int f = 0; f < 8; f++) {
-                const int g = i * 8 + f, slab = g % RP;
+            for (int f = 0; f < 8; f += 2) {
+                const int g = i * 8 + f;                // RP = 8: slab = file, ring use = tile index
+                const uint32_t free_parity = (i & 1) ^ 1;
                 TR(1, g, 0);
-                mbar_wait_warp(lane, bars + B_PL_EMPTY + slab, ((g / RP) & 1) ^ 1);
+                mbar_wait_warp(lane, bars + B_PL_EMPTY + f, free_parity);
+                mbar_wait_warp(lane, bars + B_PL_EMPTY + f + 1, free_parity);
                 TR(1, g, 1);
-                unsigned w[6];
 #pragma unroll
-                for (int j = 0; j < 6; j++) w[j] = ((cur[j] >> f) & 0x00010001u) * 0x3C00u;   // fp16 1.0 per present channel
-                uint8_t* dst = dst0 + slab * PL_SLAB;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(dst + CHUNK_B) = make_uint4(w[4], w[5], 0x3C00u, 0u);   // channel 12: constant one
+                for (int h = 0; h < 2; h++) {
+                    unsigned v[6];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) v[j] = ((cur[j] >> (f + h)) & 0x00010001u) * 0x3C00u;   // fp16 1.0 per present channel
+                    uint8_t* dst = dst0 + (f + h) * PL_SLAB;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<uint4*>(dst + CHUNK_B) = make_uint4(v[4], v[5], 0x3C00u, 0u);   // channel 12: constant one
+                }
                 TR(1, g, 2);
                 fence_proxy_async();
                 __syncwarp();
                 TR(1, g, 3);
-                if (lane == 0) mbar_arrive(bars + B_PL_FULL + slab);
+                if (lane == 0) { mbar_arrive(bars + B_PL_FULL + f); mbar_arrive(bars + B_PL_FULL + f + 1); }
             }
         }
     } else if (warp <= 13) {
