@@ -2,6 +2,7 @@
 // stream plumbing.  All compute is in the kernels; there is no CPU path.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -32,6 +33,16 @@ ProfileScope::~ProfileScope() {
 // so both persistent kernels end their last round with every SM busy
 constexpr long long FWD_CHUNK = 148 * 7 * 128;
 static inline long long tiles_of(long long n) { return (n + 127) / 128; }
+
+// With CDQ_PIPE=1, batches of at least this many positions go through the conv -> fc pipe kernel (one
+// launch, act2 stays in L2: 90 MB instead of 17 GB of DRAM traffic per 1M positions).  It is opt-in: under
+// the board's power cap it is only 1-2 % faster than the two stand-alone kernels, and its persisting-L2
+// set-aside slows down the chunked host path that runs next to it (profiles/README.md, "pipe kernel").
+constexpr long long PIPE_MIN_POSITIONS = 512 * 1024;   // measured break-even is about 256 K (profiles/README.md)
+static bool pipe_enabled() {      // read on every call so that one process can A/B the two paths
+    const char* e = getenv("CDQ_PIPE");
+    return e && e[0] == '1';
+}
 
 static int check_device() {
     static int state = 0; // 0 unknown, 1 ok, <0 error
@@ -181,7 +192,9 @@ void cdq_net_destroy(CdqNet* net) {
 size_t cdq_workspace_bytes(int64_t n) {
     if (n <= 0) return 0;
     const long long c = n < FWD_CHUNK ? n : FWD_CHUNK;
-    return (size_t)tiles_of(c) << 20; // one 1 MiB fp16 act2 block per 128 positions
+    const size_t chunked = (size_t)tiles_of(c) << 20; // one 1 MiB fp16 act2 block per 128 positions
+    const size_t piped = n >= PIPE_MIN_POSITIONS ? pipe_workspace_bytes() : 0;   // always: the env switch may change
+    return chunked > piped ? chunked : piped;
 }
 
 // conv -> fc over chunks of at most FWD_CHUNK positions
@@ -192,6 +205,9 @@ static int forward_chunks(const CdqNet* net, const CdqBoard* d_boards, int64_t n
     if (ws_bytes < cdq_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if ((uintptr_t)ws & 15) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
+    if (n >= PIPE_MIN_POSITIONS && !dbg_act1 && pipe_enabled())
+        return launch_leaf_pipe(d_boards, n, net->p, d_value, d_flags, d_leaf, ws, st);
+    release_persisting_l2();
     for (int64_t off = 0; off < n; off += FWD_CHUNK) {
         const int64_t c = (n - off) < FWD_CHUNK ? (n - off) : FWD_CHUNK;
         if (int e = launch_conv_stack(d_boards + off, c, net->p, (__half*)ws, dbg_act1 ? dbg_act1 + off * 2048 : nullptr, st))
@@ -239,6 +255,7 @@ int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeig
         return CDQ_E_BADARG;
     if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if (int e = check_device()) return e;
+    release_persisting_l2();
     return train_fwd_bwd(net, target_net, *d_weights, d_states, d_next_states, d_reward, d_done, n, gamma, loss_kind,
                          *d_grads, d_loss, d_workspace, (cudaStream_t)stream);
 }

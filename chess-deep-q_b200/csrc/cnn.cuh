@@ -31,6 +31,11 @@ int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net,
                       cudaStream_t st, __half* act1_boards = nullptr);
 int launch_conv_stack_v1(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                          cudaStream_t st, __half* act1_boards);
+// conv stack + fc head as one persistent kernel with an L2-resident hand-over (pipe_kernel.cu)
+size_t pipe_workspace_bytes();
+void release_persisting_l2();   // undo the pipe kernel's L2 persistence window before other work
+int launch_leaf_pipe(const CdqBoard* boards, long long n, const PackedNet& net, float* value, const unsigned* flags,
+                     float* leaf, void* ws, cudaStream_t st);
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
                    float* leaf, float* hidden, cudaStream_t st);
 

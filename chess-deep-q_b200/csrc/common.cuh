@@ -10,7 +10,7 @@ namespace cdq {
 void count_launch(int k = 1);
 
 // optional per-kernel timing with CUDA events on the launching stream (cdq_profile_*)
-enum KernelKind { KK_EVAL = 0, KK_CONV = 1, KK_FC = 2, KK_ENCODE = 3, KK_PLAYOUT = 4, KK_PACK = 5, KK_TRAIN = 6, KK_COUNT = 8 };
+enum KernelKind { KK_EVAL = 0, KK_CONV = 1, KK_FC = 2, KK_ENCODE = 3, KK_PLAYOUT = 4, KK_PACK = 5, KK_TRAIN = 6, KK_PIPE = 7, KK_COUNT = 8 };
 struct ProfileScope {
     int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     ProfileScope(int kind, cudaStream_t st);

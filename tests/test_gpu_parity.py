@@ -214,6 +214,25 @@ def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle):
             assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
 
 
+def test_pipe_kernel_equals_two_kernel_path(cdq, oracle, monkeypatch):
+    """With CDQ_PIPE=1 large batches run conv and fc as one persistent kernel with an L2-resident
+    hand-over (pipe_kernel.cu); the default is the two stand-alone kernels.  Same tiles, same MMAs, same
+    epilogues: leaf values, raw values, scores and flags must agree bit for bit, for sizes around
+    the ring (64 tiles of 128 positions) and the role split."""
+    net, _ = _make_net(cdq, oracle, 2.0)
+    ev = cdq.LeafEvaluator(net)
+    for n in (524_288, 540_001, 64 * 128 * 67 + 5):
+        d = _dev_playouts(cdq, n, seed=n)
+        monkeypatch.setenv("CDQ_PIPE", "0")
+        a = ev.evaluate_device(d, want_raw=True)
+        monkeypatch.setenv("CDQ_PIPE", "1")
+        b = ev.evaluate_device(d, want_raw=True)
+        c = ev.evaluate_device(d, want_raw=True)
+        for k in ("leaf", "value", "score", "flags"):
+            assert torch.equal(a[k], b[k]), (n, k)
+            assert torch.equal(b[k], c[k]), (n, k)
+
+
 def test_repack_after_weight_update(cdq, oracle):
     boards = oracle.playouts(64, seed=11)
     net, p = _make_net(cdq, oracle, 1.0)
