@@ -112,6 +112,14 @@ def cpu_port_throughput(n_sample, steps=1, passes=1):
     return n_sample * passes / mean, mean, os.cpu_count(), torch.get_num_threads()
 
 
+def workload_config(n):
+    """The workload both arms are quoted on (BASELINE configs[1] at the default size)."""
+    return {"workload": "BASELINE configs[1]: %d random-playout positions per GPU per step, "
+                        "handcrafted eval + 12-channel CNN value" % n,
+            "positions_per_gpu": n, "l2": "per-step working set (act2 %.1f GB) >> 126 MB L2" % (n * 8192 / 1e9),
+            "weights": "numpy seed 42, torch-default init ranges, weight matrices x2"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -123,7 +131,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 score / fp32 CNN", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "CPU port of the reference path on %d random-playout positions per step" % n_sample},
+            "config": dict(workload_config(args.positions or 1 << 20),
+                           sample="each step is a bounded sample of that workload: %d positions" % n_sample),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d positions/step: C oracle eval on %d threads + torch-CPU fp32 CNN (%d threads)"
                                        % (n_sample, cores, tthreads)},
@@ -364,10 +373,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bitboards + f64 score; fp16 operands / fp32 accumulate CNN", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: %d random-playout positions per GPU per step, "
-                                   "handcrafted eval + 12-channel CNN value" % n,
-                       "positions_per_gpu": n, "l2": "per-step working set (act2 %.1f GB) >> 126 MB L2" % (n * 8192 / 1e9),
-                       "weights": "numpy seed 42, torch-default init ranges, weight matrices x2"},
+            "config": workload_config(n),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * H2D_PER_POS, "d2h_bytes_per_step": n * D2H_PER_POS},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dqn": dqn}
     print(json.dumps(line))
