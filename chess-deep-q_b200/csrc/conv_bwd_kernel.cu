@@ -31,6 +31,8 @@ constexpr int CB_OFF_BAR = CB_OFF_ONES + 256;
 constexpr int CB_SMEM = CB_OFF_BAR + 64;
 static_assert(CB_SMEM <= 227 * 1024, "conv2 backward shared memory");
 constexpr int CB_THREADS = 128;
+constexpr int CB_WT_STRIDE = 292;                // floats per co row of the staged weight-gradient tile (288 + 4: bank spread)
+static_assert(64 * CB_WT_STRIDE * 4 <= CB_DZ2_BYTES, "weight-gradient tile is staged over the dz2 boards");
 constexpr int CB_TM_BIAS = 288, CB_TM_DG = 320;  // TMEM columns: taps 0..287, bias 288..295, data-gradient tiles 320..447
 
 __global__ void __launch_bounds__(CB_THREADS, 1)
@@ -69,13 +71,16 @@ conv2_bwd_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict
     const int row = tid;                                   // data-gradient tile row: (yy, position, file)
     const int r_yy = row >> 6, r_pos = (row >> 3) & 7, r_x = row & 7;
 
+    // The boards of group i+1 are fetched while the data-gradient epilogue of group i runs: the epilogue's only
+    // use of the boards -- conv1's ReLU mask -- is pulled into registers first (128 bits per thread).
+    auto fetch = [&](long long g) {
+        mbar_arrive_expect_tx(bar_load, CB_DZ2_BYTES + CB_A1_BYTES);
+        bulk_g2s(smem, reinterpret_cast<const uint8_t*>(dz2_boards) + g * CB_DZ2_BYTES, CB_DZ2_BYTES, bar_load);
+        bulk_g2s(smem + CB_OFF_A1, reinterpret_cast<const uint8_t*>(a1_boards) + g * CB_A1_BYTES, CB_A1_BYTES, bar_load);
+    };
+    if (tid == 0 && (long long)blockIdx.x < n_groups) fetch(blockIdx.x);
     uint32_t iter = 0;
     for (long long g = blockIdx.x; g < n_groups; g += gridDim.x, iter++) {
-        if (tid == 0) {
-            mbar_arrive_expect_tx(bar_load, CB_DZ2_BYTES + CB_A1_BYTES);
-            bulk_g2s(smem, reinterpret_cast<const uint8_t*>(dz2_boards) + g * CB_DZ2_BYTES, CB_DZ2_BYTES, bar_load);
-            bulk_g2s(smem + CB_OFF_A1, reinterpret_cast<const uint8_t*>(a1_boards) + g * CB_A1_BYTES, CB_A1_BYTES, bar_load);
-        }
         mbar_wait(bar_load, iter & 1);
         if (warp == 0) {
             if (elect_one_sync()) {
@@ -111,7 +116,29 @@ conv2_bwd_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict
         }
         mbar_wait(bar_mma, iter & 1);
         tc_fence_after();
-        // ---- data-gradient epilogue: ReLU mask from the a1 boards, unscale, fp32 [position][square][32]
+        // ---- ReLU mask of this thread's four rows (32 channels each) from the a1 boards, then release the boards
+        unsigned relu_mask[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int y = 2 * t + r_yy;
+            const uint8_t* m = smem + CB_OFF_A1 + (y + 1) * CB_RANK + r_pos * CB_ROW + (r_x + 1) * 16;
+            unsigned bits = 0;
+#pragma unroll
+            for (int kc = 0; kc < 4; kc++) {
+                const uint4 mk = *reinterpret_cast<const uint4*>(m + kc * CB_CHUNK);
+                const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    bits |= (((mw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ? 1u : 0u) << (kc * 8 + e);
+            }
+            relu_mask[t] = bits;
+        }
+        __syncthreads();   // every thread has its mask: the boards may be overwritten
+        if (tid == 0 && g + gridDim.x < n_groups) {
+            fence_proxy_async();
+            fetch(g + gridDim.x);
+        }
+        // ---- data-gradient epilogue: mask, unscale, fp32 [position][square][32]
         const long long pos = g * 8 + r_pos;
 #pragma unroll 1
         for (int t = 0; t < 4; t++) {
@@ -119,29 +146,31 @@ conv2_bwd_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CB_TM_DG + 32 * t, v);
             tmem_ld_wait();
             const int y = 2 * t + r_yy;
-            const uint8_t* m = smem + CB_OFF_A1 + (y + 1) * CB_RANK + r_pos * CB_ROW + (r_x + 1) * 16;
+            const unsigned bits = relu_mask[t];
             if (pos < n) {
                 float4* o = reinterpret_cast<float4*>(dz1c + (pos * 64 + y * 8 + r_x) * 32);
 #pragma unroll
-                for (int kc = 0; kc < 4; kc++) {
-                    const uint4 mk = *reinterpret_cast<const uint4*>(m + kc * CB_CHUNK);
-                    const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
-                    float r[8];
+                for (int q4 = 0; q4 < 8; q4++) {
+                    float r[4];
 #pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        r[e] = ((mw[e >> 1] >> (16 * (e & 1))) & 0xffffu) ? __uint_as_float(v[kc * 8 + e]) * inv_scale : 0.f;
-                    o[2 * kc] = make_float4(r[0], r[1], r[2], r[3]);
-                    o[2 * kc + 1] = make_float4(r[4], r[5], r[6], r[7]);
+                    for (int e = 0; e < 4; e++)
+                        r[e] = ((bits >> (q4 * 4 + e)) & 1u) ? __uint_as_float(v[q4 * 4 + e]) * inv_scale : 0.f;
+                    o[q4] = make_float4(r[0], r[1], r[2], r[3]);
                 }
             }
         }
         tc_fence_before();
-        __syncthreads();   // boards and data-gradient accumulators are reused by the next group
+        __syncthreads();   // the data-gradient accumulators are reused by the next group
     }
 
-    // ---- weight/bias gradient epilogue: rows co = 16*quadrant + lane (lanes 0..15 hold data)
+    // ---- weight/bias gradient epilogue: rows co = 16*quadrant + lane (lanes 0..15 hold data).  The tile is
+    // transposed through shared memory (the boards are dead by now) into PyTorch order [co][ci][tap] and added
+    // with coalesced 16-byte reductions: one atomic per element straight from the accumulator rows put 32
+    // transactions of every CTA on each 128-byte line of the gradient, and same-line atomics serialise in L2
+    // (about 20 us of this kernel at 148 CTAs).
     if (iter > 0) {
         tc_fence_after();
+        float* tile = reinterpret_cast<float*>(smem);              // [64 co][CB_WT_STRIDE]
         const int co = warp * 16 + lane;
 #pragma unroll 1
         for (int tap = 0; tap < 9; tap++) {
@@ -150,13 +179,19 @@ conv2_bwd_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict
             tmem_ld_wait();
             if (lane < 16) {
 #pragma unroll
-                for (int ci = 0; ci < 32; ci++) atomicAdd(g_w2 + co * 288 + ci * 9 + tap, __uint_as_float(v[ci]) * inv_scale);
+                for (int ci = 0; ci < 32; ci++) tile[co * CB_WT_STRIDE + ci * 9 + tap] = __uint_as_float(v[ci]) * inv_scale;
             }
         }
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CB_TM_BIAS, v);   // columns 288..319; the first 8 are the bias sums
         tmem_ld_wait();
         if (lane < 16) atomicAdd(g_b2 + co, __uint_as_float(v[0]) * inv_scale);
+        __syncthreads();
+        for (int i = tid; i < 64 * 72; i += CB_THREADS) {
+            const int r = i / 72, q = i - r * 72;
+            const float4 t4 = *reinterpret_cast<const float4*>(tile + r * CB_WT_STRIDE + 4 * q);
+            atomicAdd(reinterpret_cast<float4*>(g_w2) + i, t4);     // conv2.weight[co][ci][tap], 288 floats per co
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -114,12 +114,88 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0) { *d_step = step; grid_bar[1] = gen; }
 }
 
+// world = 1: no peers, so no flags and no system-scope fences.  One 16-byte chunk per thread (the grid is
+// sized so that the whole parameter vector is in flight at once; the looped, 148-CTA peer version spends
+// 28 us on 30 MB), loads issued before the bias-correction constants are needed.  The step counter is still
+// bumped by block 0 after every CTA has read it, through the same never-reset arrival counter.
+__global__ void __launch_bounds__(DP_THREADS)
+adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v,
+                   long long n_chunks, int* __restrict__ d_step, unsigned* __restrict__ grid_bar, float lr, float b1, float b2,
+                   float eps) {
+    __shared__ float s_bc[2];
+    const int step = *d_step + 1;
+    const unsigned gen = grid_bar[1] + 1u;
+    if (threadIdx.x == 0) {
+        s_bc[0] = (float)(1.0 - pow((double)b1, (double)step));
+        s_bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
+    }
+    for (long long c0 = (long long)blockIdx.x * DP_THREADS; c0 < n_chunks; c0 += (long long)gridDim.x * DP_THREADS) {
+        const long long c = c0 + threadIdx.x;
+        const bool live = c < n_chunks;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), mi = g, vi = g, pi = g;
+        if (live) {
+            g = reinterpret_cast<const float4*>(grads)[c];
+            mi = reinterpret_cast<const float4*>(m)[c];
+            vi = reinterpret_cast<const float4*>(v)[c];
+            pi = reinterpret_cast<const float4*>(params)[c];
+        }
+        __syncthreads();                                 // s_bc (first round); harmless afterwards
+        const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+#define CDQ_ADAM1(F)                                                                    \
+        {                                                                               \
+            const float gi = g.F;                                                       \
+            mi.F = b1 * mi.F + (1.f - b1) * gi;                                         \
+            vi.F = b2 * vi.F + (1.f - b2) * gi * gi;                                    \
+            pi.F -= (lr / bc1) * (mi.F / (sqrtf(vi.F) / bc2_sqrt + eps));               \
+        }
+        CDQ_ADAM1(x) CDQ_ADAM1(y) CDQ_ADAM1(z) CDQ_ADAM1(w)
+#undef CDQ_ADAM1
+        if (live) {
+            reinterpret_cast<float4*>(m)[c] = mi;
+            reinterpret_cast<float4*>(v)[c] = vi;
+            reinterpret_cast<float4*>(params)[c] = pi;
+            reinterpret_cast<float4*>(grads)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __syncthreads();                                     // every thread of this CTA has read d_step / grid_bar[1]
+    if (threadIdx.x == 0) {
+        const unsigned target = gen * gridDim.x;
+        atomicAdd(grid_bar, 1u);
+        if (blockIdx.x == 0) {
+            unsigned spins = 0;
+            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) {
+                if (++spins > CDQ_DP_SPIN_LIMIT) __trap();
+            }
+            *d_step = step;
+            grid_bar[1] = gen;
+        }
+    }
+}
+
 int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float* v, long long n_padded, int* d_step,
                    unsigned* grid_bar, float lr, float b1, float b2, float eps, cudaStream_t st) {
     const long long n_chunks = n_padded / 4;
     const long long slice = (n_chunks + world - 1) / world;
     int grid = (int)((slice + DP_THREADS - 1) / DP_THREADS);
     const int sms = device_sm_count();
+    if (world == 1) {
+        // block 0 waits for the arrival of all others, so the grid must be co-resident: cooperative launch,
+        // at most what the occupancy calculator says fits (4 CTAs of 512 threads per SM at 32 registers)
+        static int per_sm = 0;
+        if (!per_sm) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_single_kernel, DP_THREADS, 0) != cudaSuccess || per_sm < 1)
+                per_sm = 1;
+        }
+        if (grid > sms * per_sm) grid = sms * per_sm;
+        if (grid < 1) grid = 1;
+        float* params = peers.params[0];
+        float* grads = peers.grads[0];
+        ProfileScope ps(KK_TRAIN, st);
+        void* args[] = {&params, &grads, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)adam_single_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
+        count_launch();
+        return (int)e;
+    }
     if (grid > sms) grid = sms;          // all CTAs must be co-resident: block 0 waits for the others
     if (grid < 1) grid = 1;
     ProfileScope ps(KK_TRAIN, st);

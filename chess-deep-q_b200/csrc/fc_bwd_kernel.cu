@@ -12,7 +12,7 @@
 //                     scaled, fp16) straight into the zero-bordered boards conv_bwd_kernel.cu consumes
 //                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
-//                     M = 2 x 128 outputs, N = 128 (2 squares), K = positions (split over CTAs)
+//                     M = 2 x 128 outputs, N = 128 (16 squares x 8 channels), K = positions (split over CTAs)
 #include "umma.cuh"
 #include "common.cuh"
 #include "cnn.cuh"
@@ -109,30 +109,56 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
             const long long pos = (tile << 7) + pr;
             for (int c = 0; c < 4; c++, chunk_no++) {
                 const int ab = chunk_no & 1;
+                // conv2's ReLU mask of this thread's 256 outputs, gathered BEFORE the accumulator is waited for: the 32
+                // loads are in flight together and their latency hides under the MMAs (taken one block at a time next
+                // to the TMEM loads they were 55 % of this kernel's stall samples).  ReLU output > 0 iff its fp16 bits != 0.
+                unsigned relu_bits[8];
+                {
+                    const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + (cg * 4 + c) * 4) << 14) +
+                                           (pr >> 3) * 128 + (pr & 7) * 16;
+                    uint4 mk[32];
+#pragma unroll
+                    for (int p = 0; p < 8; p++)
+#pragma unroll
+                        for (int g = 0; g < 4; g++)
+                            mk[p * 4 + g] = pos < n ? *reinterpret_cast<const uint4*>(mbase + ((p >> 1) << 14) + ((p & 1) * 4 + g) * 2048)
+                                                    : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int p = 0; p < 8; p++) {
+                        unsigned bits = 0;
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            const unsigned mw[4] = {mk[p * 4 + g].x, mk[p * 4 + g].y, mk[p * 4 + g].z, mk[p * 4 + g].w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (g * 8 + 2 * e);
+                                bits |= ((mw[e] >> 16) ? 1u : 0u) << (g * 8 + 2 * e + 1);
+                            }
+                        }
+                        relu_bits[p] = bits;
+                    }
+                }
                 mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
                 tc_fence_after();
-#pragma unroll 1
+#pragma unroll
                 for (int p = 0; p < 8; p++) {
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
                     tmem_ld_wait();
                     const int sq = (cg * 4 + c) * 4 + (p >> 1), ch0 = (p & 1) * 32;
+                    const unsigned bits = relu_bits[p];
                     if (pos < n) {
-                        const uint8_t* mrow = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + sq) << 14) +
-                                              (ch0 >> 3) * 2048 + (pr >> 3) * 128 + (pr & 7) * 16;
                         // conv2-backward board of this position's group: [8 chunks][10 ranks][8 pos][10 files][8 halfs]
                         uint8_t* o = reinterpret_cast<uint8_t*>(dz2_boards) + (pos >> 3) * 102400 + (ch0 >> 3) * 12800 +
                                      (((sq >> 3) + 1) * 8 + (int)(pos & 7)) * 160 + ((sq & 7) + 1) * 16;
 #pragma unroll
                         for (int g = 0; g < 4; g++) {
-                            const uint4 m = *reinterpret_cast<const uint4*>(mrow + g * 2048);
-                            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
                             unsigned w[4];
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                // ReLU output > 0 iff its fp16 bits != 0; the value stays scaled (undone downstream)
-                                const float lo = (mw[e] & 0xffffu) ? __uint_as_float(v[g * 8 + 2 * e]) : 0.f;
-                                const float hi = (mw[e] >> 16) ? __uint_as_float(v[g * 8 + 2 * e + 1]) : 0.f;
+                                // the value stays scaled (undone downstream)
+                                const float lo = ((bits >> (g * 8 + 2 * e)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e]) : 0.f;
+                                const float hi = ((bits >> (g * 8 + 2 * e + 1)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e + 1]) : 0.f;
                                 __half2 h2 = __floats2half2_rn(lo, hi);
                                 w[e] = *reinterpret_cast<unsigned*>(&h2);
                             }
@@ -153,7 +179,7 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
 
 // ------------------------------------------------------------------------------------------ wgrad
 constexpr int WG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
-constexpr int WG_B_BYTES = 2 * 16384;           // 32 KB: act2 blocks of two squares
+constexpr int WG_B_BYTES = 16 * 2048;           // 32 KB: one 8-channel chunk of 16 consecutive squares
 constexpr int WG_STAGE = WG_A_BYTES + WG_B_BYTES;
 constexpr int WG_OFF_BAR = 2 * WG_STAGE;
 constexpr int WG_SMEM = WG_OFF_BAR + 64;
@@ -178,7 +204,13 @@ fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int pair = blockIdx.x / k_splits, split = blockIdx.x % k_splits;   // squares 2*pair, 2*pair + 1
+    // N block = squares 16*sg .. 16*sg+15 of channels 8*chunk .. 8*chunk+7: sixteen 2 KB pieces of the act2 tile,
+    // 16 KB apart in global memory and back to back in shared memory (the MN-major B operand as before).  For a
+    // fixed output j and channel the 16 squares are 64 contiguous bytes of fc1.weight's gradient, so the epilogue
+    // adds 16-byte vectors: a quarter of the L2 transactions of two-squares-by-64-channels blocks, whose
+    // one-float atomics (32 768 per CTA, each its own sector) took longer than the MMAs.
+    const int blk = blockIdx.x / k_splits, split = blockIdx.x % k_splits;
+    const int sg = blk & 3, chunk = blk >> 2;
     const long long my_tiles = split < n_tiles ? (n_tiles - split + k_splits - 1) / k_splits : 0;
     constexpr uint32_t IDESC = make_idesc_f16_ex(128, 128, true, true);
 
@@ -190,8 +222,10 @@ fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                 mbar_wait(empty + st, ((i >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(full + st, WG_STAGE);
                 bulk_g2s(smem + st * WG_STAGE, reinterpret_cast<const uint8_t*>(dz1h) + t * WG_A_BYTES, WG_A_BYTES, full + st);
-                bulk_g2s(smem + st * WG_STAGE + WG_A_BYTES,
-                         reinterpret_cast<const uint8_t*>(act2) + ((t * 64 + 2 * pair) << 14), WG_B_BYTES, full + st);
+#pragma unroll 4
+                for (int sqi = 0; sqi < 16; sqi++)
+                    bulk_g2s(smem + st * WG_STAGE + WG_A_BYTES + sqi * 2048,
+                             reinterpret_cast<const uint8_t*>(act2) + ((t * 64 + sg * 16 + sqi) << 14) + chunk * 2048, 2048, full + st);
             }
         }
     } else if (warp == 1) {
@@ -223,10 +257,13 @@ fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 128 + p * 32, v);
                 tmem_ld_wait();
-                const int sq = 2 * pair + (p >> 1), ch0 = (p & 1) * 32;
-                float* dst = g_fc1_w + (long long)j * 4096 + ch0 * 64 + sq;   // reference column = ch*64 + sq
+                // columns of this block: (square 4p + s, channel e) at 8*s + e; reference column = ch*64 + sq
+                float* dst = g_fc1_w + (long long)j * 4096 + chunk * 8 * 64 + sg * 16 + 4 * p;
 #pragma unroll
-                for (int e = 0; e < 32; e++) atomicAdd(dst + e * 64, __uint_as_float(v[e]) * inv_scale);
+                for (int e = 0; e < 8; e++)
+                    atomicAdd(reinterpret_cast<float4*>(dst + e * 64),
+                              make_float4(__uint_as_float(v[e]) * inv_scale, __uint_as_float(v[8 + e]) * inv_scale,
+                                          __uint_as_float(v[16 + e]) * inv_scale, __uint_as_float(v[24 + e]) * inv_scale));
             }
         }
     }

@@ -20,11 +20,47 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
 }
 
 // ------------------------------------------------------------------------------------------
-// weight repacking: fp32 PyTorch layouts -> fp16 UMMA K-major no-swizzle tiles
+// weight repacking: fp32 PyTorch layouts -> fp16 UMMA K-major no-swizzle tiles.
+// The two fc1 buffers (98 % of the bytes) are written one 16-byte vector per thread: the eight source
+// floats of a vector are 64 or 4096 floats apart, so the thread index runs over the SQUARE first and every
+// one of the eight loads of a warp is one coalesced 128-byte line (the first version moved one half
+// per thread with 256-byte-strided loads: 12 us of the 320 us training step).  The conv tiles are small
+// and stay one element per thread.
+__device__ __forceinline__ uint4 pack8_f16(const float (&v)[8]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    return make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b), *reinterpret_cast<unsigned*>(&c),
+                      *reinterpret_cast<unsigned*>(&d));
+}
+constexpr long long PK_N1 = 9 * 32 * 16, PK_N2 = 9 * 64 * 32, PK_V3 = 64ll * 256 * 64 / 8;
+constexpr long long PK_SMALL = 2 * PK_N1 + 3 * PK_N2 + 577;
+constexpr long long PK_SMALL_PAD = (PK_SMALL + 255) / 256 * 256;     // the vector parts start on a CTA boundary
 __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
                                     __half* wss, float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long N1 = 9 * 32 * 16, N2 = 9 * 64 * 32, N3 = 64ll * 256 * 64;
+    constexpr long long N1 = PK_N1, N2 = PK_N2;
+    if (i >= PK_SMALL_PAD) {
+        const long long t = i - PK_SMALL_PAD;
+        float v[8];
+        if (t < PK_V3) {
+            // fc1p[square 64][kc 8][ng 32][n8][k8]; reference column = c*64 + square
+            const int sq = t & 63, kc = (t >> 6) & 7, nn = (int)(t >> 9);
+            const float* src = w.fc1_w + (long long)nn * 4096 + kc * 512 + sq;
+#pragma unroll
+            for (int k8 = 0; k8 < 8; k8++) v[k8] = src[k8 * 64];
+            *reinterpret_cast<uint4*>(fc1p + ((((long long)sq * 8 + kc) * 32 + (nn >> 3)) * 8 + (nn & 7)) * 8) = pack8_f16(v);
+        } else if (t < 2 * PK_V3) {
+            // fc1tp[chunk 16][stage 4][kc 8][ng 32][n8][j8]: row n' = sq*64 + ch, K = fc1 output j
+            const long long u = t - PK_V3;
+            const int sq = u & 63, ch = (u >> 6) & 63, jg = (int)(u >> 12);          // jg = sg*8 + kc
+            const float* src = w.fc1_w + (long long)jg * 8 * 4096 + ch * 64 + sq;
+#pragma unroll
+            for (int j8 = 0; j8 < 8; j8++) v[j8] = src[(long long)j8 * 4096];
+            const int np = sq * 64 + ch, ck = np >> 8, ng = (np >> 3) & 31, n8 = np & 7;
+            *reinterpret_cast<uint4*>(fc1tp + (((((long long)ck * 32 + jg) * 32 + ng) * 8 + n8) * 8)) = pack8_f16(v);
+        }
+        return;
+    }
     if (i < N1) {
         // w1p[tap][kc 2][ng 4][n8][k8]
         const int k8 = i & 7, n8 = (i >> 3) & 7, ng = (i >> 6) & 3, kc = (i >> 8) & 1, tap = (int)(i >> 9);
@@ -39,27 +75,15 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
         const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 7, kc = (j >> 9) & 3, tap = (int)(j >> 11);
         const int nn = ng * 8 + n8, k = kc * 8 + k8;
         w2p[j] = __float2half_rn(w.conv2_w[(nn * 32 + k) * 9 + tap]);
-    } else if (i < N1 + N2 + N3) {
-        // fc1p[square 64][kc 8][ng 32][n8][k8]; reference column = c*64 + square
-        const long long j = i - N1 - N2;
-        const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 31, kc = (j >> 11) & 7, sq = (int)(j >> 14);
-        const int nn = ng * 8 + n8, c = kc * 8 + k8;
-        fc1p[j] = __float2half_rn(w.fc1_w[(long long)nn * 4096 + c * 64 + sq]);
-    } else if (i < N1 + N2 + 2 * N3) {
-        // fc1tp[chunk 16][stage 4][kc 8][ng 32][n8][j8]: row n' = sq*64 + ch, K = fc1 output j
-        const long long j = i - N1 - N2 - N3;
-        const int j8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 31, kc = (j >> 11) & 7, sg = (j >> 14) & 3, ck = (int)(j >> 16);
-        const int np = ck * 256 + ng * 8 + n8, sq = np >> 6, ch = np & 63, jo = sg * 64 + kc * 8 + j8;
-        fc1tp[j] = __float2half_rn(w.fc1_w[(long long)jo * 4096 + ch * 64 + sq]);
-    } else if (i < N1 + 2 * N2 + 2 * N3) {
+    } else if (i < N1 + 2 * N2) {
         // w2tp[u 9][kc 8 (co)][ng 4 (ci)][ci8][co8] = conv2.weight[co][ci][8 - u]   (flipped taps)
-        const long long j = i - N1 - N2 - 2 * N3;
+        const long long j = i - N1 - N2;
         const int co8 = j & 7, ci8 = (j >> 3) & 7, ng = (j >> 6) & 3, kc = (j >> 8) & 7, u = (int)(j >> 11);
         const int co = kc * 8 + co8, ci = ng * 8 + ci8;
         w2tp[j] = __float2half_rn(w.conv2_w[(co * 32 + ci) * 9 + (8 - u)]);
-    } else if (i < 2 * N1 + 2 * N2 + 2 * N3) {
+    } else if (i < 2 * N1 + 2 * N2) {
         // wss, first part: conv1 in the stream kernel's order [dy 3][kc 2][dx = +1, 0, -1][ng 4][n8][k8]
-        const long long j = i - N1 - 2 * N2 - 2 * N3;
+        const long long j = i - N1 - 2 * N2;
         const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 3, blk = (int)(j >> 8);
         const int dxb = blk % 3, kc = (blk / 3) % 2, dyi = blk / 6, tap = dyi * 3 + (2 - dxb);
         const int nn = ng * 8 + n8, k = kc * 8 + k8;
@@ -67,16 +91,16 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
         if (k < 12) v = w.conv1_w[(nn * 12 + k) * 9 + tap];
         else if (k == 12 && tap == 4) v = w.conv1_b[nn];
         wss[j] = __float2half_rn(v);
-    } else if (i < 2 * N1 + 3 * N2 + 2 * N3) {
+    } else if (i < 2 * N1 + 3 * N2) {
         // wss, second part: conv2 as [dy 3][kc 4][dx = +1, 0, -1][ng 8][n8][k8]
-        const long long j = i - 2 * N1 - 2 * N2 - 2 * N3;
+        const long long j = i - 2 * N1 - 2 * N2;
         const int k8 = j & 7, n8 = (j >> 3) & 7, ng = (j >> 6) & 7, blk = (int)(j >> 9);
         const int dxb = blk % 3, kc = (blk / 3) % 4, dyi = blk / 12, tap = dyi * 3 + (2 - dxb);
         const int nn = ng * 8 + n8, k = kc * 8 + k8;
         wss[N1 + j] = __float2half_rn(w.conv2_w[(nn * 32 + k) * 9 + tap]);
     } else {
         // the fp32 vectors the kernels read directly: conv2 bias, fc1 bias, fc2 weight, fc2 bias
-        const long long j = i - 2 * N1 - 3 * N2 - 2 * N3;
+        const long long j = i - 2 * N1 - 3 * N2;
         if (j < 64) conv2_b[j] = w.conv2_b[j];
         else if (j < 320) fc1_b[j - 64] = w.fc1_b[j - 64];
         else if (j < 576) fc2_w[j - 320] = w.fc2_w[j - 320];
@@ -85,7 +109,7 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
 }
 
 int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st) {
-    const long long total = 2 * 9 * 32 * 16 + 3 * 9 * 64 * 32 + 2 * 64ll * 256 * 64 + 577;
+    const long long total = PK_SMALL_PAD + 2 * PK_V3;
     ProfileScope ps(KK_PACK, st);
     pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         w, (__half*)p.w1p, (__half*)p.w2p, (__half*)p.fc1p, (__half*)p.fc1tp, (__half*)p.w2tp, (__half*)p.wss, (float*)p.conv2_b,

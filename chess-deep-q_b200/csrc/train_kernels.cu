@@ -84,79 +84,121 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
 }
 
 // conv1 weight + bias gradient.  The input is one-hot, so the GEMM collapses to a gather:
-// dW1[co][p][tap] += dz1c[b][sq][co] for every piece p standing on square sq + tap.  One warp per
-// board, lane = output channel, and the 12 x 9 accumulators of a lane live in REGISTERS: the board's
-// 8 KB of gradients are staged in shared memory with 64 independent coalesced loads, then the loop
-// runs over the pieces of the board (bitboard & colour masks from the record, at most 32 set bits)
-// and, per piece, over the nine output squares around it -- 288 conflict-free shared-memory reads
-// per board instead of 576 dependent read-modify-writes (the first version of this kernel took
-// 115 us of the 430 us step).  Warps of a CTA are then summed through shared
-// memory and each CTA issues one atomicAdd per accumulator cell.
-constexpr int C1W_WARPS = 8;
-constexpr int C1W_SMEM = C1W_WARPS * 109 * 32 * 4;
-__global__ void __launch_bounds__(C1W_WARPS * 32)
+// dW1[co][p][tap] += dz1c[b][sq][co] for every piece p standing on square sq + tap.  A board is handled by
+// THREE warps, one per kernel row dy; lane = output channel, and the 12 pieces x 3 taps accumulators of a
+// lane live in registers.  The board's 8 KB of gradients and its bitboards are brought into shared memory
+// with cp.async, double buffered (the copy of the slot's next board runs under the gather of the current
+// one and costs no registers); each warp then runs over the pieces of the board (at most 32 set bits) and
+// reads the three output squares of its row around the piece -- conflict-free shared-memory reads.  Seven
+// such board slots per CTA, one CTA per SM, each slot synchronised by its own named barrier.  At the end the
+// slots of a CTA are summed through shared memory into PyTorch order and added to the gradient with
+// coalesced 16-byte reductions: same-line atomics serialise in L2, so what matters is the number of
+// transactions per 128-byte line (one scalar atomic per cell and CTA with the channel as the fast index put
+// 32 per CTA on each line and cost more than the gather itself).
+constexpr int C1W_SLOTS = 7, C1W_WARPS = 3 * C1W_SLOTS, C1W_THREADS = 32 * C1W_WARPS;
+constexpr int C1W_STAGE_BYTES = C1W_SLOTS * 2 * 8192;             // [slot][2][64 squares][32 channels] fp32
+constexpr int C1W_RED_BYTES = C1W_WARPS * 37 * 32 * 4;            // reduction buffer, aliases the staging buffers
+static_assert(C1W_RED_BYTES <= C1W_STAGE_BYTES, "reduction buffer aliases the staging buffers");
+constexpr int C1W_OFF_BOARD = C1W_STAGE_BYTES;                    // [slot][2][8 bitboards]
+constexpr int C1W_OFF_OUT = C1W_OFF_BOARD + C1W_SLOTS * 2 * 64;   // [32 co][108] summed over the slots
+constexpr int C1W_SMEM = C1W_OFF_OUT + 32 * 108 * 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__global__ void __launch_bounds__(C1W_THREADS, 1)
 conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
                    float* __restrict__ g_w, float* __restrict__ g_b) {
-    extern __shared__ float acc_all[];                 // [warps][12 pieces x 9 taps + bias][32]
+    extern __shared__ __align__(16) uint8_t c1w_raw[];
+    float* c1w_smem = reinterpret_cast<float*>(c1w_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc[12][9];
+    const int slot = warp / 3, sub = warp % 3, t96 = sub * 32 + lane;
+    const int dy = sub - 1;
+    float acc[12][3];
 #pragma unroll
     for (int p = 0; p < 12; p++)
 #pragma unroll
-        for (int t = 0; t < 9; t++) acc[p][t] = 0.f;
+        for (int t = 0; t < 3; t++) acc[p][t] = 0.f;
     float bias = 0.f;
-    float* stage = acc_all + warp * (109 * 32);        // this warp's board: [64 squares][32 channels] (8 KB of its 13.6 KB)
-    for (long long b = (long long)blockIdx.x * C1W_WARPS + warp; b < n; b += (long long)gridDim.x * C1W_WARPS) {
-        const unsigned long long* r = reinterpret_cast<const unsigned long long*>(boards) + b * 9;
-        const float* g = dz1c + b * 64 * 32 + lane;     // g[sq * 32] = gradient of ReLU(conv1) at (sq, channel lane)
-        const unsigned long long white = __ldg(r + 6), black = __ldg(r + 7) & ~white;
-        unsigned long long masks[12];
+    float* stage0 = c1w_smem + slot * 4096;             // two buffers of [64 squares][32 channels]
+    unsigned long long* board0 = reinterpret_cast<unsigned long long*>(c1w_raw + C1W_OFF_BOARD) + slot * 16;
+    const long long stride = (long long)gridDim.x * C1W_SLOTS;
+    auto fetch = [&](long long bb, int buf) {           // this thread's share of board bb: 512 16-byte pieces over 96 threads
+        if (bb < n) {
+            const float* src = dz1c + bb * 2048;
+            float* dst = stage0 + buf * 2048;
 #pragma unroll
-        for (int p = 0; p < 12; p++) masks[p] = __ldg(r + (p % 6)) & (p < 6 ? white : black);
-        // stage the board's 8 KB of gradients: 64 independent coalesced loads in flight, bias on the way
-        {
+            for (int i = 0; i < 6; i++) {
+                const int u = i * 96 + t96;
+                if (u < 512) cp_async16(dst + 4 * u, src + 4 * u);
+            }
+            if (t96 < 8) cp_async8(board0 + buf * 8 + t96, reinterpret_cast<const unsigned long long*>(boards) + bb * 9 + t96);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long b = (long long)blockIdx.x * C1W_SLOTS + slot;
+    fetch(b, 0);
+    for (int it = 0; b < n; b += stride, it++) {
+        const int buf = it & 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("bar.sync %0, 96;" ::"r"(slot + 1) : "memory");   // all three warps: copies landed, previous board done
+        fetch(b + stride, buf ^ 1);
+        const float* stage = stage0 + buf * 2048;
+        const unsigned long long* r = board0 + buf * 8;
+        {   // bias: every thread sums a third of the squares of its channel
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int sq = 0; sq < 64; sq += 2) {
-                const float a = g[sq * 32], c = g[(sq + 1) * 32];
-                stage[sq * 32 + lane] = a;
-                stage[(sq + 1) * 32 + lane] = c;
-                s0 += a; s1 += c;
+            for (int i = 0; i < 22; i += 2) {
+                const int q0 = sub + 3 * i, q1 = sub + 3 * (i + 1);
+                if (q0 < 64) s0 += stage[q0 * 32 + lane];
+                if (q1 < 64) s1 += stage[q1 * 32 + lane];
             }
             bias += s0 + s1;
         }
-        __syncwarp();
+        const unsigned long long white = r[6], black = r[7] & ~white;
 #pragma unroll
         for (int p = 0; p < 12; p++) {                  // channel = type + 6 * black (board_utils.py:17-30)
-            unsigned long long m = masks[p];
+            unsigned long long m = r[p % 6] & (p < 6 ? white : black);
             while (m) {                                 // warp-uniform
                 const int s = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                const int y = s >> 3, x = s & 7;
-#pragma unroll
-                for (int t = 0; t < 9; t++) {
-                    // the piece on (y, x) is read through tap (dy, dx) by output square (y - dy, x - dx)
-                    const int oy = y - (t / 3 - 1), ox = x - (t % 3 - 1);
-                    if (oy >= 0 && oy <= 7 && ox >= 0 && ox <= 7) acc[p][t] += stage[(oy * 8 + ox) * 32 + lane];
-                }
+                // the piece on (y, x) is read through tap (dy, dx) by output square (y - dy, x - dx)
+                const int oy = (s >> 3) - dy, x = s & 7;
+                if (oy < 0 || oy > 7) continue;
+                const float* row = stage + (oy * 8 + x) * 32 + lane;
+                if (x < 7) acc[p][0] += row[32];        // dx = -1
+                acc[p][1] += row[0];                    // dx =  0
+                if (x > 0) acc[p][2] += row[-32];       // dx = +1
             }
         }
-        __syncwarp();                                   // the next board overwrites the staging rows
     }
-    __syncthreads();                                    // staging rows become the reduction buffer
-    float* mine = acc_all + warp * (109 * 32);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                    // all slots done: the staging buffers become the reduction buffer
+    // ---- sum the slots (channel = fast index: conflict free) into PyTorch order, then coalesced 16-byte reductions
+    float* mine = c1w_smem + warp * (37 * 32);
 #pragma unroll
     for (int p = 0; p < 12; p++)
 #pragma unroll
-        for (int t = 0; t < 9; t++) mine[(t * 12 + p) * 32 + lane] = acc[p][t];
-    mine[108 * 32 + lane] = bias;
+        for (int t = 0; t < 3; t++) mine[(p * 3 + t) * 32 + lane] = acc[p][t];
+    mine[36 * 32 + lane] = bias;
     __syncthreads();
-    for (int i = threadIdx.x; i < 109 * 32; i += C1W_WARPS * 32) {
+    float* out = reinterpret_cast<float*>(c1w_raw + C1W_OFF_OUT);
+    for (int i = threadIdx.x; i < 3 * 36 * 32; i += C1W_THREADS) {
+        const int co = i & 31, cell = (i >> 5) % 36, sb = i / (36 * 32);          // cell = p * 3 + dx index
         float v = 0.f;
-        for (int w = 0; w < C1W_WARPS; w++) v += acc_all[w * (109 * 32) + i];
-        const int cell = i >> 5, co = i & 31;
-        if (cell == 108) atomicAdd(g_b + co, v);
-        else atomicAdd(g_w + co * 108 + (cell % 12) * 9 + cell / 12, v);   // conv1.weight[co][p][tap]
+#pragma unroll
+        for (int sl = 0; sl < C1W_SLOTS; sl++) v += c1w_smem[(sl * 3 + sb) * (37 * 32) + cell * 32 + co];
+        out[co * 108 + (cell / 3) * 9 + sb * 3 + cell % 3] = v;                   // conv1.weight[co][p][tap], tap = (dy+1)*3 + (dx+1)
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 108 / 4; i += C1W_THREADS)
+        atomicAdd(reinterpret_cast<float4*>(g_w) + i, reinterpret_cast<const float4*>(out)[i]);
+    if (threadIdx.x < 32) {
+        float v = 0.f;
+        for (int w = 0; w < C1W_WARPS; w++) v += c1w_smem[w * (37 * 32) + 36 * 32 + threadIdx.x];
+        atomicAdd(g_b + threadIdx.x, v);
     }
 }
 
@@ -281,9 +323,9 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
             cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM);
             attr_set = true;
         }
-        const long long want = (n + C1W_WARPS - 1) / C1W_WARPS;     // 164 registers x 256 threads: one CTA per SM
+        const long long want = (n + C1W_SLOTS - 1) / C1W_SLOTS;     // one CTA of 21 warps per SM (7 x 148 slots: 4 096 boards in 4 rounds)
         const unsigned blocks = (unsigned)(want < device_sm_count() ? want : device_sm_count());
-        conv1_wgrad_kernel<<<blocks, C1W_WARPS * 32, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
+        conv1_wgrad_kernel<<<blocks, C1W_THREADS, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
         count_launch();
     }
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
