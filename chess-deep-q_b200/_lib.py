@@ -43,6 +43,7 @@ SIGNATURES = {
     "cdq_launch_count": (c_uint64, []),
     "cdq_profile_enable": (None, [c_int]),
     "cdq_profile_collect": (c_int, [c_void_p, c_void_p]),
+    "cdq_profile_collect_ex": (c_int, [c_void_p, c_void_p]),
     "cdq_debug_conv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 

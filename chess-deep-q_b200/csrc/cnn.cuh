@@ -38,6 +38,12 @@ int launch_leaf_pipe(const CdqBoard* boards, long long n, const PackedNet& net, 
                      float* leaf, void* ws, cudaStream_t st);
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
                    float* leaf, float* hidden, cudaStream_t st);
+// small batches: fc1's K dimension split over a cluster of four CTAs per tile (fc_split_kernel.cu); launch_fc_head
+// routes batches of at most FC_SPLIT_MAX_TILES tiles of 128 positions there unless CDQ_FC_SPLIT=0
+constexpr long long FC_SPLIT_MAX_TILES = 64;
+bool fc_split_enabled();
+int launch_fc_head_split(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
+                         float* leaf, float* hidden, cudaStream_t st);
 
 size_t train_workspace_bytes(long long n);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2,

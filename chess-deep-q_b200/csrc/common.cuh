@@ -10,7 +10,10 @@ namespace cdq {
 void count_launch(int k = 1);
 
 // optional per-kernel timing with CUDA events on the launching stream (cdq_profile_*)
-enum KernelKind { KK_EVAL = 0, KK_CONV = 1, KK_FC = 2, KK_ENCODE = 3, KK_PLAYOUT = 4, KK_PACK = 5, KK_TRAIN = 6, KK_PIPE = 7, KK_COUNT = 8 };
+enum KernelKind { KK_EVAL = 0, KK_CONV = 1, KK_FC = 2, KK_ENCODE = 3, KK_PLAYOUT = 4, KK_PACK = 5, KK_TRAIN = 6, KK_PIPE = 7, KK_COUNT = 8,
+                  // the training kernels one by one (cdq_profile_collect_ex; cdq_profile_collect folds them into KK_TRAIN)
+                  KK_HEAD_BWD = 8, KK_FC1_WGRAD = 9, KK_FC1_DGRAD = 10, KK_CONV2_BWD = 11, KK_CONV1_WGRAD = 12, KK_ADAM = 13,
+                  KK_COUNT_EX = 16 };
 struct ProfileScope {
     int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     ProfileScope(int kind, cudaStream_t st);

@@ -138,24 +138,30 @@ conv2_bwd_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict
             fence_proxy_async();
             fetch(g + gridDim.x);
         }
-        // ---- data-gradient epilogue: mask, unscale, fp32 [position][square][32]
+        // ---- data-gradient epilogue: mask, unscale, fp32 [position][square][32].  The four tiles are read from
+        // TMEM two at a time: one tcgen05.ld latency per pair instead of per tile.
         const long long pos = g * 8 + r_pos;
-#pragma unroll 1
-        for (int t = 0; t < 4; t++) {
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CB_TM_DG + 32 * t, v);
+#pragma unroll
+        for (int tp = 0; tp < 4; tp += 2) {
+            uint32_t v[2][32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CB_TM_DG + 32 * tp, v[0]);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CB_TM_DG + 32 * (tp + 1), v[1]);
             tmem_ld_wait();
-            const int y = 2 * t + r_yy;
-            const unsigned bits = relu_mask[t];
-            if (pos < n) {
-                float4* o = reinterpret_cast<float4*>(dz1c + (pos * 64 + y * 8 + r_x) * 32);
 #pragma unroll
-                for (int q4 = 0; q4 < 8; q4++) {
-                    float r[4];
+            for (int h = 0; h < 2; h++) {
+                const int t = tp + h;
+                const int y = 2 * t + r_yy;
+                const unsigned bits = relu_mask[t];
+                if (pos < n) {
+                    float4* o = reinterpret_cast<float4*>(dz1c + (pos * 64 + y * 8 + r_x) * 32);
 #pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        r[e] = ((bits >> (q4 * 4 + e)) & 1u) ? __uint_as_float(v[q4 * 4 + e]) * inv_scale : 0.f;
-                    o[q4] = make_float4(r[0], r[1], r[2], r[3]);
+                    for (int q4 = 0; q4 < 8; q4++) {
+                        float r[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            r[e] = ((bits >> (q4 * 4 + e)) & 1u) ? __uint_as_float(v[h][q4 * 4 + e]) * inv_scale : 0.f;
+                        o[q4] = make_float4(r[0], r[1], r[2], r[3]);
+                    }
                 }
             }
         }
@@ -207,7 +213,7 @@ int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __
     }
     const long long groups = ((n + 127) >> 7) * 16;
     const int sms = device_sm_count();
-    ProfileScope ps(KK_TRAIN, st);
+    ProfileScope ps(KK_CONV2_BWD, st);
     conv2_bwd_kernel<<<(unsigned)(groups < sms ? groups : sms), CB_THREADS, CB_SMEM, st>>>(
         dz2_boards, a1_boards, w2tp, groups, n, inv_scale, g_w2, g_b2, dz1c);
     count_launch();

@@ -190,7 +190,7 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
         if (grid < 1) grid = 1;
         float* params = peers.params[0];
         float* grads = peers.grads[0];
-        ProfileScope ps(KK_TRAIN, st);
+        ProfileScope ps(KK_ADAM, st);
         void* args[] = {&params, &grads, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
         cudaError_t e = cudaLaunchCooperativeKernel((const void*)adam_single_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
         count_launch();
@@ -198,7 +198,7 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
     }
     if (grid > sms) grid = sms;          // all CTAs must be co-resident: block 0 waits for the others
     if (grid < 1) grid = 1;
-    ProfileScope ps(KK_TRAIN, st);
+    ProfileScope ps(KK_ADAM, st);
     void* args[] = {(void*)&peers, &rank, &world, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)dp_adam_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
     count_launch();

@@ -107,46 +107,53 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
             const int cg = (int)(item & 3);
             const int pr = q * 32 + lane;
             const long long pos = (tile << 7) + pr;
-            for (int c = 0; c < 4; c++, chunk_no++) {
+            // conv2's ReLU mask of this thread's outputs, gathered half a chunk (128 outputs, 16 loads) AHEAD of its
+            // use: the loads are in flight together and their latency hides under the previous half's epilogue (taken
+            // one block at a time next to the TMEM loads they were 55 % of this kernel's stall samples).
+            // ReLU output > 0 iff its fp16 bits != 0.
+            uint4 mk[16];
+            auto mask_loads = [&](int hc) {           // hc = 2 * chunk + half; blocks p = 4 * half .. 4 * half + 3
+                const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) +
+                                       ((tile * 64 + (cg * 4 + (hc >> 1)) * 4 + (hc & 1) * 2) << 14) + (pr >> 3) * 128 + (pr & 7) * 16;
+#pragma unroll
+                for (int pp = 0; pp < 4; pp++)
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+                        mk[pp * 4 + g] = pos < n ? *reinterpret_cast<const uint4*>(mbase + ((pp >> 1) << 14) + ((pp & 1) * 4 + g) * 2048)
+                                                 : make_uint4(0, 0, 0, 0);
+            };
+            mask_loads(0);
+            for (int hc = 0; hc < 8; hc++) {
+                const int c = hc >> 1, half = hc & 1;
                 const int ab = chunk_no & 1;
-                // conv2's ReLU mask of this thread's 256 outputs, gathered BEFORE the accumulator is waited for: the 32
-                // loads are in flight together and their latency hides under the MMAs (taken one block at a time next
-                // to the TMEM loads they were 55 % of this kernel's stall samples).  ReLU output > 0 iff its fp16 bits != 0.
-                unsigned relu_bits[8];
-                {
-                    const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + (cg * 4 + c) * 4) << 14) +
-                                           (pr >> 3) * 128 + (pr & 7) * 16;
-                    uint4 mk[32];
+                unsigned relu_bits[4];
 #pragma unroll
-                    for (int p = 0; p < 8; p++)
+                for (int pp = 0; pp < 4; pp++) {
+                    unsigned bits = 0;
 #pragma unroll
-                        for (int g = 0; g < 4; g++)
-                            mk[p * 4 + g] = pos < n ? *reinterpret_cast<const uint4*>(mbase + ((p >> 1) << 14) + ((p & 1) * 4 + g) * 2048)
-                                                    : make_uint4(0, 0, 0, 0);
+                    for (int g = 0; g < 4; g++) {
+                        const unsigned mw[4] = {mk[pp * 4 + g].x, mk[pp * 4 + g].y, mk[pp * 4 + g].z, mk[pp * 4 + g].w};
 #pragma unroll
-                    for (int p = 0; p < 8; p++) {
-                        unsigned bits = 0;
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            const unsigned mw[4] = {mk[p * 4 + g].x, mk[p * 4 + g].y, mk[p * 4 + g].z, mk[p * 4 + g].w};
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (g * 8 + 2 * e);
-                                bits |= ((mw[e] >> 16) ? 1u : 0u) << (g * 8 + 2 * e + 1);
-                            }
+                        for (int e = 0; e < 4; e++) {
+                            bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (g * 8 + 2 * e);
+                            bits |= ((mw[e] >> 16) ? 1u : 0u) << (g * 8 + 2 * e + 1);
                         }
-                        relu_bits[p] = bits;
                     }
+                    relu_bits[pp] = bits;
                 }
-                mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
-                tc_fence_after();
+                if (hc < 7) mask_loads(hc + 1);
+                if (half == 0) {
+                    mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
+                    tc_fence_after();
+                }
 #pragma unroll
-                for (int p = 0; p < 8; p++) {
+                for (int pp = 0; pp < 4; pp++) {
+                    const int p = half * 4 + pp;
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
                     tmem_ld_wait();
                     const int sq = (cg * 4 + c) * 4 + (p >> 1), ch0 = (p & 1) * 32;
-                    const unsigned bits = relu_bits[p];
+                    const unsigned bits = relu_bits[pp];
                     if (pos < n) {
                         // conv2-backward board of this position's group: [8 chunks][10 ranks][8 pos][10 files][8 halfs]
                         uint8_t* o = reinterpret_cast<uint8_t*>(dz2_boards) + (pos >> 3) * 102400 + (ch0 >> 3) * 12800 +
@@ -166,9 +173,12 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + ab);
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + ab);
+                    chunk_no++;
+                }
             }
         }
     }
@@ -282,7 +292,7 @@ int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp
     }
     const long long items = ((n + 127) >> 7) * 4;
     const int sms = device_sm_count();
-    ProfileScope ps(KK_TRAIN, st);
+    ProfileScope ps(KK_FC1_DGRAD, st);
     fc1_dgrad_kernel<<<(unsigned)(items < sms ? items : sms), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, dz2_boards);
     count_launch();
     return (int)cudaGetLastError();
@@ -297,7 +307,7 @@ int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float 
     }
     const long long tiles = (n + 127) >> 7;
     const int k_splits = (int)(tiles < 4 ? tiles : 4);
-    ProfileScope ps(KK_TRAIN, st);
+    ProfileScope ps(KK_FC1_WGRAD, st);
     fc1_wgrad_kernel<<<32 * k_splits, WG_THREADS, WG_SMEM, st>>>(dz1h, act2, tiles, k_splits, inv_scale, g_fc1_w);
     count_launch();
     return (int)cudaGetLastError();

@@ -132,6 +132,7 @@ int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float*
                    float* leaf, float* hidden, cudaStream_t st) {
     if (n == 0) return 0;
     const long long tiles = (n + 127) / 128;
+    if (tiles <= FC_SPLIT_MAX_TILES && fc_split_enabled()) return launch_fc_head_split(act2, n, net, value, flags, leaf, hidden, st);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(fc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);

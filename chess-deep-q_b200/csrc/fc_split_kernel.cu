@@ -1,0 +1,216 @@
+// fc_split_kernel.cu -- K2b for SMALL batches: fc1 (4096 -> 256) + ReLU + fc2 (256 -> 1) + tanh with the K
+// dimension of fc1 split over a thread-block CLUSTER of four CTAs.
+//
+// fc_head_kernel gives every 128-position tile to one CTA, which streams 3 MB (1 MB of act2, 2 MB of fc1
+// weights) through its shared memory: about 27 us at the 110 GB/s one SM pulls from L2, whatever the batch
+// size.  A replay batch of 4 096 positions is 32 tiles, so 32 of the 148 SMs worked for those 27 us, twice per
+// training step, and an MCTS wave of a few thousand leaves paid the same latency.  Here a tile belongs to a
+// cluster of four CTAs:
+//   * CTA r contracts squares 16 r .. 16 r + 15 (768 KB of operands, 64 UMMAs of M = 128, N = 256, K = 16)
+//     into its own TMEM accumulator;
+//   * every CTA parks its 128 x 256 fp32 partial sums in its shared memory (the operand ring is dead by then),
+//     column-major, so that a warp reads 128 contiguous bytes per column;
+//   * after a cluster barrier CTA r owns fc1 outputs 64 r .. 64 r + 63: it adds the four partial sums through
+//     distributed shared memory (always in rank order 0, 1, 2, 3, so the bits do not depend on who adds),
+//     applies bias + ReLU, optionally keeps ReLU(fc1) for the backward pass, and reduces its slice of the fc2
+//     dot product per position;
+//   * the four partial dot products meet in CTA 0's shared memory (remote stores, second cluster barrier), and
+//     CTA 0 applies fc2's bias, tanh and the leaf post-processing of mcts.py:196-232.
+// No global scratch, no atomics, no second launch.  Used for at most FC_SPLIT_MAX_TILES tiles (two waves of
+// 32 clusters); larger batches keep the persistent one-CTA-per-tile kernel, whose fp32 summation order differs
+// (one chain of 256 UMMAs instead of four chains of 64), so values from the two kernels agree to fp32 rounding,
+// not bit for bit.
+#include <cstdlib>
+#include "fc_head.cuh"
+
+namespace cdq {
+
+constexpr int FS_SPLIT = 4;                               // CTAs per cluster = K slices
+constexpr int FS_SQUARES = 64 / FS_SPLIT;                 // squares (K stages) per CTA
+constexpr int FS_STAGES = 4;
+constexpr int FS_STAGE_BYTES = FC_A_BYTES + FC_B_BYTES;   // 48 KB
+constexpr int FS_PART_BYTES = 256 * 128 * 4;              // partial sums [256 columns][128 rows] fp32, over the ring
+static_assert(FS_PART_BYTES <= FS_STAGES * FS_STAGE_BYTES, "partial sums alias the operand ring");
+constexpr int FS_OFF_VEC = FS_STAGES * FS_STAGE_BYTES;    // fc1 bias[256], fc2 weight[256], fc2 bias (+ pad)
+constexpr int FS_OFF_DOT = FS_OFF_VEC + 2 * 256 * 4 + 16; // [4 ranks][128 rows] partial fc2 dot products (CTA 0's copy is used)
+constexpr int FS_OFF_BAR = FS_OFF_DOT + FS_SPLIT * 128 * 4;
+constexpr int FS_SMEM = FS_OFF_BAR + 128;
+static_assert(FS_SMEM <= 227 * 1024, "fc split kernel shared memory");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float dsmem_ld(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(FS_SPLIT, 1, 1) __launch_bounds__(FC_THREADS, 1)
+fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedNet net, float* __restrict__ value,
+                     const unsigned* __restrict__ flags, float* __restrict__ leaf, float* __restrict__ hidden) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* sb1 = reinterpret_cast<float*>(smem + FS_OFF_VEC);
+    float* sw2 = sb1 + 256;
+    float* sb2 = sw2 + 256;
+    float* sdot = reinterpret_cast<float*>(smem + FS_OFF_DOT);
+    float* part = reinterpret_cast<float*>(smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + FS_OFF_BAR);   // [FS_STAGES]
+    uint64_t* empty = full + FS_STAGES;                                // [FS_STAGES]
+    uint64_t* acc_full = empty + FS_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const long long tile = blockIdx.x / FS_SPLIT;
+    for (int i = tid; i < 256; i += (int)blockDim.x) { sb1[i] = net.fc1_b[i]; sw2[i] = net.fc2_w[i]; }
+    if (tid == 0) {
+        sb2[0] = net.fc2_b[0];
+        for (int s = 0; s < FS_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+
+    if (warp == 0) {
+        // ---------------- producer: this CTA's 16 squares of (A, B) K-stages
+        if (lane == 0) {
+            const uint8_t* a_tile = reinterpret_cast<const uint8_t*>(act2) + (tile << 20);
+            for (int i = 0; i < FS_SQUARES; i++) {
+                const int sq = (int)rank * FS_SQUARES + i;
+                const int st = i % FS_STAGES;
+                mbar_wait(empty + st, ((i / FS_STAGES) & 1) ^ 1);
+                uint8_t* sa = smem + st * FS_STAGE_BYTES;
+                mbar_arrive_expect_tx(full + st, FS_STAGE_BYTES);
+                bulk_g2s(sa, a_tile + ((long long)sq << 14), FC_A_BYTES, full + st);
+                bulk_g2s(sa + FC_A_BYTES, reinterpret_cast<const uint8_t*>(net.fc1p) + ((long long)sq << 15), FC_B_BYTES, full + st);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            for (int i = 0; i < FS_SQUARES; i++) {
+                const int st = i % FS_STAGES;
+                mbar_wait(full + st, (i / FS_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a = smem_u32(smem + st * FS_STAGE_BYTES), b = a + FC_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    umma_f16(tmem, make_smem_desc(a + j * 2 * 2048, 2048, 128), make_smem_desc(b + j * 2 * 4096, 4096, 128), IDESC,
+                             (i | j) != 0);
+                umma_commit(empty + st);
+            }
+            umma_commit(acc_full);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue, phase 1: park the partial sums (TMEM lane quarter = warp % 4, row = position)
+        const int q = warp & 3, row = q * 32 + lane;
+        mbar_wait(acc_full, 0);             // all UMMAs done: the operand ring is free
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 8; c++) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) part[(c * 32 + j) * 128 + row] = __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+    }
+    cluster_sync_all();                     // every CTA's partial sums are visible cluster-wide
+
+    if (warp >= 2) {
+        // ---------------- phase 2: fc1 outputs 64 rank .. 64 rank + 63 of all 128 positions
+        const int q = warp & 3, row = q * 32 + lane;
+        const long long pos = (tile << 7) + row;
+        uint32_t pbase[FS_SPLIT];
+#pragma unroll
+        for (int k = 0; k < FS_SPLIT; k++) pbase[k] = dsmem_addr(smem_u32(part), (uint32_t)k) + (uint32_t)row * 4u;
+        float dot = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+            float p[FS_SPLIT][8];
+#pragma unroll
+            for (int k = 0; k < FS_SPLIT; k++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) p[k][j] = dsmem_ld(pbase[k] + (uint32_t)(((int)rank * 64 + c0 + j) * 128 * 4));
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c = (int)rank * 64 + c0 + j;
+                const float z = ((p[0][j] + p[1][j]) + p[2][j]) + p[3][j];       // rank order, whoever adds
+                h[j] = fmaxf(z + sb1[c], 0.f);
+                dot = fmaf(h[j], sw2[c], dot);
+            }
+            if (hidden && pos < n) {
+                float4* hp = reinterpret_cast<float4*>(hidden + pos * 256 + (int)rank * 64 + c0);
+                hp[0] = make_float4(h[0], h[1], h[2], h[3]);
+                hp[1] = make_float4(h[4], h[5], h[6], h[7]);
+            }
+        }
+        dsmem_st(dsmem_addr(smem_u32(sdot), 0u) + (uint32_t)(((int)rank * 128 + row) * 4), dot);
+    }
+    cluster_sync_all();                     // partial dot products have landed in CTA 0; nobody reads remote memory after this
+
+    if (rank == 0 && warp >= 2) {
+        const int q = warp & 3, row = q * 32 + lane;
+        const long long pos = (tile << 7) + row;
+        if (pos < n) {
+            const float v = tanhf((((sdot[row] + sdot[128 + row]) + sdot[256 + row]) + sdot[384 + row]) + sb2[0]);
+            if (value) value[pos] = v;
+            if (leaf) {
+                // mcts.py:196-232: terminal short-circuits, else clamp(net, -1, 1)
+                const unsigned f = flags[pos];
+                float lv = fminf(1.f, fmaxf(-1.f, v));
+                if (f & CDQ_F_CHECKMATE) lv = (f & CDQ_F_WHITE_TO_MOVE) ? -1.f : 1.f;
+                else if (f & (CDQ_F_STALEMATE | CDQ_F_INSUFFICIENT | CDQ_F_REP3)) lv = 0.f;
+                leaf[pos] = lv;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+bool fc_split_enabled() {      // read on every call so that one process can A/B the two kernels
+    const char* e = getenv("CDQ_FC_SPLIT");
+    return !(e && e[0] == '0');
+}
+
+int launch_fc_head_split(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
+                         float* leaf, float* hidden, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fc_head_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
+        attr_set = true;
+    }
+    const long long tiles = (n + 127) / 128;
+    ProfileScope ps(KK_FC, st);
+    fc_head_split_kernel<<<(unsigned)(tiles * FS_SPLIT), FC_THREADS, FS_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+} // namespace cdq

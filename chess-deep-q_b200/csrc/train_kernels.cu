@@ -221,7 +221,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
                 float eps, float grad_scale, cudaStream_t st) {
     if (n == 0) return 0;
     const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
-    ProfileScope ps(KK_TRAIN, st);
+    ProfileScope ps(KK_ADAM, st);
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
     count_launch();
     return (int)cudaGetLastError();
@@ -300,7 +300,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     // ---- loss, tanh, fc2, fc1 bias
     const float scale = 64.f * (float)n;      // lift into fp16's normal range; undone in the fp32 epilogues
     {
-        ProfileScope ps(KK_TRAIN, st);
+        ProfileScope ps(KK_HEAD_BWD, st);
         const long long n_pad = ((n + 127) >> 7) << 7;
         const unsigned blocks = (unsigned)(n_pad / 8 < 1184 ? n_pad / 8 : 1184);
         head_bwd_kernel<<<blocks, 256, 0, st>>>(ws.q, ws.qn, reward, done, ws.hidden, w.fc2_w, n, gamma, loss_kind, scale, ws.dz1h,
@@ -317,7 +317,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
                               ws.dz1c, st))) return e;
     {
         // ---- conv1: weight + bias gradient by scatter over the one-hot input
-        ProfileScope ps(KK_TRAIN, st);
+        ProfileScope ps(KK_CONV1_WGRAD, st);
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM);

@@ -240,6 +240,9 @@ uint64_t cdq_launch_count(void);
  * 5 weight pack, 6 train. */
 void cdq_profile_enable(int on);
 int cdq_profile_collect(double* ms_per_kind /*[8]*/, uint64_t* launches_per_kind /*[8]*/);
+/* same, training kernels one by one: kinds 8 head (loss/tanh/fc2), 9 fc1 weight gradient, 10 fc1 data gradient,
+ * 11 conv2 backward, 12 conv1 weight gradient, 13 optimizer (kind 6 stays empty) */
+int cdq_profile_collect_ex(double* ms_per_kind /*[16]*/, uint64_t* launches_per_kind /*[16]*/);
 
 /* Parity/debug hook: runs only the conv stack; dumps ReLU(conv1) as fp16 [n][64][32] (optional)
  * and the fc1 operand tiles (fp16, ceil(n/128) MiB). */

@@ -197,21 +197,37 @@ def test_value_ragged_batch_sizes(cdq, oracle, n):
     assert np.abs(v - ref).max() <= 1e-3
 
 
-def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle):
+def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle, monkeypatch):
     """The stream conv kernel hands tiles between five warp roles through ~50 mbarriers; a missing
     fence or a slot reused too early would show up as run-to-run or placement-dependent bits.
     Twelve repetitions and evaluations of shifted sub-ranges (other tile / CTA assignment, other
-    ring phases) must reproduce every value bit for bit."""
+    ring phases) must reproduce every value bit for bit.  Batches of at most 8 192 positions take
+    the cluster split-K fc kernel (fc_split_kernel.cu), whose fp32 summation order differs from the
+    persistent kernel's: with CDQ_FC_SPLIT=0 they must reproduce the large batch's bits as well,
+    with the split kernel they must agree to fp32 rounding and be bitwise stable among themselves."""
     n = 200_000
     d = _dev_playouts(cdq, n, seed=9)
     net, _ = _make_net(cdq, oracle, 3.0)
+    small = [(1, 4095), (3, 16), (5, 1), (777, 8192)]
     with torch.no_grad():
         ref = net.forward_packed(d).reshape(-1).clone()
         for _ in range(12):
             assert torch.equal(net.forward_packed(d).reshape(-1), ref)
-        for off, cnt in [(1, 4095), (17, 70_001), (12_345, 132_608), (99_999, 100_001), (3, 16), (5, 1)]:
+        for off, cnt in [(17, 70_001), (12_345, 132_608), (99_999, 100_001), (777, 8193)]:
             v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
             assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
+        monkeypatch.setenv("CDQ_FC_SPLIT", "0")
+        for off, cnt in small:
+            v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
+            assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
+        monkeypatch.delenv("CDQ_FC_SPLIT")
+        split_ref = net.forward_packed(d[:8192].contiguous()).reshape(-1).clone()
+        assert (split_ref - ref[:8192]).abs().max().item() <= 5e-6      # |value| up to 0.99 with these weights
+        for _ in range(12):
+            assert torch.equal(net.forward_packed(d[:8192].contiguous()).reshape(-1), split_ref)
+        for off, cnt in [(1, 4095), (3, 16), (5, 1), (130, 8000), (4000, 4192)]:
+            v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
+            assert torch.equal(v, split_ref[off:off + cnt]), (off, cnt)
 
 
 def test_pipe_kernel_equals_two_kernel_path(cdq, oracle, monkeypatch):
