@@ -28,7 +28,7 @@ int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __
                      float* g_w2, float* g_b2, float* dz1c, cudaStream_t st);
 int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float inv_scale, float* g_fc1_w, cudaStream_t st);
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
-                      cudaStream_t st, __half* act1_boards = nullptr);
+                      cudaStream_t st, __half* act1_boards = nullptr, int max_ctas = 0);
 int launch_conv_stack_v1(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                          cudaStream_t st, __half* act1_boards);
 // conv stack + fc head as one persistent kernel with an L2-resident hand-over (pipe_kernel.cu)

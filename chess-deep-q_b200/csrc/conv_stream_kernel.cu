@@ -22,7 +22,7 @@ extern "C" int cdq_debug_set_trace(long long* d_buf) {
 #endif
 
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
-                      cudaStream_t st, __half* act1_boards) {
+                      cudaStream_t st, __half* act1_boards, int max_ctas) {
     if (n == 0) return 0;
     static const bool use_v1 = getenv("CDQ_CONV_V1") != nullptr;   // A/B switch, see conv_kernel.cu
     if (use_v1) return launch_conv_stack_v1(boards, n, net, act2, dbg_act1, st, act1_boards);
@@ -33,7 +33,8 @@ int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net,
     }
     const long long tiles = ((n + 127) >> 7) * (128 / cs::TILE_POS);
     const int sms = device_sm_count();
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    if (max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;   // leave SMs to a concurrent launch
     ProfileScope ps(KK_CONV, st);
     cs::conv_stream_kernel<<<grid, cs::THREADS, cs::SMEM, st>>>(boards, n, net, act2, dbg_act1, act1_boards);
     count_launch();

@@ -289,12 +289,16 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     // ---- forward: target value of next_states (inference, side stream) next to q of states (keeps activations)
     CDQ_CUDA(cudaEventRecord(g_side.fork, st));
     CDQ_CUDA(cudaStreamWaitEvent(side, g_side.fork, 0));
-    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side))) return e;
+    // The two conv launches are persistent, one CTA per SM, and cannot share an SM (170 KB of shared memory each):
+    // on the whole machine they would run one after the other, each with its own prologue and a half-empty
+    // last round, so each gets half of the SMs and they run side by side.
+    const int half_sms = device_sm_count() / 2;
+    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, half_sms))) return e;
     if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
     // the online network's fp16 tiles are rebuilt from the fp32 parameters next to the target forward
     if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st))) return e;
-    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards))) return e;
+    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards, half_sms))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // ---- loss, tanh, fc2, fc1 bias

@@ -330,7 +330,11 @@ class GraphedDQNStep:
             self._body()                       # eager once: function attributes, lazy tables
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # Captured on a HIGH-priority stream: the library's side stream (target forward, fc1 weight gradient)
+            # has default = lowest priority, so wherever both have CTAs pending the critical chain
+            # (fc1 data gradient -> conv2 backward -> conv1 gradient) gets the SMs first and the weight
+            # gradient fills what it leaves free.  Kernel nodes inherit the priority of the stream they were captured on.
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(priority=-1)):
                 self._body()
             self.graph = g
             self.optimizer.step_count -= 1     # capture recorded the launch but did not run it
