@@ -204,7 +204,8 @@ conv2_bwd_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
+// first formulation (whole groups, one buffer); CDQ_CONV2_BWD_V1=1 selects it in launch_conv2_bwd (conv_bwd2_kernel.cu)
+int launch_conv2_bwd_v1(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
                      float* g_w2, float* g_b2, float* dz1c, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
