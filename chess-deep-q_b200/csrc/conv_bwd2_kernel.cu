@@ -1,15 +1,20 @@
 // conv_bwd2_kernel.cu -- backward of conv2 (32 -> 64, 3x3) on tcgen05, pipelined over HALF groups.
 //
-// Same math and the same global board layouts as conv_bwd_kernel.cu (kept behind CDQ_CONV2_BWD_V1=1):
-//   dz2 boards  [group of 8 positions][8 chunks of 8 out-channels][10 ranks][8 positions][10 files][8 halfs]
-//   a1  boards  [group of 8 positions][4 chunks of 8 in-channels ][10 ranks][8 positions][10 files][8 halfs]
-//   weight gradient  dW2[co][ci][tap] += sum_cells dz2[cell][co] * a1[cell + tap][ci]      M = 64, N = 32, K = 16 cells, MN-major
+// Operands are zero-bordered boards, so that every 3x3 tap is an operand start address:
+//   dz2 boards  [group of 4 positions][8 chunks of 8 out-channels][10 ranks][4 positions][10 files][8 halfs]   (fc1_dgrad_kernel)
+//   a1  boards  [group of 4 positions][10 ranks][4 chunks of 8 in-channels][4 positions][10 files][8 halfs]    (the forward's epilogue 1)
+//   weight gradient  dW2[co][ci][tap] += sum_cells dz2[cell][co] * a1[cell + tap][ci]      M = 64, N = 3 x 32, K = 16 cells, MN-major
+//       The a1 boards are RANK-major: (kernel row dy, channel chunk) is one linear index with a 640-byte stride,
+//       so the three taps of a kernel COLUMN are one B operand of N = 96 and a UMMA fills three tap accumulators.
+//       A small UMMA costs about 40 + 0.22 N cycles whatever it computes, so what counts is their number:
+//       48 per unit instead of 144 (one per tap, N = 32).
 //   bias gradient    db2[co] += sum_cells dz2[cell][co]                                    same A against a tile of ones
 //   data gradient    dz1[cell][ci] = ReLU'(a1) * sum_{co,tap} dz2[cell - tap][co] W2[co][ci][tap]   M = 128, N = 32, K = 64
-// The first kernel handled a whole group (150 KB of boards) per iteration with one buffer: load, UMMAs and
+// The first kernel (removed) handled a whole group (150 KB of boards) per iteration with one buffer: load, UMMAs and
 // epilogue ran one after the other (3.4 + 7.4 + 3 us per group, four rounds of 148 CTAs over 512 groups, the
-// last one 46 % full).  Here the unit of work is HALF a group (positions 0..3 or 4..7: 75 KB of boards, fetched
-// as 120 bulk copies of 640 bytes, one per chunk and rank), so that
+// last one 46 % full).  Here the unit of work is a group of FOUR positions (75 KB of boards, which the producers of
+// the boards lay out so that a unit is two contiguous blocks: two bulk copies; as 120 copies of 640 bytes out of
+// 8-position groups the fetch, not the UMMAs, set the pace), so that
 //   * two units fit in shared memory: the producer warp fetches unit i+1 while the UMMAs of unit i run;
 //   * the data-gradient accumulators are double buffered in TMEM: the epilogue warps drain unit i while the
 //     UMMAs of unit i+1 run;
@@ -23,10 +28,9 @@
 namespace cdq {
 namespace cb2 {
 
-constexpr int G_ROW = 160, G_RANK = 1280, G_CHUNK = 12800;          // global board strides (group of 8 positions)
-constexpr int G_DZ2 = 8 * G_CHUNK, G_A1 = 4 * G_CHUNK;              // 102 400 / 51 200 bytes per group
-constexpr int ROW = 160, RANK = 640, CHUNK = 6400;                  // shared-memory strides (unit of 4 positions)
-constexpr int U_DZ2 = 8 * CHUNK, U_A1 = 4 * CHUNK, U_BYTES = U_DZ2 + U_A1;     // 51 200 + 25 600 = 76 800
+constexpr int ROW = 160, RANK = 640, CHUNK = 6400;                  // dz2 unit strides, global = shared memory
+constexpr int A_CHUNK = 4 * ROW, A_RANK = 4 * A_CHUNK;               // a1 unit, rank-major: 640 / 2 560
+constexpr int U_DZ2 = 8 * CHUNK, U_A1 = 10 * A_RANK, U_BYTES = U_DZ2 + U_A1;   // 51 200 + 25 600 = 76 800
 constexpr int W_BYTES = 9 * 64 * 32 * 2;                            // 36 864 : [9 taps][8 chunks of co][4 groups of ci][8 ci][8 co]
 constexpr int OFF_W = 2 * U_BYTES;
 constexpr int OFF_ONES = OFF_W + W_BYTES;
@@ -34,7 +38,7 @@ constexpr int OFF_BAR = OFF_ONES + 256;
 constexpr int SMEM = OFF_BAR + 128;
 static_assert(SMEM <= 227 * 1024, "conv2 backward shared memory");
 constexpr int THREADS = 192;
-constexpr int TM_BIAS = 288, TM_DG = 320;       // TMEM columns: taps 0..287, bias 288..295, data-gradient 320 + 64 buffer + 32 tile
+constexpr int TM_BIAS = 288, TM_DG = 320;       // TMEM columns: taps at 96 dx + 32 dy + ci, bias 288..295, data-gradient 320 + 64 buffer + 32 tile
 constexpr int WT_STRIDE = 292;                  // floats per co row of the staged weight-gradient tile
 static_assert(64 * WT_STRIDE * 4 <= U_BYTES, "weight-gradient tile is staged over unit buffer 0");
 
@@ -79,28 +83,24 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
             const int b = (int)(i & 1);
             mbar_wait(empty + b, ((i >> 1) & 1) ^ 1);
             if (lane == 0) mbar_arrive_expect_tx(full + b, U_BYTES);
-            __syncwarp();
-            const uint8_t* gd = reinterpret_cast<const uint8_t*>(dz2_boards) + (u >> 1) * G_DZ2 + (u & 1) * (4 * G_ROW);
-            const uint8_t* ga = reinterpret_cast<const uint8_t*>(a1_boards) + (u >> 1) * G_A1 + (u & 1) * (4 * G_ROW);
-            uint8_t* sb = smem + b * U_BYTES;
-            for (int c = lane; c < 120; c += 32) {               // (chunk, rank): 4 rows of 160 bytes each
-                const int ch = c / 10, rk = c - ch * 10;
-                if (ch < 8) bulk_g2s(sb + ch * CHUNK + rk * RANK, gd + ch * G_CHUNK + rk * G_RANK, RANK, full + b);
-                else bulk_g2s(sb + U_DZ2 + (ch - 8) * CHUNK + rk * RANK, ga + (ch - 8) * G_CHUNK + rk * G_RANK, RANK, full + b);
+            if (lane == 0) {
+                uint8_t* sb = smem + b * U_BYTES;
+                bulk_g2s(sb, reinterpret_cast<const uint8_t*>(dz2_boards) + u * U_DZ2, U_DZ2, full + b);
+                bulk_g2s(sb + U_DZ2, reinterpret_cast<const uint8_t*>(a1_boards) + u * U_A1, U_A1, full + b);
             }
         }
     } else if (warp == 1) {
         // ---------------- UMMA issuer
         if (elect_one_sync()) {
-            constexpr uint32_t ID_WG = make_idesc_f16_ex(64, 32, true, true);
-            constexpr uint32_t ID_BIAS = make_idesc_f16_ex(64, 8, true, true);
+            constexpr uint32_t ID_WG = make_idesc_f16_ex(64, 96, true, true);
+            constexpr uint32_t ID_B1 = make_idesc_f16_ex(64, 8, true, true);
             constexpr uint32_t ID_DG = make_idesc_f16(128, 32);
             mbar_wait(bar_w, 0);
             // Every operand descriptor is a per-buffer base plus a COMPILE-TIME offset (all loops below are fully
             // unrolled): with run-time descriptor arithmetic the single issuing thread, not the tensor pipe, set
             // the pace (about 50 cycles per UMMA, 232 UMMAs per unit).
             const uint64_t dA_wg0 = make_smem_desc(s0 + 4 * ROW + 16, ROW, CHUNK);             // dz2, MN-major, interior
-            const uint64_t dB_wg0 = make_smem_desc(s0 + U_DZ2 + 4 * ROW + 16, ROW, CHUNK);     // a1,  MN-major, interior
+            const uint64_t dB_wg0 = make_smem_desc(s0 + U_DZ2, ROW, A_CHUNK);                  // a1,  MN-major: rank 0 = dy -1 of the first interior rank, file 0 = dx -1
             const uint64_t dA_dg0 = make_smem_desc(s0, CHUNK, ROW);                            // dz2, K-major
             const uint64_t dB_w = make_smem_desc(s0 + OFF_W, 512, 128);
             const uint64_t d_ones = make_smem_desc(s0 + OFF_ONES, 128, 128);
@@ -113,19 +113,18 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
                 const uint64_t boff = (uint64_t)(b * (U_BYTES >> 4));
                 const uint64_t dA_wg = dA_wg0 + boff, dB_wg = dB_wg0 + boff, dA_dg = dA_dg0 + boff;
                 const bool acc0 = i != 0;
-                // ---- weight gradient: 9 taps x 16 steps of 16 cells (two rows of 8 files); interior row groups 4..35
+                // ---- weight gradient: 16 steps of 16 cells (two rows of 8 files, interior row groups 4..35) x 3 kernel
+                // columns; B = the a1 rows of ranks R-1, R, R+1 (N = 3 x 32, 640 bytes between 8-channel groups)
 #pragma unroll
-                for (int tap = 0; tap < 9; tap++) {
-                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                for (int k = 0; k < 16; k++)
 #pragma unroll
-                    for (int k = 0; k < 16; k++)
-                        umma_f16(tmem + tap * 32, dA_wg + (uint64_t)((k * 2 * ROW) >> 4),
-                                 dB_wg + (uint64_t)(long long)((k * 2 * ROW + dy * RANK + dx * 16) / 16), ID_WG, k != 0 || acc0);
-                }
+                    for (int dxi = 0; dxi < 3; dxi++)
+                        umma_f16(tmem + dxi * 96, dA_wg + (uint64_t)((k * 2 * ROW) >> 4),
+                                 dB_wg + (uint64_t)(((k >> 1) * A_RANK + (k & 1) * 2 * ROW + dxi * 16) >> 4), ID_WG, k != 0 || acc0);
                 // ---- bias gradient: same A against ones
 #pragma unroll
                 for (int k = 0; k < 16; k++)
-                    umma_f16(tmem + TM_BIAS, dA_wg + (uint64_t)((k * 2 * ROW) >> 4), d_ones, ID_BIAS, k != 0 || acc0);
+                    umma_f16(tmem + TM_BIAS, dA_wg + (uint64_t)((k * 2 * ROW) >> 4), d_ones, ID_B1, k != 0 || acc0);
                 // ---- data gradient: 2 tiles (4 ranks x 4 positions x 8 files) x 9 flipped taps x 4 K-steps of 16 out-channels
                 const uint32_t dg = tmem + TM_DG + 64 * b;
 #pragma unroll
@@ -160,11 +159,11 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
 #pragma unroll
             for (int t = 0; t < 2; t++) {
                 const int y = 4 * t + r_rk;
-                const uint8_t* m = smem + b * U_BYTES + U_DZ2 + (y + 1) * RANK + r_pos * ROW + (r_x + 1) * 16;
+                const uint8_t* m = smem + b * U_BYTES + U_DZ2 + (y + 1) * A_RANK + r_pos * ROW + (r_x + 1) * 16;
                 unsigned bits = 0;
 #pragma unroll
                 for (int kc = 0; kc < 4; kc++) {
-                    const uint4 mk = *reinterpret_cast<const uint4*>(m + kc * CHUNK);
+                    const uint4 mk = *reinterpret_cast<const uint4*>(m + kc * A_CHUNK);
                     const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                     for (int e = 0; e < 8; e++)
@@ -181,7 +180,7 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dg_empty + b);
-            const long long pos = (u >> 1) * 8 + (u & 1) * 4 + r_pos;
+            const long long pos = u * 4 + r_pos;
             if (pos < n) {
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
@@ -210,7 +209,7 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
 #pragma unroll 1
             for (int tap = 0; tap < 9; tap++) {
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tap * 32, v);
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (tap % 3) * 96 + (tap / 3) * 32, v);   // tap = 3 (dy + 1) + (dx + 1)
                 tmem_ld_wait();
                 if (lane < 16) {
 #pragma unroll
@@ -236,19 +235,14 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
 
 } // namespace cb2
 
-int launch_conv2_bwd_v1(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
-                        float* g_w2, float* g_b2, float* dz1c, cudaStream_t st);
-
 int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
                      float* g_w2, float* g_b2, float* dz1c, cudaStream_t st) {
-    static const bool use_v1 = [] { const char* e = getenv("CDQ_CONV2_BWD_V1"); return e && e[0] == '1'; }();
-    if (use_v1) return launch_conv2_bwd_v1(dz2_boards, a1_boards, w2tp, n, inv_scale, g_w2, g_b2, dz1c, st);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(cb2::conv2_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb2::SMEM);
         attr_set = true;
     }
-    const long long units = ((n + 127) >> 7) * 32;      // half groups of 4 positions
+    const long long units = ((n + 127) >> 7) * 32;      // groups of 4 positions
     const int sms = device_sm_count();
     ProfileScope ps(KK_CONV2_BWD, st);
     cb2::conv2_bwd2_kernel<<<(unsigned)(units < sms ? units : sms), cb2::THREADS, cb2::SMEM, st>>>(

@@ -108,9 +108,12 @@ constexpr int TM_C1 = 64 * S2;      // conv1 slot s: columns TM_C1 + 32 s
 static_assert(TM_C1 + 32 * S1 <= 512, "TMEM columns");
 static_assert(RP == 8, "the plane encoder addresses slab = file");
 
-// layout of the training copy of ReLU(conv1) (consumed by conv_bwd_kernel.cu): zero-bordered boards
+// layout of the training copy of ReLU(conv1) (consumed by conv_bwd2_kernel.cu): zero-bordered boards
 // per group of 8 positions, [4 chunks][10 ranks][8 positions][10 files][16 B]
-constexpr int TB_ROW = 160, TB_RANK = 8 * TB_ROW, TB_CHUNK = 10 * TB_RANK, TB_GROUP = 4 * TB_CHUNK;
+// training boards of ReLU(conv1), RANK-major in groups of FOUR positions (the unit conv_bwd2_kernel.cu fetches with one bulk
+// copy): [group][10 ranks][4 channel chunks][4 positions][10 files][8 halfs]; (kernel row dy, channel chunk) is ONE linear
+// index for conv2's weight gradient
+constexpr int TB_ROW = 160, TB_CHUNK = 4 * TB_ROW, TB_RANK = 4 * TB_CHUNK, TB_GROUP = 10 * TB_RANK;
 
 // ---------------------------------------------------------------- MMA issue of one source file step
 // A source file feeds output files x-1, x, x+1 (dx blocks 0, 1, 2 of the re-ordered weights) whose
@@ -412,8 +415,8 @@ __device__ __forceinline__ void conv_stream_body(uint8_t* smem, const CdqBoard* 
                 u.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]), __uint_as_float(v[kc * 8 + 7]));
                 *reinterpret_cast<uint4*>(dst + kc * CHUNK_B) = u;
                 if (act1_boards)   // training: ReLU(conv1) as zero-bordered boards for conv2's backward pass
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 3) * TB_GROUP + kc * TB_CHUNK +
-                                              (y + 1) * TB_RANK + (int)(pos & 7) * TB_ROW + (f + 1) * CELL) = u;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 2) * TB_GROUP + kc * TB_CHUNK +
+                                              (y + 1) * TB_RANK + (int)(pos & 3) * TB_ROW + (f + 1) * CELL) = u;
                 if (dbg_act1 && pos < n)
                     *reinterpret_cast<uint4*>(dbg_act1 + (pos * 64 + y * 8 + f) * 32 + kc * 8) = u;
             }

@@ -9,7 +9,7 @@
 //       the B operand of the weight gradient (tests/cuda/umma_mn_probe.cu checks the encoding).
 //
 //  fc1_dgrad_kernel   dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq], written (still
-//                     scaled, fp16) straight into the zero-bordered boards conv_bwd_kernel.cu consumes
+//                     scaled, fp16) straight into the zero-bordered boards conv_bwd2_kernel.cu consumes
 //                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
 //                     M = 2 x 128 outputs, N = 128 (16 squares x 8 channels), K = positions (split over CTAs)
@@ -186,15 +186,15 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                     {
                         const int chk = lane >> 2, sqi = lane & 3, piece = sqi * 8 + chk;
                         const int sq0 = (cg * 4 + c) * 4;                   // first square of the chunk: file 0 or 4 of one rank
-                        const long long off_lane = (long long)chk * 12800 + ((sq0 >> 3) + 1) * 1280 + ((sq0 & 7) + sqi + 1) * 16;
+                        const long long off_lane = (long long)chk * 6400 + ((sq0 >> 3) + 1) * 640 + ((sq0 & 7) + sqi + 1) * 16;
 #pragma unroll 4
                         for (int r = 0; r < 32; r++) {
                             const int rowi = q * 32 + r;
                             const long long rpos = (tile << 7) + rowi;
                             const uint4 val = *reinterpret_cast<const uint4*>(smem + DG_OFF_OUT + rowi * 512 + ((piece ^ (rowi & 31)) << 4));
-                            // conv2-backward board of this position's group: [8 chunks][10 ranks][8 pos][10 files][8 halfs]
+                            // conv2-backward board of this position's group of four: [8 chunks][10 ranks][4 pos][10 files][8 halfs]
                             if (rpos < n)
-                                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dz2_boards) + (rpos >> 3) * 102400 + (int)(rpos & 7) * 160 + off_lane) = val;
+                                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dz2_boards) + (rpos >> 2) * 51200 + (int)(rpos & 3) * 160 + off_lane) = val;
                         }
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");         // staging buffer free for the next chunk

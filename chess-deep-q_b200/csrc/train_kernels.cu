@@ -6,7 +6,7 @@
 //   backward through tanh, fc2, fc1, conv2, conv1; Adam (neural_network.py:65,244-246)
 //
 // Every GEMM-shaped piece runs on tcgen05: the forward (conv_kernel.cu, fc_kernel.cu), fc1's data and
-// weight gradients (fc_bwd_kernel.cu) and conv2's data/weight/bias gradients (conv_bwd_kernel.cu).
+// weight gradients (fc_bwd_kernel.cu) and conv2's data/weight/bias gradients (conv_bwd2_kernel.cu).
 // This file holds the glue: the loss/tanh/fc2 head, conv1's weight gradient (a scatter, because its
 // input is one-hot), Adam, and the workspace carve-up.  Gradients flow between kernels as fp16
 // scaled by 64*n (a power of two for the usual batch sizes) and are unscaled in fp32 epilogues;
