@@ -277,7 +277,7 @@ def main():
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 20))
     for _ in range(e2e_steps):
         ev.evaluate_host(h_boards, h_out)       # synchronises before returning
     e2e_s = time.perf_counter() - t0

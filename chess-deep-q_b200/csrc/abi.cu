@@ -322,10 +322,14 @@ int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n, f
     if (int e = check_device()) return e;
     std::lock_guard<std::mutex> lock(g_host.mu);
     if (int e = g_host.init()) return e;
+    // Chunks ramp up (1/8, 1/4, 1/2 of the full chunk, then full chunks): the first chunk's host-to-device copy is
+    // the one transfer nothing can hide, so it is kept short; from then on copies run under the other stream's kernels.
     int c_idx = 0;
-    for (int64_t off = 0; off < n; off += HostPath::CHUNK, c_idx++) {
+    for (int64_t off = 0; off < n; c_idx++) {
         const int s = c_idx & 1;
-        const int64_t c = (n - off) < HostPath::CHUNK ? (n - off) : HostPath::CHUNK;
+        const char* ramp = getenv("CDQ_HOST_RAMP");     // "0": full chunks from the start (A/B)
+        const int64_t cap = c_idx < 3 && !(ramp && ramp[0] == '0') ? HostPath::CHUNK >> (3 - c_idx) : HostPath::CHUNK;
+        const int64_t c = (n - off) < cap ? (n - off) : cap;
         cudaStream_t st = g_host.st[s];
         // the slot's previous use (two chunks ago) is ordered before this one by the stream itself
         CDQ_CUDA(cudaMemcpyAsync(g_host.boards[s], h_boards + off, c * sizeof(CdqBoard), cudaMemcpyHostToDevice, st));
@@ -335,6 +339,7 @@ int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n, f
         CDQ_CUDA(cudaMemcpyAsync(h_leaf + off, g_host.leaf[s], c * 4, cudaMemcpyDeviceToHost, st));
         if (h_score) CDQ_CUDA(cudaMemcpyAsync(h_score + off, g_host.score[s], c * 8, cudaMemcpyDeviceToHost, st));
         if (h_flags) CDQ_CUDA(cudaMemcpyAsync(h_flags + off, g_host.flags[s], c * 4, cudaMemcpyDeviceToHost, st));
+        off += c;
     }
     CDQ_CUDA(cudaStreamSynchronize(g_host.st[0]));
     CDQ_CUDA(cudaStreamSynchronize(g_host.st[1]));
