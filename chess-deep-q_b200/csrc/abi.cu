@@ -269,7 +269,7 @@ int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeig
                       float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!net || !target_net || !net->loaded || !target_net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 ||
         !d_states || !d_next_states || !d_reward || !d_done || !d_workspace ||
-        ((loss_kind & 0xff) != 0 && (loss_kind & 0xff) != 1) || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT | CDQ_TRAIN_REPACK)))
+        ((loss_kind & 0xff) != 0 && (loss_kind & 0xff) != 1) || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT | CDQ_TRAIN_REPACK | CDQ_TRAIN_ZERO_LOSS)))
         return CDQ_E_BADARG;
     if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if (int e = check_device()) return e;

@@ -18,7 +18,11 @@
 //   * two units fit in shared memory: the producer warp fetches unit i+1 while the UMMAs of unit i run;
 //   * the data-gradient accumulators are double buffered in TMEM: the epilogue warps drain unit i while the
 //     UMMAs of unit i+1 run;
-//   * 1 024 units spread over 148 CTAs in 7 rounds of half the size (3.5 group-rounds instead of 4).
+//   * 1 024 units spread over 148 CTAs in 7 rounds of half the size (3.5 group-rounds instead of 4);
+//   * units are handed out DYNAMICALLY (one atomicAdd per unit by the producer, the index travels to the other warps
+//     through shared memory next to the full barrier): in the training graph this kernel starts while the side
+//     stream's fc1 weight gradient still holds some SMs, and with a static round-robin split the CTAs that start
+//     late finished late by as much (+7 us on the whole kernel).  The two counters reset themselves.
 // Warp roles: 0 producer, 1 UMMA issuer, 2..5 epilogue (TMEM lane quarter = warp % 4).
 #include <cstdlib>
 #include "umma.cuh"
@@ -45,7 +49,8 @@ static_assert(64 * WT_STRIDE * 4 <= U_BYTES, "weight-gradient tile is staged ove
 __global__ void __launch_bounds__(THREADS, 1)
 conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restrict__ a1_boards,
                   const __half* __restrict__ w2tp, long long n_units, long long n, float inv_scale,
-                  float* __restrict__ g_w2, float* __restrict__ g_b2, float* __restrict__ dz1c) {
+                  float* __restrict__ g_w2, float* __restrict__ g_b2, float* __restrict__ dz1c,
+                  unsigned* __restrict__ sched /* [0] next unit, [1] finished CTAs; zero at entry, zero again at exit */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* full = bar_w + 1;          // [2] unit buffer filled (bulk-copy bytes)
@@ -54,6 +59,7 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
     uint64_t* dg_empty = bar_w + 7;      // [2] ... drained by the four epilogue warps
     uint64_t* wg_full = bar_w + 9;       //     every UMMA of this CTA complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 10);
+    volatile int* u_slot = reinterpret_cast<volatile int*>(bar_w + 11);   // [2] unit index of buffer b, -1 = no more work
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid < 128) reinterpret_cast<uint16_t*>(smem + OFF_ONES)[tid] = 0x3C00;   // fp16 1.0
@@ -70,7 +76,6 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t s0 = smem_u32(smem);
-    const long long my_units = (long long)blockIdx.x < n_units ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) {
         // ---------------- producer: weights once, then one unit (half group) per iteration
@@ -78,16 +83,25 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
             mbar_arrive_expect_tx(bar_w, W_BYTES);
             bulk_g2s(smem + OFF_W, w2tp, W_BYTES, bar_w);
         }
-        for (long long i = 0; i < my_units; i++) {
-            const long long u = blockIdx.x + i * gridDim.x;
+        for (long long i = 0;; i++) {
             const int b = (int)(i & 1);
             mbar_wait(empty + b, ((i >> 1) & 1) ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(full + b, U_BYTES);
+            int more = 1;
             if (lane == 0) {
-                uint8_t* sb = smem + b * U_BYTES;
-                bulk_g2s(sb, reinterpret_cast<const uint8_t*>(dz2_boards) + u * U_DZ2, U_DZ2, full + b);
-                bulk_g2s(sb + U_DZ2, reinterpret_cast<const uint8_t*>(a1_boards) + u * U_A1, U_A1, full + b);
+                const unsigned u = atomicAdd(sched, 1u);
+                if ((long long)u < n_units) {
+                    u_slot[b] = (int)u;
+                    mbar_arrive_expect_tx(full + b, U_BYTES);
+                    uint8_t* sb = smem + b * U_BYTES;
+                    bulk_g2s(sb, reinterpret_cast<const uint8_t*>(dz2_boards) + (long long)u * U_DZ2, U_DZ2, full + b);
+                    bulk_g2s(sb + U_DZ2, reinterpret_cast<const uint8_t*>(a1_boards) + (long long)u * U_A1, U_A1, full + b);
+                } else {
+                    u_slot[b] = -1;
+                    mbar_arrive(full + b);          // wakes the other warps; nothing is in flight
+                    more = 0;
+                }
             }
+            if (!__shfl_sync(0xffffffffu, more, 0)) break;
         }
     } else if (warp == 1) {
         // ---------------- UMMA issuer
@@ -104,10 +118,11 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
             const uint64_t dA_dg0 = make_smem_desc(s0, CHUNK, ROW);                            // dz2, K-major
             const uint64_t dB_w = make_smem_desc(s0 + OFF_W, 512, 128);
             const uint64_t d_ones = make_smem_desc(s0 + OFF_ONES, 128, 128);
-            for (long long i = 0; i < my_units; i++) {
+            for (long long i = 0;; i++) {
                 const int b = (int)(i & 1);
                 const uint32_t ph = (uint32_t)((i >> 1) & 1);
                 mbar_wait(full + b, ph);
+                if (u_slot[b] < 0) break;
                 mbar_wait(dg_empty + b, ph ^ 1);
                 tc_fence_after();
                 const uint64_t boff = (uint64_t)(b * (U_BYTES >> 4));
@@ -147,11 +162,13 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
         // ---------------- epilogue warps: thread = data-gradient tile row (rank in tile, position, file)
         const int q = warp & 3, row = q * 32 + lane;
         const int r_rk = row >> 5, r_pos = (row >> 3) & 3, r_x = row & 7;
-        for (long long i = 0; i < my_units; i++) {
-            const long long u = blockIdx.x + i * gridDim.x;
+        long long i = 0;
+        for (;; i++) {
             const int b = (int)(i & 1);
             const uint32_t ph = (uint32_t)((i >> 1) & 1);
             mbar_wait(full + b, ph);                 // the boards (for the mask) ...
+            const long long u = u_slot[b];
+            if (u < 0) break;
             mbar_wait(dg_full + b, ph);              // ... and the accumulators
             tc_fence_after();
             // conv1's ReLU mask of this thread's two rows (32 channels each), then the boards are released
@@ -201,7 +218,7 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
         // ---- weight/bias gradient: rows co = 16 * quadrant + lane (lanes 0..15 hold data), transposed through shared
         // memory (unit buffer 0 is dead: every UMMA is complete and the producer has nothing in flight) into PyTorch
         // order [co][ci][tap] and added with coalesced 16-byte reductions
-        if (my_units > 0) {
+        if (i > 0) {
             mbar_wait(wg_full, 0);
             tc_fence_after();
             float* tile = reinterpret_cast<float*>(smem);              // [64 co][WT_STRIDE]
@@ -231,12 +248,16 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
+    if (tid == 0 && atomicAdd(sched + 1, 1u) == gridDim.x - 1) {     // last CTA out: every producer has seen the end
+        sched[0] = 0;
+        sched[1] = 0;
+    }
 }
 
 } // namespace cb2
 
 int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
-                     float* g_w2, float* g_b2, float* dz1c, cudaStream_t st) {
+                     float* g_w2, float* g_b2, float* dz1c, unsigned* sched, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(cb2::conv2_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb2::SMEM);
@@ -246,7 +267,7 @@ int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __
     const int sms = device_sm_count();
     ProfileScope ps(KK_CONV2_BWD, st);
     cb2::conv2_bwd2_kernel<<<(unsigned)(units < sms ? units : sms), cb2::THREADS, cb2::SMEM, st>>>(
-        dz2_boards, a1_boards, w2tp, units, n, inv_scale, g_w2, g_b2, dz1c);
+        dz2_boards, a1_boards, w2tp, units, n, inv_scale, g_w2, g_b2, dz1c, sched);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -13,6 +13,7 @@
 //                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
 //                     M = 2 x 128 outputs, N = 128 (16 squares x 8 channels), K = positions (split over CTAs)
+#include <cstdlib>
 #include "umma.cuh"
 #include "common.cuh"
 #include "cnn.cuh"
@@ -326,7 +327,9 @@ int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float 
         attr_set = true;
     }
     const long long tiles = (n + 127) >> 7;
-    const int k_splits = (int)(tiles < 4 ? tiles : 4);
+    // K (positions) split: more splits = more CTAs but one epilogue (32 768 elements of atomics) and one prologue each
+    static const int max_splits = [] { const char* e = getenv("CDQ_WGRAD_SPLITS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 2; }();
+    const int k_splits = (int)(tiles < max_splits ? tiles : max_splits);
     ProfileScope ps(KK_FC1_WGRAD, st);
     fc1_wgrad_kernel<<<32 * k_splits, WG_THREADS, WG_SMEM, st>>>(dz1h, act2, tiles, k_splits, inv_scale, g_fc1_w);
     count_launch();

@@ -36,8 +36,9 @@ constexpr long long PK_N1 = 9 * 32 * 16, PK_N2 = 9 * 64 * 32, PK_V3 = 64ll * 256
 constexpr long long PK_SMALL = 2 * PK_N1 + 3 * PK_N2 + 577;
 constexpr long long PK_SMALL_PAD = (PK_SMALL + 255) / 256 * 256;     // the vector parts start on a CTA boundary
 __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
-                                    __half* wss, float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b) {
+                                    __half* wss, float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b, float* zero_me) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && zero_me) *zero_me = 0.f;       // the training step's loss accumulator (saves a fill launch in the graph)
     constexpr long long N1 = PK_N1, N2 = PK_N2;
     if (i >= PK_SMALL_PAD) {
         const long long t = i - PK_SMALL_PAD;
@@ -108,12 +109,12 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
     }
 }
 
-int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st) {
+int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me) {
     const long long total = PK_SMALL_PAD + 2 * PK_V3;
     ProfileScope ps(KK_PACK, st);
     pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         w, (__half*)p.w1p, (__half*)p.w2p, (__half*)p.fc1p, (__half*)p.fc1tp, (__half*)p.w2tp, (__half*)p.wss, (float*)p.conv2_b,
-        (float*)p.fc1_b, (float*)p.fc2_w, (float*)p.fc2_b);
+        (float*)p.fc1_b, (float*)p.fc2_w, (float*)p.fc2_b, zero_me);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "cnn.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace cdq {
 
@@ -230,7 +231,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
-    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_boards; __half* dz2_boards; float* hidden; float* q; float* qn; float* dz1c;
+    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_boards; __half* dz2_boards; unsigned* sched; float* hidden; float* q; float* qn; float* dz1c;
     size_t zero_from, zero_bytes;   // [a1_boards, dz2_boards]: borders must be zero, cleared every step
     size_t total;
 };
@@ -245,6 +246,7 @@ static TrainWs carve(void* base, long long n) {
     w.zero_from = off;
     w.a1_boards = (__half*)take((size_t)groups * 51200);
     w.dz2_boards = (__half*)take((size_t)groups * 102400);
+    w.sched = (unsigned*)take(256);           // conv2 backward's work counters: zero at entry (they reset themselves)
     w.zero_bytes = off - w.zero_from;
     w.hidden = (float*)take((size_t)n * 256 * 4);
     w.q = (float*)take((size_t)n * 4);
@@ -292,13 +294,18 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     // The two conv launches are persistent, one CTA per SM, and cannot share an SM (170 KB of shared memory each):
     // on the whole machine they would run one after the other, each with its own prologue and a half-empty
     // last round, so each gets half of the SMs and they run side by side.
-    const int half_sms = device_sm_count() / 2;
-    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, half_sms))) return e;
+    // The online launch also writes the ReLU(conv1) boards and sits on the longer chain (repack -> conv -> fc),
+    // so it gets the larger share (CDQ_TRAIN_CONV_SPLIT = percent of the SMs for the online network, default 50: measured flat between 50 and 61, profiles/conv_split_sweep.sh).
+    static const int online_pct = [] { const char* e = getenv("CDQ_TRAIN_CONV_SPLIT"); const int v = e ? atoi(e) : 0; return v >= 20 && v <= 80 ? v : 50; }();
+    const int online_sms = device_sm_count() * online_pct / 100, target_sms = device_sm_count() - online_sms;
+    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, target_sms))) return e;
     if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
     // the online network's fp16 tiles are rebuilt from the fp32 parameters next to the target forward
-    if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st))) return e;
-    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards, half_sms))) return e;
+    const bool zero_in_pack = (loss_kind_flags & CDQ_TRAIN_REPACK) && (loss_kind_flags & CDQ_TRAIN_ZERO_LOSS);
+    if ((loss_kind_flags & CDQ_TRAIN_ZERO_LOSS) && !zero_in_pack) CDQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st, zero_in_pack ? loss : nullptr))) return e;
+    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards, online_sms))) return e;
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // ---- loss, tanh, fc2, fc1 bias
@@ -318,7 +325,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
     if ((e = launch_fc1_dgrad(ws.dz1h, ws.act2_tiles, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
     if ((e = launch_conv2_bwd(ws.dz2_boards, ws.a1_boards, net->p.w2tp, n, 1.f / scale, (float*)g.conv2_w, (float*)g.conv2_b,
-                              ws.dz1c, st))) return e;
+                              ws.dz1c, ws.sched, st))) return e;
     {
         // ---- conv1: weight + bias gradient by scatter over the one-hot input
         ProfileScope ps(KK_CONV1_WGRAD, st);

@@ -19,6 +19,7 @@ NPARAMS_PAD = (NPARAMS + 3) // 4 * 4      # flat buffers are padded to whole 16-
 
 LOSS_MSE, LOSS_HUBER = 0, 1
 REPACK = 0x200             # CDQ_TRAIN_REPACK: the call re-packs the online network from the fp32 parameters
+ZERO_LOSS = 0x400          # CDQ_TRAIN_ZERO_LOSS: the call zeroes the loss accumulator itself
 WS_PERSISTENT = 0x100      # CDQ_TRAIN_WS_PERSISTENT: the workspace is ours, zero-filled once, reused every step
 
 
@@ -310,11 +311,10 @@ class GraphedDQNStep:
         weights = _weights_struct([params[k] for k in PARAM_ORDER])
         gv = self.optimizer.grad_views()
         grads = _weights_struct([gv[k] for k in PARAM_ORDER])
-        self.loss.zero_()
         _lib.check(_lib.lib().cdq_train_fwd_bwd(
             self.q_network.raw_handle(), self.target_network.net_handle(), ctypes.byref(weights),
             self.states.data_ptr(), self.next_states.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
-            self.batch, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
+            self.batch, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK | ZERO_LOSS, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
             self.ws.numel(), _lib.stream_ptr()))
         self.optimizer.step_fused()
 

@@ -169,6 +169,7 @@ int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
  * cdq_adam_step: torch.optim.Adam defaults (neural_network.py:65) over one flat fp32 buffer. */
 #define CDQ_TRAIN_WS_PERSISTENT 0x100
 #define CDQ_TRAIN_REPACK 0x200 /* re-pack `net` from d_weights inside the call (next to the target forward) */
+#define CDQ_TRAIN_ZERO_LOSS 0x400 /* *d_loss is zeroed inside the call (no separate fill launch in a captured step) */
 size_t cdq_train_workspace_bytes(int64_t n);
 int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
                       const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,
