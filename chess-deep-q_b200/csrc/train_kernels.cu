@@ -86,42 +86,53 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
 
 // conv1 weight + bias gradient.  The input is one-hot, so the GEMM collapses to a gather:
 // dW1[co][p][tap] += dz1c[b][sq][co] for every piece p standing on square sq + tap.  A board is handled by
-// THREE warps, one per kernel row dy; lane = output channel, and the 12 pieces x 3 taps accumulators of a
-// lane live in registers.  The board's 8 KB of gradients and its bitboards are brought into shared memory
-// with cp.async, double buffered (the copy of the slot's next board runs under the gather of the current
-// one and costs no registers); each warp then runs over the pieces of the board (at most 32 set bits) and
-// reads the three output squares of its row around the piece -- conflict-free shared-memory reads.  Seven
-// such board slots per CTA, one CTA per SM, each slot synchronised by its own named barrier.  At the end the
-// slots of a CTA are summed through shared memory into PyTorch order and added to the gradient with
-// coalesced 16-byte reductions: same-line atomics serialise in L2, so what matters is the number of
-// transactions per 128-byte line (one scalar atomic per cell and CTA with the channel as the fast index put
-// 32 per CTA on each line and cost more than the gather itself).
-constexpr int C1W_SLOTS = 7, C1W_WARPS = 3 * C1W_SLOTS, C1W_THREADS = 32 * C1W_WARPS;
+// THREE warps that split the PIECE TYPES (white pawns + black rooks and queen / black pawns + white rooks and
+// queen / all knights, bishops and kings: 11 + 11 + 10 pieces on a full board), lane = output channel, and a
+// lane's accumulators (its types x 9 taps) live in registers.  Per piece a warp pays the bit scan and the
+// address arithmetic once and then reads the nine output squares around the piece -- conflict-free
+// shared-memory reads (the previous split, one kernel row per warp, made every warp walk ALL pieces: three
+// times the per-piece overhead, which was two thirds of the instructions).  The board's 8 KB of gradients
+// and its bitboards are brought into shared memory with cp.async, double buffered (the copy of the slot's
+// next board runs under the gather of the current one and costs no registers).  Six such board slots per
+// CTA, one CTA per SM, each slot synchronised by its own named barrier.  At the end the slots of a CTA are
+// summed through shared memory into PyTorch order and added to the gradient with coalesced 16-byte
+// reductions: same-line atomics serialise in L2, so what matters is the number of transactions per 128-byte
+// line (one scalar atomic per cell and CTA with the channel as the fast index put 32 per CTA on each line
+// and cost more than the gather itself).
+constexpr int C1W_SLOTS = 6, C1W_WARPS = 3 * C1W_SLOTS, C1W_THREADS = 32 * C1W_WARPS;
 constexpr int C1W_STAGE_BYTES = C1W_SLOTS * 2 * 8192;             // [slot][2][64 squares][32 channels] fp32
-constexpr int C1W_RED_BYTES = C1W_WARPS * 37 * 32 * 4;            // reduction buffer, aliases the staging buffers
-static_assert(C1W_RED_BYTES <= C1W_STAGE_BYTES, "reduction buffer aliases the staging buffers");
-constexpr int C1W_OFF_BOARD = C1W_STAGE_BYTES;                    // [slot][2][8 bitboards]
+constexpr int C1W_ROWS = 6 * 9 + 1;                               // per warp: up to 6 types x 9 taps, + the bias row
+constexpr int C1W_RED_BYTES = C1W_WARPS * C1W_ROWS * 32 * 4;      // reduction buffer, aliases the staging buffers
+constexpr int C1W_OFF_BOARD = C1W_RED_BYTES > C1W_STAGE_BYTES ? C1W_RED_BYTES : C1W_STAGE_BYTES;   // [slot][2][8 bitboards]
 constexpr int C1W_OFF_OUT = C1W_OFF_BOARD + C1W_SLOTS * 2 * 64;   // [32 co][108] summed over the slots
 constexpr int C1W_SMEM = C1W_OFF_OUT + 32 * 108 * 4;
+static_assert(C1W_SMEM <= 227 * 1024, "conv1 gather shared memory");
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-__global__ void __launch_bounds__(C1W_THREADS, 1)
-conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
-                   float* __restrict__ g_w, float* __restrict__ g_b) {
-    extern __shared__ __align__(16) uint8_t c1w_raw[];
-    float* c1w_smem = reinterpret_cast<float*>(c1w_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = warp / 3, sub = warp % 3, t96 = sub * 32 + lane;
-    const int dy = sub - 1;
-    float acc[12][3];
+// piece types (channel = type + 6 * black, board_utils.py:17-30) of the three warp roles
+__host__ __device__ constexpr int c1w_ntypes(int g) { return g == 2 ? 6 : 3; }
+__host__ __device__ constexpr int c1w_type(int g, int i) {
+    return g == 0 ? (i == 0 ? 0 : i == 1 ? 9 : 10)
+         : g == 1 ? (i == 0 ? 6 : i == 1 ? 3 : 4)
+                  : (i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 5 : i == 3 ? 7 : i == 4 ? 8 : 11);
+}
+__constant__ int c1w_group_of[12] = {0, 2, 2, 1, 1, 2, 1, 2, 2, 0, 0, 2};
+__constant__ int c1w_local_of[12] = {0, 0, 1, 1, 2, 2, 0, 3, 4, 1, 2, 5};
+
+template <int G>
+__device__ __forceinline__ void c1w_gather(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
+                                           float* c1w_smem, uint8_t* c1w_raw, int slot, int sub, int lane, int warp) {
+    constexpr int NT = c1w_ntypes(G);
+    const int t96 = sub * 32 + lane;
+    float acc[NT][9];
 #pragma unroll
-    for (int p = 0; p < 12; p++)
+    for (int p = 0; p < NT; p++)
 #pragma unroll
-        for (int t = 0; t < 3; t++) acc[p][t] = 0.f;
+        for (int t = 0; t < 9; t++) acc[p][t] = 0.f;
     float bias = 0.f;
     float* stage0 = c1w_smem + slot * 4096;             // two buffers of [64 squares][32 channels]
     unsigned long long* board0 = reinterpret_cast<unsigned long long*>(c1w_raw + C1W_OFF_BOARD) + slot * 16;
@@ -160,45 +171,69 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
         }
         const unsigned long long white = r[6], black = r[7] & ~white;
 #pragma unroll
-        for (int p = 0; p < 12; p++) {                  // channel = type + 6 * black (board_utils.py:17-30)
+        for (int pi = 0; pi < NT; pi++) {
+            const int p = c1w_type(G, pi);
             unsigned long long m = r[p % 6] & (p < 6 ? white : black);
             while (m) {                                 // warp-uniform
                 const int s = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                // the piece on (y, x) is read through tap (dy, dx) by output square (y - dy, x - dx)
-                const int oy = (s >> 3) - dy, x = s & 7;
-                if (oy < 0 || oy > 7) continue;
-                const float* row = stage + (oy * 8 + x) * 32 + lane;
-                if (x < 7) acc[p][0] += row[32];        // dx = -1
-                acc[p][1] += row[0];                    // dx =  0
-                if (x > 0) acc[p][2] += row[-32];       // dx = +1
+                // the piece on (y, x) is read through tap (dy, dx) by output square (y - dy, x - dx); tap = 3 (dy + 1) + (dx + 1)
+                const int y = s >> 3, x = s & 7;
+                const float* c = stage + s * 32 + lane;
+                const bool up = y < 7, dn = y > 0, rt = x < 7, lf = x > 0;     // output square one rank up / down, one file right / left exists
+                if (up) {                               // dy = -1: output rank y + 1
+                    if (rt) acc[pi][0] += c[288];
+                    acc[pi][1] += c[256];
+                    if (lf) acc[pi][2] += c[224];
+                }
+                if (rt) acc[pi][3] += c[32];            // dy = 0
+                acc[pi][4] += c[0];
+                if (lf) acc[pi][5] += c[-32];
+                if (dn) {                               // dy = +1: output rank y - 1
+                    if (rt) acc[pi][6] += c[-224];
+                    acc[pi][7] += c[-256];
+                    if (lf) acc[pi][8] += c[-288];
+                }
             }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                    // all slots done: the staging buffers become the reduction buffer
-    // ---- sum the slots (channel = fast index: conflict free) into PyTorch order, then coalesced 16-byte reductions
-    float* mine = c1w_smem + warp * (37 * 32);
+    float* mine = c1w_smem + warp * (C1W_ROWS * 32);
 #pragma unroll
-    for (int p = 0; p < 12; p++)
+    for (int pi = 0; pi < NT; pi++)
 #pragma unroll
-        for (int t = 0; t < 3; t++) mine[(p * 3 + t) * 32 + lane] = acc[p][t];
-    mine[36 * 32 + lane] = bias;
+        for (int t = 0; t < 9; t++) mine[(pi * 9 + t) * 32 + lane] = acc[pi][t];
+    mine[(C1W_ROWS - 1) * 32 + lane] = bias;
+}
+
+__global__ void __launch_bounds__(C1W_THREADS, 1)
+conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
+                   float* __restrict__ g_w, float* __restrict__ g_b) {
+    extern __shared__ __align__(16) uint8_t c1w_raw[];
+    float* c1w_smem = reinterpret_cast<float*>(c1w_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp / 3, sub = warp % 3;
+    if (sub == 0) c1w_gather<0>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
+    else if (sub == 1) c1w_gather<1>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
+    else c1w_gather<2>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
     __syncthreads();
+    // ---- sum the slots (channel = fast index: conflict free) into PyTorch order, then coalesced 16-byte reductions
     float* out = reinterpret_cast<float*>(c1w_raw + C1W_OFF_OUT);
-    for (int i = threadIdx.x; i < 3 * 36 * 32; i += C1W_THREADS) {
-        const int co = i & 31, cell = (i >> 5) % 36, sb = i / (36 * 32);          // cell = p * 3 + dx index
+    for (int i = threadIdx.x; i < 108 * 32; i += C1W_THREADS) {
+        const int co = i & 31, cell = i >> 5, p = cell / 9, tap = cell - p * 9;
+        const int g = c1w_group_of[p], row = c1w_local_of[p] * 9 + tap;
         float v = 0.f;
 #pragma unroll
-        for (int sl = 0; sl < C1W_SLOTS; sl++) v += c1w_smem[(sl * 3 + sb) * (37 * 32) + cell * 32 + co];
-        out[co * 108 + (cell / 3) * 9 + sb * 3 + cell % 3] = v;                   // conv1.weight[co][p][tap], tap = (dy+1)*3 + (dx+1)
+        for (int sl = 0; sl < C1W_SLOTS; sl++) v += c1w_smem[(sl * 3 + g) * (C1W_ROWS * 32) + row * 32 + co];
+        out[co * 108 + cell] = v;                                                 // conv1.weight[co][p][tap]
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * 108 / 4; i += C1W_THREADS)
         atomicAdd(reinterpret_cast<float4*>(g_w) + i, reinterpret_cast<const float4*>(out)[i]);
     if (threadIdx.x < 32) {
         float v = 0.f;
-        for (int w = 0; w < C1W_WARPS; w++) v += c1w_smem[w * (37 * 32) + 36 * 32 + threadIdx.x];
+        for (int w = 0; w < C1W_WARPS; w++) v += c1w_smem[w * (C1W_ROWS * 32) + (C1W_ROWS - 1) * 32 + threadIdx.x];
         atomicAdd(g_b + threadIdx.x, v);
     }
 }
@@ -334,7 +369,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
             cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM);
             attr_set = true;
         }
-        const long long want = (n + C1W_SLOTS - 1) / C1W_SLOTS;     // one CTA of 21 warps per SM (7 x 148 slots: 4 096 boards in 4 rounds)
+        const long long want = (n + C1W_SLOTS - 1) / C1W_SLOTS;     // one CTA of 18 warps per SM
         const unsigned blocks = (unsigned)(want < device_sm_count() ? want : device_sm_count());
         conv1_wgrad_kernel<<<blocks, C1W_THREADS, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
         count_launch();
