@@ -343,7 +343,7 @@ def main():
 
     # ---- roofline of the dominant kernel (tensor bound)
     peaks = measured_peaks()
-    kinds = {0: ("eval_terms_kernel", None), 1: ("conv_stream_kernel", FLOP_CONV), 2: ("fc_head_kernel", FLOP_FC),
+    kinds = {0: ("eval_terms_kernel", None), 1: ("conv_stream_kernel", FLOP_CONV), 2: ("fc_head_pairs_kernel", FLOP_FC),
              7: ("leaf_pipe_kernel", FLOP_CONV + FLOP_FC)}      # 7 = conv + fc as one kernel (act2 stays in L2)
     dom = max((1, 2, 7), key=lambda k: kms[k])
     per_launch_pos = n * args.steps / max(1, kcnt[dom])

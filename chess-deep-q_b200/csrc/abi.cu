@@ -31,7 +31,7 @@ ProfileScope::~ProfileScope() {
 
 // positions per conv->fc pass (act2 = 1 036 MiB): 148 SMs x 7 fc tiles of 128 = 148 SMs x 56 conv tiles of 16,
 // so both persistent kernels end their last round with every SM busy
-constexpr long long FWD_CHUNK = 148 * 7 * 128;
+constexpr long long FWD_CHUNK = 148 * 8 * 128;      // 148 SMs x 4 pairs of fc tiles = 148 x 64 conv tiles
 static inline long long tiles_of(long long n) { return (n + 127) / 128; }
 
 // With CDQ_PIPE=1, batches of at least this many positions go through the conv -> fc pipe kernel (one
@@ -288,7 +288,7 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
 // ------------------------------------------------------------------ host-buffer path (e2e)
 namespace {
 struct HostPath {
-    static constexpr long long CHUNK = 2 * 148 * 7 * 128;   // two forward chunks
+    static constexpr long long CHUNK = 2 * FWD_CHUNK;       // two forward chunks
     std::mutex mu;
     bool ready = false;
     cudaStream_t st[2];

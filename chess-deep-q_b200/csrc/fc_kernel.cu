@@ -7,6 +7,7 @@
 // The epilogue applies bias + ReLU and the 256 -> 1 fc2 dot product per TMEM lane (= per position),
 // tanh, and optionally the leaf post-processing of mcts.py:196-232.
 // Algorithmic work: 2 097 664 FLOP/position; reads 8 KB/position of act2.
+#include <cstdlib>
 #include "fc_head.cuh"
 
 namespace cdq {
@@ -17,6 +18,162 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
                float* __restrict__ hidden /* optional [n][256] ReLU(fc1), kept for the backward pass */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     fc_head_body<false>(smem, act2, n, net, value, flags, leaf, hidden, (int)blockIdx.x, (int)gridDim.x, cs::PipeCtl{});
+}
+
+// ------------------------------------------------------------------------------------------
+// fc_head_pairs_kernel: the same GEMM with TWO position tiles per weight stage.  One tile per stage moves 16 KB of
+// A and 32 KB of B per 64 K-elements, i.e. every tile re-reads the whole 2 MB of fc1 weights from L2: 3 MB per
+// tile, 24 GB of L2 -> SM traffic per 1M positions, and an SM keeps only its 192 KB ring in flight (about
+// 110 GB/s at the L2 latency under load), which is what a tile took.  Here a stage holds A of tiles 2p and 2p+1
+// and ONE B (64 KB, three stages), the two 128 x 256 accumulators fill all 512 TMEM columns, and a pair costs
+// 4 MB: a third less operand traffic per tile.  The accumulators are single buffered, so the tensor pipe waits
+// while the epilogue drains them (16 TMEM loads per pair); the producer keeps prefetching meanwhile.  Same UMMAs
+// in the same K order per tile as fc_head_kernel, so the values are bit-identical.
+constexpr int FCP_STAGES = 3;
+constexpr int FCP_STAGE_BYTES = 2 * FC_A_BYTES + FC_B_BYTES;
+constexpr int FCP_OFF_VEC = FCP_STAGES * FCP_STAGE_BYTES;
+constexpr int FCP_OFF_BAR = FCP_OFF_VEC + 2 * 256 * 4 + 16;
+constexpr int FCP_SMEM = FCP_OFF_BAR + 128;
+static_assert(FCP_SMEM <= 227 * 1024, "fc pairs kernel shared memory");
+
+__global__ void __launch_bounds__(FC_THREADS, 1)
+fc_head_pairs_kernel(const __half* __restrict__ act2, long long n, const PackedNet net,
+                     float* __restrict__ value, const unsigned* __restrict__ flags, float* __restrict__ leaf,
+                     float* __restrict__ hidden) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* sb1 = reinterpret_cast<float*>(smem + FCP_OFF_VEC);
+    float* sw2 = sb1 + 256;
+    float* sb2 = sw2 + 256;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + FCP_OFF_BAR); // [FCP_STAGES]
+    uint64_t* empty = full + FCP_STAGES;                              // [FCP_STAGES]
+    uint64_t* acc_full = empty + FCP_STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 256; i += (int)blockDim.x) { sb1[i] = net.fc1_b[i]; sw2[i] = net.fc2_w[i]; }
+    if (tid == 0) {
+        sb2[0] = net.fc2_b[0];
+        for (int s = 0; s < FCP_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const long long n_tiles = (n + 127) >> 7, n_pairs = (n_tiles + 1) >> 1;
+    const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
+    constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+
+    if (warp == 0) {
+        // ---------------- producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long p = cta; p < n_pairs; p += n_cta) {
+                const bool two = 2 * p + 1 < n_tiles;
+                const uint8_t* a_tile = reinterpret_cast<const uint8_t*>(act2) + (p << 21);
+                for (int s = 0; s < 64; s++, it++) {
+                    const int sq = ((s & 7) << 3) | (s >> 3);          // the K order of fc_head_kernel (file-major)
+                    const int st = it % FCP_STAGES;
+                    mbar_wait(empty + st, ((it / FCP_STAGES) & 1) ^ 1);
+                    uint8_t* sa = smem + st * FCP_STAGE_BYTES;
+                    mbar_arrive_expect_tx(full + st, (two ? 2 : 1) * FC_A_BYTES + FC_B_BYTES);
+                    bulk_g2s(sa, a_tile + ((long long)sq << 14), FC_A_BYTES, full + st);
+                    if (two) bulk_g2s(sa + FC_A_BYTES, a_tile + (1ll << 20) + ((long long)sq << 14), FC_A_BYTES, full + st);
+                    bulk_g2s(sa + 2 * FC_A_BYTES, reinterpret_cast<const uint8_t*>(net.fc1p) + ((long long)sq << 15), FC_B_BYTES, full + st);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, pc = 0;
+            for (long long p = cta; p < n_pairs; p += n_cta, pc++) {
+                const bool two = 2 * p + 1 < n_tiles;
+                mbar_wait(acc_empty, (pc & 1) ^ 1);
+                tc_fence_after();
+                for (int s = 0; s < 64; s++, it++) {
+                    const int st = it % FCP_STAGES;
+                    mbar_wait(full + st, (it / FCP_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(smem + st * FCP_STAGE_BYTES), b = a + 2 * FC_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        umma_f16(tmem, make_smem_desc(a + j * 2 * 2048, 2048, 128), make_smem_desc(b + j * 2 * 4096, 4096, 128), IDESC,
+                                 (s | j) != 0);
+                    if (two) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            umma_f16(tmem + 256, make_smem_desc(a + FC_A_BYTES + j * 2 * 2048, 2048, 128),
+                                     make_smem_desc(b + j * 2 * 4096, 4096, 128), IDESC, (s | j) != 0);
+                    }
+                    umma_commit(empty + st);
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- epilogue: TMEM lane quarter = warp % 4, one position per thread and tile
+        const int q = warp & 3;
+        uint32_t pc = 0;
+        for (long long p = cta; p < n_pairs; p += n_cta, pc++) {
+            const int n_here = 2 * p + 1 < n_tiles ? 2 : 1;
+            mbar_wait(acc_full, pc & 1);
+            tc_fence_after();
+            float dots[2] = {0.f, 0.f};
+#pragma unroll
+            for (int tt = 0; tt < 2; tt++) {
+                if (tt < n_here) {
+                    const long long pos = ((2 * p + tt) << 7) + q * 32 + lane;
+                    float dot = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < 8; c++) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tt * 256 + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float h = fmaxf(__uint_as_float(v[j]) + sb1[c * 32 + j], 0.f);
+                            dot = fmaf(h, sw2[c * 32 + j], dot);
+                            v[j] = __float_as_uint(h);
+                        }
+                        if (hidden && pos < n) {
+                            float4* hp = reinterpret_cast<float4*>(hidden + pos * 256 + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                hp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        }
+                    }
+                    dots[tt] = dot;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+#pragma unroll
+            for (int tt = 0; tt < 2; tt++) {
+                const long long pos = ((2 * p + tt) << 7) + q * 32 + lane;
+                if (tt < n_here && pos < n) {
+                    const float v = tanhf(dots[tt] + sb2[0]);
+                    if (value) value[pos] = v;
+                    if (leaf) {
+                        // mcts.py:196-232: terminal short-circuits, else clamp(net, -1, 1)
+                        const unsigned f = flags[pos];
+                        float lv = fminf(1.f, fmaxf(-1.f, v));
+                        if (f & CDQ_F_CHECKMATE) lv = (f & CDQ_F_WHITE_TO_MOVE) ? -1.f : 1.f;
+                        else if (f & (CDQ_F_STALEMATE | CDQ_F_INSUFFICIENT | CDQ_F_REP3)) lv = 0.f;
+                        leaf[pos] = lv;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -140,6 +297,19 @@ int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float*
         attr_set = true;
     }
     const int sms = device_sm_count();
+    const char* pe = getenv("CDQ_FC_PAIRS");             // "0": one tile per weight stage (A/B)
+    if (!(pe && pe[0] == '0')) {
+        static bool pattr = false;
+        if (!pattr) {
+            cudaFuncSetAttribute(fc_head_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FCP_SMEM);
+            pattr = true;
+        }
+        const long long pairs = (tiles + 1) / 2;
+        ProfileScope ps(KK_FC, st);
+        fc_head_pairs_kernel<<<(unsigned)(pairs < sms ? pairs : sms), FC_THREADS, FCP_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
+        count_launch();
+        return (int)cudaGetLastError();
+    }
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     ProfileScope ps(KK_FC, st);
     fc_head_kernel<<<grid, FC_THREADS, FC_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
