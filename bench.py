@@ -349,15 +349,17 @@ def main():
     per_launch_pos = n * args.steps / max(1, kcnt[dom])
     avg_ms = kms[dom] / max(1, kcnt[dom])
     achieved = per_launch_pos * kinds[dom][1] / (avg_ms * 1e-3) / 1e12
-    traffic = None        # DRAM bytes per launch of that kernel from the committed ncu capture (same launch size only)
-    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    traffic = None        # DRAM bytes per launch of that kernel from the committed ncu capture, scaled to this launch size
+    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if kinds[dom][0] in tj and int(per_launch_pos) == tj[kinds[dom][0]].get("positions_per_launch", tj["positions_per_launch"]):
-            traffic = tj[kinds[dom][0]]["traffic_bytes"]
+        ent = tj.get(kinds[dom][0])
+        if ent:
+            traffic = ent["traffic_bytes"] * per_launch_pos / ent.get("captured_positions", tj["captured_positions"])
     roofline = {"kernel": kinds[dom][0], "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                "traffic_note": "DRAM read+write bytes per launch from the committed ncu capture (profiles/r1b_traffic.json)",
+                "traffic_note": "DRAM read+write bytes per launch: ncu capture of a 151 552-position launch (profiles/r1c_traffic.json) scaled to "
+                                "this run's average launch of %d positions; algorithmic %.3f GB" % (per_launch_pos, per_launch_pos * 8264 / 1e9),
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kind::f16 shares the bf16 rate)",
                 "kernel_ms_per_step": {kinds[k][0]: kms[k] / args.steps for k in kinds if kms[k] > 0},
                 "eval_kernel_hbm": {"achieved_GBps": n * args.steps * 84 / (kms[0] * 1e-3) / 1e9 if kms[0] else None,
