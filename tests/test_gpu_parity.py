@@ -249,6 +249,22 @@ def test_pipe_kernel_equals_two_kernel_path(cdq, oracle, monkeypatch):
             assert torch.equal(b[k], c[k]), (n, k)
 
 
+def test_fc_pairs_kernel_equals_single_tile_kernel(cdq, oracle, monkeypatch):
+    """Large batches run the fc head with two position tiles per weight stage (fc_head_pairs_kernel);
+    CDQ_FC_PAIRS=0 selects one tile per stage.  Same UMMAs in the same K order per tile: bit-identical
+    values, for even and odd tile counts and a ragged last tile."""
+    net, _ = _make_net(cdq, oracle, 2.0)
+    ev = cdq.LeafEvaluator(net)
+    for n in (65 * 128, 66 * 128 + 77, 300_001):
+        d = _dev_playouts(cdq, n, seed=n)
+        monkeypatch.setenv("CDQ_FC_PAIRS", "0")
+        a = ev.evaluate_device(d, want_raw=True)
+        monkeypatch.delenv("CDQ_FC_PAIRS")
+        b = ev.evaluate_device(d, want_raw=True)
+        for k in ("leaf", "value", "score", "flags"):
+            assert torch.equal(a[k], b[k]), (n, k)
+
+
 def test_repack_after_weight_update(cdq, oracle):
     boards = oracle.playouts(64, seed=11)
     net, p = _make_net(cdq, oracle, 1.0)
