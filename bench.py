@@ -148,7 +148,8 @@ def run_sweep(args, cdq, L, ev, rank, world, local, dist):
     import torch
     peaks = measured_peaks()
     rows = []
-    for n in (4096, 16384, 65536, 262144, 1048576, 4194304, 16777216):
+    import ctypes
+    for n in (4096, 16384, 65536, 262144, 1048576, 4194304, 8388608, 16777216):     # 8 GPUs x 8M = the 64M-position point
         boards = torch.empty((n, 9), dtype=torch.int64, device="cuda")
         cdq._lib.check(L.cdq_random_playouts(boards.data_ptr(), n, 42 + rank, 199, cdq._lib.stream_ptr()))
         steps = max(3, min(200, (8 << 20) // n))
@@ -158,19 +159,29 @@ def run_sweep(args, cdq, L, ev, rank, world, local, dist):
         if dist:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        L.cdq_profile_enable(1)                 # event pair around every launch: per-kernel time of this rank
         e0.record()
         for _ in range(steps):
             ev.evaluate_device(boards)
         e1.record()
         torch.cuda.synchronize()
+        L.cdq_profile_enable(0)
+        kms, kcnt = (ctypes.c_double * 8)(), (ctypes.c_uint64 * 8)()
+        cdq._lib.check(L.cdq_profile_collect(kms, kcnt))
         ms = e0.elapsed_time(e1)
         if dist:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         pps = world * n * steps / (ms * 1e-3)
+        per_s = lambda k: n * steps / (kms[k] * 1e-3) if kms[k] > 0 else None       # noqa: E731  positions/s inside kernel kind k
         rows.append({"positions_per_gpu": n, "steps": steps, "ms_per_step": ms / steps, "positions_per_s": pps,
-                     "tensor_frac_whole_step": pps / world * (FLOP_CONV + FLOP_FC) / 1e12 / peaks["tflops"]})
+                     "tensor_frac_whole_step": pps / world * (FLOP_CONV + FLOP_FC) / 1e12 / peaks["tflops"],
+                     "kernel_ms_per_step": {"eval_terms": kms[0] / steps, "conv_stream": kms[1] / steps, "fc_head": kms[2] / steps},
+                     "roofline_frac": {"conv_stream_tensor": per_s(1) * FLOP_CONV / 1e12 / peaks["tflops"] if per_s(1) else None,
+                                       "fc_head_tensor": per_s(2) * FLOP_FC / 1e12 / peaks["tflops"] if per_s(2) else None,
+                                       "fc_head_hbm": per_s(2) * 8196 / 1e9 / peaks["hbm"] if per_s(2) else None,
+                                       "eval_terms_hbm": per_s(0) * 84 / 1e9 / peaks["hbm"] if per_s(0) else None}})
         del boards
     if rank == 0:
         print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "scaling": "weak", "sweep": rows,
