@@ -8,7 +8,11 @@
 // act2: the forward's fc1 A tiles; read MN-major (N = channels of a square, K = positions) they are
 //       the B operand of the weight gradient (tests/cuda/umma_mn_probe.cu checks the encoding).
 //
-//  fc1_dgrad_kernel   dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq], written (still
+//  fc1_dgrad_kernel   (work item = one 256-column chunk of one position tile; a CTA takes a CONTIGUOUS range of
+//                     items, so the dz1h tile is fetched once per tile it touches: with one (tile, four chunks)
+//                     item per CTA the kernel's time was the latency chain of a single item -- 512 KB of W1^T
+//                     through a two-stage ring -- whatever the batch size)
+//                     dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq], written (still
 //                     scaled, fp16) straight into the zero-bordered boards conv_bwd2_kernel.cu consumes
 //                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
@@ -23,7 +27,7 @@ namespace cdq {
 // ------------------------------------------------------------------------------------------ dgrad
 constexpr int DG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
 constexpr int DG_B_BYTES = 256 * 64 * 2;        // 32 KB: W1^T, 256 columns x 64 outputs
-constexpr int DG_STAGES = 2;
+constexpr int DG_STAGES = 3;
 constexpr int DG_OFF_B = DG_A_BYTES;
 constexpr int DG_OFF_OUT = DG_OFF_B + DG_STAGES * DG_B_BYTES;   // 64 KB: one chunk of the output (128 positions x 4 squares x 64 channels)
 constexpr int DG_OUT_BYTES = 128 * 512;
@@ -54,152 +58,156 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const long long n_items = ((n + 127) >> 7) * 4;     // (position tile, group of 4 column chunks)
+    const long long n_chunks = ((n + 127) >> 7) * 16;   // (position tile, one of its 16 chunks of 256 columns = 4 squares)
+    const long long g_lo = n_chunks * blockIdx.x / gridDim.x, g_hi = n_chunks * (blockIdx.x + 1) / gridDim.x;
     constexpr uint32_t IDESC = make_idesc_f16(128, 256);
 
     if (warp == 0) {
         if (elect_one_sync()) {
-            uint32_t it = 0, item_no = 0;
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, item_no++) {
-                const long long tile = item >> 2;
-                const int cg = (int)(item & 3);
-                mbar_wait(a_empty, (item_no & 1) ^ 1);
-                mbar_arrive_expect_tx(a_full, DG_A_BYTES);
-                bulk_g2s(smem, reinterpret_cast<const uint8_t*>(dz1h) + tile * DG_A_BYTES, DG_A_BYTES, a_full);
-                for (int c = 0; c < 4; c++)
-                    for (int s = 0; s < 4; s++, it++) {
-                        const int st = it % DG_STAGES;
-                        mbar_wait(empty + st, ((it / DG_STAGES) & 1) ^ 1);
-                        mbar_arrive_expect_tx(full + st, DG_B_BYTES);
-                        bulk_g2s(smem + DG_OFF_B + st * DG_B_BYTES,
-                                 reinterpret_cast<const uint8_t*>(fc1tp) + ((long long)((cg * 4 + c) * 4 + s) << 15), DG_B_BYTES, full + st);
-                    }
+            uint32_t it = 0, a_no = 0;
+            for (long long g = g_lo; g < g_hi; g++) {
+                const long long tile = g >> 4;
+                const int ck = (int)(g & 15);
+                if (g == g_lo || ck == 0) {              // first chunk of a tile in this CTA's range: its dz1h tile
+                    mbar_wait(a_empty, (a_no & 1) ^ 1);
+                    mbar_arrive_expect_tx(a_full, DG_A_BYTES);
+                    bulk_g2s(smem, reinterpret_cast<const uint8_t*>(dz1h) + tile * DG_A_BYTES, DG_A_BYTES, a_full);
+                    a_no++;
+                }
+                for (int s = 0; s < 4; s++, it++) {
+                    const int st = it % DG_STAGES;
+                    mbar_wait(empty + st, ((it / DG_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(full + st, DG_B_BYTES);
+                    bulk_g2s(smem + DG_OFF_B + st * DG_B_BYTES,
+                             reinterpret_cast<const uint8_t*>(fc1tp) + ((long long)(ck * 4 + s) << 15), DG_B_BYTES, full + st);
+                }
             }
         }
     } else if (warp == 1) {
         if (elect_one_sync()) {
-            uint32_t it = 0, item_no = 0, chunk_no = 0;
+            uint32_t it = 0, a_no = 0, chunk_no = 0;
             const uint32_t a0 = smem_u32(smem);
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, item_no++) {
-                mbar_wait(a_full, item_no & 1);
-                for (int c = 0; c < 4; c++, chunk_no++) {
-                    const int ab = chunk_no & 1;
-                    mbar_wait(acc_empty + ab, ((chunk_no >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    for (int s = 0; s < 4; s++, it++) {
-                        const int st = it % DG_STAGES;
-                        mbar_wait(full + st, (it / DG_STAGES) & 1);
-                        tc_fence_after();
-                        const uint32_t b0 = a0 + DG_OFF_B + st * DG_B_BYTES;
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            umma_f16(tmem + ab * 256, make_smem_desc(a0 + (s * 8 + 2 * j) * 2048, 2048, 128),
-                                     make_smem_desc(b0 + j * 2 * 4096, 4096, 128), IDESC, (s | j) != 0);
-                        umma_commit(empty + st);
-                    }
-                    umma_commit(acc_full + ab);
+            for (long long g = g_lo; g < g_hi; g++, chunk_no++) {
+                const int ck = (int)(g & 15);
+                if (g == g_lo || ck == 0) {
+                    mbar_wait(a_full, a_no & 1);
+                    a_no++;
                 }
-                umma_commit(a_empty);
+                const int ab = chunk_no & 1;
+                mbar_wait(acc_empty + ab, ((chunk_no >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int s = 0; s < 4; s++, it++) {
+                    const int st = it % DG_STAGES;
+                    mbar_wait(full + st, (it / DG_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t b0 = a0 + DG_OFF_B + st * DG_B_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        umma_f16(tmem + ab * 256, make_smem_desc(a0 + (s * 8 + 2 * j) * 2048, 2048, 128),
+                                 make_smem_desc(b0 + j * 2 * 4096, 4096, 128), IDESC, (s | j) != 0);
+                    umma_commit(empty + st);
+                }
+                umma_commit(acc_full + ab);
+                if (g + 1 == g_hi || ck == 15) umma_commit(a_empty);    // last chunk of this tile in the range
             }
         }
     } else {
         const int q = warp & 3;
+        const int pr = q * 32 + lane;
         uint32_t chunk_no = 0;
-        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const long long tile = item >> 2;
-            const int cg = (int)(item & 3);
-            const int pr = q * 32 + lane;
-            const long long pos = (tile << 7) + pr;
-            // conv2's ReLU mask of this thread's outputs, gathered half a chunk (128 outputs, 16 loads) AHEAD of its
-            // use: the loads are in flight together and their latency hides under the previous half's epilogue (taken
-            // one block at a time next to the TMEM loads they were 55 % of this kernel's stall samples).
-            // ReLU output > 0 iff its fp16 bits != 0.
-            uint4 mk[16];
-            auto mask_loads = [&](int hc) {           // hc = 2 * chunk + half; blocks p = 4 * half .. 4 * half + 3
-                const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) +
-                                       ((tile * 64 + (cg * 4 + (hc >> 1)) * 4 + (hc & 1) * 2) << 14) + (pr >> 3) * 128 + (pr & 7) * 16;
+        // conv2's ReLU mask of this thread's outputs, gathered half a chunk (128 outputs, 16 loads) AHEAD of its
+        // use: the loads are in flight together and their latency hides under the previous half's epilogue (taken
+        // one block at a time next to the TMEM loads they were 55 % of this kernel's stall samples).
+        // ReLU output > 0 iff its fp16 bits != 0.
+        uint4 mk[16];
+        auto mask_loads = [&](long long h) {          // h = 2 * (global chunk index) + half; blocks p = 4 * half .. 4 * half + 3
+            const long long g = h >> 1, tile = g >> 4;
+            const int ck = (int)(g & 15);
+            const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) +
+                                   ((tile * 64 + ck * 4 + (int)(h & 1) * 2) << 14) + (pr >> 3) * 128 + (pr & 7) * 16;
+            const bool live = (tile << 7) + pr < n;
 #pragma unroll
-                for (int pp = 0; pp < 4; pp++)
+            for (int pp = 0; pp < 4; pp++)
 #pragma unroll
-                    for (int g = 0; g < 4; g++)
-                        mk[pp * 4 + g] = pos < n ? *reinterpret_cast<const uint4*>(mbase + ((pp >> 1) << 14) + ((pp & 1) * 4 + g) * 2048)
-                                                 : make_uint4(0, 0, 0, 0);
-            };
-            mask_loads(0);
-            for (int hc = 0; hc < 8; hc++) {
-                const int c = hc >> 1, half = hc & 1;
-                const int ab = chunk_no & 1;
-                unsigned relu_bits[4];
+                for (int gg = 0; gg < 4; gg++)
+                    mk[pp * 4 + gg] = live ? *reinterpret_cast<const uint4*>(mbase + ((pp >> 1) << 14) + ((pp & 1) * 4 + gg) * 2048)
+                                           : make_uint4(0, 0, 0, 0);
+        };
+        if (g_lo < g_hi) mask_loads(2 * g_lo);
+        for (long long h = 2 * g_lo; h < 2 * g_hi; h++) {
+            const long long gch = h >> 1, tile = gch >> 4;
+            const int ck = (int)(gch & 15), half = (int)(h & 1);
+            const int ab = chunk_no & 1;
+            unsigned relu_bits[4];
 #pragma unroll
-                for (int pp = 0; pp < 4; pp++) {
-                    unsigned bits = 0;
+            for (int pp = 0; pp < 4; pp++) {
+                unsigned bits = 0;
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const unsigned mw[4] = {mk[pp * 4 + g].x, mk[pp * 4 + g].y, mk[pp * 4 + g].z, mk[pp * 4 + g].w};
+                for (int g = 0; g < 4; g++) {
+                    const unsigned mw[4] = {mk[pp * 4 + g].x, mk[pp * 4 + g].y, mk[pp * 4 + g].z, mk[pp * 4 + g].w};
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (g * 8 + 2 * e);
-                            bits |= ((mw[e] >> 16) ? 1u : 0u) << (g * 8 + 2 * e + 1);
-                        }
-                    }
-                    relu_bits[pp] = bits;
-                }
-                if (hc < 7) mask_loads(hc + 1);
-                if (half == 0) {
-                    mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
-                    tc_fence_after();
-                }
-#pragma unroll
-                for (int pp = 0; pp < 4; pp++) {
-                    const int p = half * 4 + pp;
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
-                    tmem_ld_wait();
-                    const unsigned bits = relu_bits[pp];
-                    // Staged in shared memory as [position][32 pieces of 16 bytes], piece = square-in-chunk * 8 + channel
-                    // chunk, XOR-swizzled with the position so that neither these row-wise writes nor the piece-wise
-                    // reads below conflict.  Written straight from the accumulator rows, every warp store put 16 bytes
-                    // on each of 32 different 128-byte lines: 2.1 M line requests, 22 of this kernel's 39 us.
-                    uint8_t* srow = smem + DG_OFF_OUT + pr * 512;
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        unsigned w[4];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            // the value stays scaled (undone downstream)
-                            const float lo = ((bits >> (g * 8 + 2 * e)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e]) : 0.f;
-                            const float hi = ((bits >> (g * 8 + 2 * e + 1)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e + 1]) : 0.f;
-                            __half2 h2 = __floats2half2_rn(lo, hi);
-                            w[e] = *reinterpret_cast<unsigned*>(&h2);
-                        }
-                        const int piece = (p >> 1) * 8 + (p & 1) * 4 + g;
-                        *reinterpret_cast<uint4*>(srow + ((piece ^ (pr & 31)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int e = 0; e < 4; e++) {
+                        bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (g * 8 + 2 * e);
+                        bits |= ((mw[e] >> 16) ? 1u : 0u) << (g * 8 + 2 * e + 1);
                     }
                 }
-                if (half == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + ab);
-                    chunk_no++;
-                    // ---- copy-out: lanes = (channel chunk, square): four lanes write the 64 contiguous bytes of one
-                    // (position, channel chunk, rank), a warp store covers 8 such runs instead of 32 separate lines
-                    asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps: chunk staged
-                    {
-                        const int chk = lane >> 2, sqi = lane & 3, piece = sqi * 8 + chk;
-                        const int sq0 = (cg * 4 + c) * 4;                   // first square of the chunk: file 0 or 4 of one rank
-                        const long long off_lane = (long long)chk * 6400 + ((sq0 >> 3) + 1) * 640 + ((sq0 & 7) + sqi + 1) * 16;
+                relu_bits[pp] = bits;
+            }
+            if (h + 1 < 2 * g_hi) mask_loads(h + 1);
+            if (half == 0) {
+                mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) {
+                const int p = half * 4 + pp;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
+                tmem_ld_wait();
+                const unsigned bits = relu_bits[pp];
+                // Staged in shared memory as [position][32 pieces of 16 bytes], piece = square-in-chunk * 8 + channel
+                // chunk, XOR-swizzled with the position so that neither these row-wise writes nor the piece-wise
+                // reads below conflict.  Written straight from the accumulator rows, every warp store put 16 bytes
+                // on each of 32 different 128-byte lines: 2.1 M line requests, 22 of this kernel's 39 us.
+                uint8_t* srow = smem + DG_OFF_OUT + pr * 512;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    unsigned w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        // the value stays scaled (undone downstream)
+                        const float lo = ((bits >> (g * 8 + 2 * e)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e]) : 0.f;
+                        const float hi = ((bits >> (g * 8 + 2 * e + 1)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e + 1]) : 0.f;
+                        __half2 h2 = __floats2half2_rn(lo, hi);
+                        w[e] = *reinterpret_cast<unsigned*>(&h2);
+                    }
+                    const int piece = (p >> 1) * 8 + (p & 1) * 4 + g;
+                    *reinterpret_cast<uint4*>(srow + ((piece ^ (pr & 31)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            if (half == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + ab);
+                chunk_no++;
+                // ---- copy-out: lanes = (channel chunk, square): four lanes write the 64 contiguous bytes of one
+                // (position, channel chunk, rank), a warp store covers 8 such runs instead of 32 separate lines
+                asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps: chunk staged
+                {
+                    const int chk = lane >> 2, sqi = lane & 3, piece = sqi * 8 + chk;
+                    const int sq0 = ck * 4;                             // first square of the chunk: file 0 or 4 of one rank
+                    const long long off_lane = (long long)chk * 6400 + ((sq0 >> 3) + 1) * 640 + ((sq0 & 7) + sqi + 1) * 16;
 #pragma unroll 4
-                        for (int r = 0; r < 32; r++) {
-                            const int rowi = q * 32 + r;
-                            const long long rpos = (tile << 7) + rowi;
-                            const uint4 val = *reinterpret_cast<const uint4*>(smem + DG_OFF_OUT + rowi * 512 + ((piece ^ (rowi & 31)) << 4));
-                            // conv2-backward board of this position's group of four: [8 chunks][10 ranks][4 pos][10 files][8 halfs]
-                            if (rpos < n)
-                                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dz2_boards) + (rpos >> 2) * 51200 + (int)(rpos & 3) * 160 + off_lane) = val;
-                        }
+                    for (int r = 0; r < 32; r++) {
+                        const int rowi = q * 32 + r;
+                        const long long rpos = (tile << 7) + rowi;
+                        const uint4 val = *reinterpret_cast<const uint4*>(smem + DG_OFF_OUT + rowi * 512 + ((piece ^ (rowi & 31)) << 4));
+                        // conv2-backward board of this position's group of four: [8 chunks][10 ranks][4 pos][10 files][8 halfs]
+                        if (rpos < n)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dz2_boards) + (rpos >> 2) * 51200 + (int)(rpos & 3) * 160 + off_lane) = val;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");         // staging buffer free for the next chunk
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");         // staging buffer free for the next chunk
             }
         }
     }
@@ -311,10 +319,11 @@ int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp
         cudaFuncSetAttribute(fc1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
         attr_set = true;
     }
-    const long long items = ((n + 127) >> 7) * 4;
+    const long long chunks = ((n + 127) >> 7) * 16;     // work items: (tile, 256-column chunk), contiguous ranges per CTA
     const int sms = device_sm_count();
     ProfileScope ps(KK_FC1_DGRAD, st);
-    fc1_dgrad_kernel<<<(unsigned)(items < sms ? items : sms), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, dz2_boards);
+    const long long per_cta = (chunks + sms - 1) / sms;      // no CTA takes more than this: use as few CTAs as that allows
+    fc1_dgrad_kernel<<<(unsigned)((chunks + per_cta - 1) / per_cta), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, dz2_boards);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 import chess_deep_q_b200 as cdq  # noqa: E402
 from chess_deep_q_b200.train import FusedAdam, GraphedDQNStep  # noqa: E402
 
-n = 4096
+n = int(os.environ.get("BATCH", "4096"))
 boards = torch.empty((n + 1, 9), dtype=torch.int64, device="cuda")
 L = cdq._lib.lib()
 cdq._lib.check(L.cdq_random_playouts(boards.data_ptr(), n + 1, 42, 199, cdq._lib.stream_ptr()))
