@@ -346,6 +346,14 @@ def test_full_size_properties_1m(cdq, oracle):
     # (4) ranges
     assert float(out["leaf"].abs().max()) <= 1.0
     assert bool(torch.isfinite(out["score"]).all())
+    # (5) the host-buffer path (cdq_leaf_eval_host: ramped, double-buffered chunks, copies inside) returns the same
+    #     bits for the whole batch and for a ragged prefix that ends inside a ramp chunk
+    h = _np(d).view(np.uint64).reshape(-1).view(oracle.BOARD_DTYPE)
+    for m in (n, 100_003):
+        host = ev.evaluate_host(h[:m])
+        for k in ("leaf", "score"):
+            assert np.array_equal(host[k], _np(out[k])[:m]), (m, k)
+        assert np.array_equal(host["flags"], _np(out["flags"]).view(np.uint32)[:m]), m
 
 
 def test_attack_and_movement_maps(cdq, oracle, eval_golden):
