@@ -115,56 +115,36 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
         const int q = warp & 3;
         const int pr = q * 32 + lane;
         uint32_t chunk_no = 0;
-        // conv2's ReLU mask of this thread's outputs, gathered half a chunk (128 outputs, 16 loads) AHEAD of its
-        // use: the loads are in flight together and their latency hides under the previous half's epilogue (taken
-        // one block at a time next to the TMEM loads they were 55 % of this kernel's stall samples).
-        // ReLU output > 0 iff its fp16 bits != 0.
-        uint4 mk[16];
-        auto mask_loads = [&](long long h) {          // h = 2 * (global chunk index) + half; blocks p = 4 * half .. 4 * half + 3
-            const long long g = h >> 1, tile = g >> 4;
+        // conv2's ReLU mask (ReLU output > 0 iff its fp16 value != 0) is applied as a bitwise AND with __hne2_mask(act2, 0)
+        // = {0xffff, 0} per half: two instructions per pair of outputs (packing the mask into bits and selecting per
+        // element was two thirds of this kernel's instructions).  The raw act2 words of a 32-column block are loaded two blocks ahead of
+        // their use (a ring of four register slots; taken next to the TMEM loads they were 55 % of the stall samples).
+        uint4 mraw[4][4];
+        auto mload = [&](uint4 (&dst)[4], long long g, int p) {   // block p of chunk g: square 4 ck + p / 2, channel chunks 4 (p & 1) ..
+            const long long tile = g >> 4;
             const int ck = (int)(g & 15);
-            const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) +
-                                   ((tile * 64 + ck * 4 + (int)(h & 1) * 2) << 14) + (pr >> 3) * 128 + (pr & 7) * 16;
+            const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + ck * 4 + (p >> 1)) << 14) +
+                                   (p & 1) * 4 * 2048 + (pr >> 3) * 128 + (pr & 7) * 16;
             const bool live = (tile << 7) + pr < n;
 #pragma unroll
-            for (int pp = 0; pp < 4; pp++)
-#pragma unroll
-                for (int gg = 0; gg < 4; gg++)
-                    mk[pp * 4 + gg] = live ? *reinterpret_cast<const uint4*>(mbase + ((pp >> 1) << 14) + ((pp & 1) * 4 + gg) * 2048)
-                                           : make_uint4(0, 0, 0, 0);
+            for (int gg = 0; gg < 4; gg++)
+                dst[gg] = live ? *reinterpret_cast<const uint4*>(mbase + gg * 2048) : make_uint4(0, 0, 0, 0);
         };
-        if (g_lo < g_hi) mask_loads(2 * g_lo);
-        for (long long h = 2 * g_lo; h < 2 * g_hi; h++) {
-            const long long gch = h >> 1, tile = gch >> 4;
-            const int ck = (int)(gch & 15), half = (int)(h & 1);
+        if (g_lo < g_hi) { mload(mraw[0], g_lo, 0); mload(mraw[1], g_lo, 1); }
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+        for (long long gch = g_lo; gch < g_hi; gch++) {
+            const long long tile = gch >> 4;
+            const int ck = (int)(gch & 15);
             const int ab = chunk_no & 1;
-            unsigned relu_bits[4];
+            mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
+            tc_fence_after();
 #pragma unroll
-            for (int pp = 0; pp < 4; pp++) {
-                unsigned bits = 0;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const unsigned mw[4] = {mk[pp * 4 + g].x, mk[pp * 4 + g].y, mk[pp * 4 + g].z, mk[pp * 4 + g].w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (g * 8 + 2 * e);
-                        bits |= ((mw[e] >> 16) ? 1u : 0u) << (g * 8 + 2 * e + 1);
-                    }
-                }
-                relu_bits[pp] = bits;
-            }
-            if (h + 1 < 2 * g_hi) mask_loads(h + 1);
-            if (half == 0) {
-                mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
-                tc_fence_after();
-            }
-#pragma unroll
-            for (int pp = 0; pp < 4; pp++) {
-                const int p = half * 4 + pp;
+            for (int p = 0; p < 8; p++) {
+                if (p + 2 < 8) mload(mraw[(p + 2) & 3], gch, p + 2);
+                else if (gch + 1 < g_hi) mload(mraw[(p + 2) & 3], gch + 1, p + 2 - 8);
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
                 tmem_ld_wait();
-                const unsigned bits = relu_bits[pp];
                 // Staged in shared memory as [position][32 pieces of 16 bytes], piece = square-in-chunk * 8 + channel
                 // chunk, XOR-swizzled with the position so that neither these row-wise writes nor the piece-wise
                 // reads below conflict.  Written straight from the accumulator rows, every warp store put 16 bytes
@@ -172,20 +152,19 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                 uint8_t* srow = smem + DG_OFF_OUT + pr * 512;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
+                    const unsigned mw[4] = {mraw[p & 3][g].x, mraw[p & 3][g].y, mraw[p & 3][g].z, mraw[p & 3][g].w};
                     unsigned w[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         // the value stays scaled (undone downstream)
-                        const float lo = ((bits >> (g * 8 + 2 * e)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e]) : 0.f;
-                        const float hi = ((bits >> (g * 8 + 2 * e + 1)) & 1u) ? __uint_as_float(v[g * 8 + 2 * e + 1]) : 0.f;
-                        __half2 h2 = __floats2half2_rn(lo, hi);
-                        w[e] = *reinterpret_cast<unsigned*>(&h2);
+                        const __half2 h2 = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * e]), __uint_as_float(v[g * 8 + 2 * e + 1]));
+                        w[e] = *reinterpret_cast<const unsigned*>(&h2) & __hne2_mask(*reinterpret_cast<const __half2*>(&mw[e]), zero2);
                     }
                     const int piece = (p >> 1) * 8 + (p & 1) * 4 + g;
                     *reinterpret_cast<uint4*>(srow + ((piece ^ (pr & 31)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            if (half == 1) {
+            {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + ab);
