@@ -22,7 +22,8 @@ struct PackedNet {
 
 int device_sm_count();
 int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me = nullptr);   // fp32 parameters -> all of p
-int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, __half* dz2_boards,
+int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream_t st);   // 1 bit per ReLU(conv2) output, dgrad's order
+int launch_fc1_dgrad(const __half* dz1h, const unsigned* relu_mask, const __half* fc1tp, long long n, __half* dz2_boards,
                      cudaStream_t st);
 int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
                      float* g_w2, float* g_b2, float* dz1c, unsigned* sched, cudaStream_t st);

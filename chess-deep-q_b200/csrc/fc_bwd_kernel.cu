@@ -24,6 +24,43 @@
 
 namespace cdq {
 
+// ------------------------------------------------------------------------------------------ ReLU bit mask of conv2
+// One bit per ReLU(conv2) output (value != 0), in the order the data gradient's epilogue consumes them: word
+// [tile][chunk of 4 squares][block p = 2 (square in chunk) + channel half][position] holds the 32 channels of that half,
+// bit 8 gg + e = channel chunk gg, channel e.  The data gradient used to read the fp16 activations themselves for the
+// mask: 64 KB per chunk and CTA through 16 KB of loads in flight, which at the L2 latency is 7 of the 8 us a chunk
+// took.  This kernel reads the 8 KB per position once, coalesced, on the side stream under the fc forward.
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(const __half* __restrict__ act2, long long n_tiles, unsigned* __restrict__ mask) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (tile, square, half, position), position fastest
+    if (t >= n_tiles * 64 * 2 * 128) return;
+    const int pos = (int)(t & 127), h = (int)((t >> 7) & 1), sq = (int)((t >> 8) & 63);
+    const long long tile = t >> 14;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + sq) << 14) + h * 4 * 2048 + (pos >> 3) * 128 + (pos & 7) * 16;
+    uint4 m[4];
+#pragma unroll
+    for (int gg = 0; gg < 4; gg++) m[gg] = *reinterpret_cast<const uint4*>(src + gg * 2048);
+    unsigned bits = 0;
+#pragma unroll
+    for (int gg = 0; gg < 4; gg++) {
+        const unsigned mw[4] = {m[gg].x, m[gg].y, m[gg].z, m[gg].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            bits |= ((mw[e] & 0xffffu) ? 1u : 0u) << (gg * 8 + 2 * e);
+            bits |= ((mw[e] >> 16) ? 1u : 0u) << (gg * 8 + 2 * e + 1);
+        }
+    }
+    mask[(((tile * 16 + (sq >> 2)) * 8) + (sq & 3) * 2 + h) * 128 + pos] = bits;
+}
+
+int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream_t st) {
+    const long long tiles = (n + 127) >> 7, threads = tiles * 64 * 2 * 128;
+    ProfileScope ps(KK_TRAIN, st);
+    relu_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(act2, tiles, mask);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ dgrad
 constexpr int DG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
 constexpr int DG_B_BYTES = 256 * 64 * 2;        // 32 KB: W1^T, 256 columns x 64 outputs
@@ -36,7 +73,7 @@ constexpr int DG_SMEM = DG_OFF_BAR + 128;
 constexpr int DG_THREADS = 192;
 
 __global__ void __launch_bounds__(DG_THREADS, 1)
-fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act2, const __half* __restrict__ fc1tp,
+fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ relu_mask, const __half* __restrict__ fc1tp,
                  long long n, __half* __restrict__ dz2_boards) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + DG_OFF_BAR);   // [4]
@@ -115,36 +152,32 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
         const int q = warp & 3;
         const int pr = q * 32 + lane;
         uint32_t chunk_no = 0;
-        // conv2's ReLU mask (ReLU output > 0 iff its fp16 value != 0) is applied as a bitwise AND with __hne2_mask(act2, 0)
-        // = {0xffff, 0} per half: two instructions per pair of outputs (packing the mask into bits and selecting per
-        // element was two thirds of this kernel's instructions).  The raw act2 words of a 32-column block are loaded two blocks ahead of
-        // their use (a ring of four register slots; taken next to the TMEM loads they were 55 % of the stall samples).
-        uint4 mraw[4][4];
-        auto mload = [&](uint4 (&dst)[4], long long g, int p) {   // block p of chunk g: square 4 ck + p / 2, channel chunks 4 (p & 1) ..
-            const long long tile = g >> 4;
-            const int ck = (int)(g & 15);
-            const uint8_t* mbase = reinterpret_cast<const uint8_t*>(act2) + ((tile * 64 + ck * 4 + (p >> 1)) << 14) +
-                                   (p & 1) * 4 * 2048 + (pr >> 3) * 128 + (pr & 7) * 16;
-            const bool live = (tile << 7) + pr < n;
+        // conv2's ReLU mask: one 32-bit word per 32-column block (relu_mask_kernel), the eight words of a chunk loaded one
+        // chunk ahead; applied as a bitwise AND on the packed fp16 pairs.
+        unsigned mcur[8], mnext[8];
+        auto mload = [&](unsigned (&dst)[8], long long g) {
+            const unsigned* src = relu_mask + g * 8 * 128 + pr;
 #pragma unroll
-            for (int gg = 0; gg < 4; gg++)
-                dst[gg] = live ? *reinterpret_cast<const uint4*>(mbase + gg * 2048) : make_uint4(0, 0, 0, 0);
+            for (int p = 0; p < 8; p++) dst[p] = src[p * 128];
         };
-        if (g_lo < g_hi) { mload(mraw[0], g_lo, 0); mload(mraw[1], g_lo, 1); }
-        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+        if (g_lo < g_hi) mload(mnext, g_lo);
         for (long long gch = g_lo; gch < g_hi; gch++) {
             const long long tile = gch >> 4;
             const int ck = (int)(gch & 15);
             const int ab = chunk_no & 1;
+#pragma unroll
+            for (int p = 0; p < 8; p++) mcur[p] = mnext[p];
+            if (gch + 1 < g_hi) mload(mnext, gch + 1);
             mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
             tc_fence_after();
+            // the TMEM load of block p + 1 is in flight while block p is converted and staged
+            uint32_t vv[2][32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256, vv[0]);
 #pragma unroll
             for (int p = 0; p < 8; p++) {
-                if (p + 2 < 8) mload(mraw[(p + 2) & 3], gch, p + 2);
-                else if (gch + 1 < g_hi) mload(mraw[(p + 2) & 3], gch + 1, p + 2 - 8);
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + p * 32, v);
                 tmem_ld_wait();
+                if (p + 1 < 8) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + (p + 1) * 32, vv[(p + 1) & 1]);
+                uint32_t (&v)[32] = vv[p & 1];
                 // Staged in shared memory as [position][32 pieces of 16 bytes], piece = square-in-chunk * 8 + channel
                 // chunk, XOR-swizzled with the position so that neither these row-wise writes nor the piece-wise
                 // reads below conflict.  Written straight from the accumulator rows, every warp store put 16 bytes
@@ -152,13 +185,13 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
                 uint8_t* srow = smem + DG_OFF_OUT + pr * 512;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const unsigned mw[4] = {mraw[p & 3][g].x, mraw[p & 3][g].y, mraw[p & 3][g].z, mraw[p & 3][g].w};
                     unsigned w[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         // the value stays scaled (undone downstream)
                         const __half2 h2 = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * e]), __uint_as_float(v[g * 8 + 2 * e + 1]));
-                        w[e] = *reinterpret_cast<const unsigned*>(&h2) & __hne2_mask(*reinterpret_cast<const __half2*>(&mw[e]), zero2);
+                        const unsigned two = mcur[p] >> (g * 8 + 2 * e);
+                        w[e] = *reinterpret_cast<const unsigned*>(&h2) & ((two & 1u ? 0xffffu : 0u) | (two & 2u ? 0xffff0000u : 0u));
                     }
                     const int piece = (p >> 1) * 8 + (p & 1) * 4 + g;
                     *reinterpret_cast<uint4*>(srow + ((piece ^ (pr & 31)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -290,7 +323,7 @@ fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp, long long n, __half* dz2_boards,
+int launch_fc1_dgrad(const __half* dz1h, const unsigned* relu_mask, const __half* fc1tp, long long n, __half* dz2_boards,
                      cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -302,7 +335,7 @@ int launch_fc1_dgrad(const __half* dz1h, const __half* act2, const __half* fc1tp
     const int sms = device_sm_count();
     ProfileScope ps(KK_FC1_DGRAD, st);
     const long long per_cta = (chunks + sms - 1) / sms;      // no CTA takes more than this: use as few CTAs as that allows
-    fc1_dgrad_kernel<<<(unsigned)((chunks + per_cta - 1) / per_cta), DG_THREADS, DG_SMEM, st>>>(dz1h, act2, fc1tp, n, dz2_boards);
+    fc1_dgrad_kernel<<<(unsigned)((chunks + per_cta - 1) / per_cta), DG_THREADS, DG_SMEM, st>>>(dz1h, relu_mask, fc1tp, n, dz2_boards);
     count_launch();
     return (int)cudaGetLastError();
 }

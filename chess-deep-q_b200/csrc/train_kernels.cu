@@ -266,7 +266,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
-    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_boards; __half* dz2_boards; unsigned* sched; float* hidden; float* q; float* qn; float* dz1c;
+    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_boards; __half* dz2_boards; unsigned* sched; unsigned* relu_mask; float* hidden; float* q; float* qn; float* dz1c;
     size_t zero_from, zero_bytes;   // [a1_boards, dz2_boards]: borders must be zero, cleared every step
     size_t total;
 };
@@ -283,6 +283,7 @@ static TrainWs carve(void* base, long long n) {
     w.dz2_boards = (__half*)take((size_t)groups * 102400);
     w.sched = (unsigned*)take(256);           // conv2 backward's work counters: zero at entry (they reset themselves)
     w.zero_bytes = off - w.zero_from;
+    w.relu_mask = (unsigned*)take((size_t)tiles * 16 * 8 * 128 * 4);      // 1 bit per ReLU(conv2) output
     w.hidden = (float*)take((size_t)n * 256 * 4);
     w.q = (float*)take((size_t)n * 4);
     w.qn = (float*)take((size_t)n * 4);
@@ -299,12 +300,13 @@ size_t train_workspace_bytes(long long n) { return n > 0 ? carve(nullptr, n).tot
 namespace {
 struct SideStream {
     cudaStream_t st = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr;
     int init() {
         if (st) return 0;
         CDQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CDQ_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         CDQ_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        CDQ_CUDA(cudaEventCreateWithFlags(&mid, cudaEventDisableTiming));
         return 0;
     }
 };
@@ -335,12 +337,16 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     const int online_sms = device_sm_count() * online_pct / 100, target_sms = device_sm_count() - online_sms;
     if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, target_sms))) return e;
     if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
-    CDQ_CUDA(cudaEventRecord(g_side.join, side));
     // the online network's fp16 tiles are rebuilt from the fp32 parameters next to the target forward
     const bool zero_in_pack = (loss_kind_flags & CDQ_TRAIN_REPACK) && (loss_kind_flags & CDQ_TRAIN_ZERO_LOSS);
     if ((loss_kind_flags & CDQ_TRAIN_ZERO_LOSS) && !zero_in_pack) CDQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st, zero_in_pack ? loss : nullptr))) return e;
     if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards, online_sms))) return e;
+    // ReLU(conv2)'s bit mask for the fc1 data gradient: side stream, after the target forward, under the online fc head
+    CDQ_CUDA(cudaEventRecord(g_side.mid, st));
+    CDQ_CUDA(cudaStreamWaitEvent(side, g_side.mid, 0));
+    if ((e = launch_relu_mask(ws.act2_tiles, n, ws.relu_mask, side))) return e;
+    CDQ_CUDA(cudaEventRecord(g_side.join, side));
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // ---- loss, tanh, fc2, fc1 bias
@@ -358,7 +364,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     CDQ_CUDA(cudaStreamWaitEvent(side, g_side.fork, 0));
     if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, side))) return e;
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
-    if ((e = launch_fc1_dgrad(ws.dz1h, ws.act2_tiles, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
+    if ((e = launch_fc1_dgrad(ws.dz1h, ws.relu_mask, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
     if ((e = launch_conv2_bwd(ws.dz2_boards, ws.a1_boards, net->p.w2tp, n, 1.f / scale, (float*)g.conv2_w, (float*)g.conv2_b,
                               ws.dz1c, ws.sched, st))) return e;
     {
