@@ -26,7 +26,7 @@ namespace cdq {
 
 // ------------------------------------------------------------------------------------------ ReLU bit mask of conv2
 // One bit per ReLU(conv2) output (value != 0), in the order the data gradient's epilogue consumes them: word
-// [tile][chunk of 4 squares][block p = 2 (square in chunk) + channel half][position] holds the 32 channels of that half,
+// [tile][chunk = 2 rank + channel half][block p = file][position] holds the 32 channels of that half of one square,
 // bit 8 gg + e = channel chunk gg, channel e.  The data gradient used to read the fp16 activations themselves for the
 // mask: 64 KB per chunk and CTA through 16 KB of loads in flight, which at the L2 latency is 7 of the 8 us a chunk
 // took.  This kernel reads the 8 KB per position once, coalesced, on the side stream under the fc forward.
@@ -50,7 +50,7 @@ relu_mask_kernel(const __half* __restrict__ act2, long long n_tiles, unsigned* _
             bits |= ((mw[e] >> 16) ? 1u : 0u) << (gg * 8 + 2 * e + 1);
         }
     }
-    mask[(((tile * 16 + (sq >> 2)) * 8) + (sq & 3) * 2 + h) * 128 + pos] = bits;
+    mask[(((tile * 16 + (sq >> 3) * 2 + h) * 8) + (sq & 7)) * 128 + pos] = bits;
 }
 
 int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream_t st) {
@@ -64,10 +64,11 @@ int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream
 // ------------------------------------------------------------------------------------------ dgrad
 constexpr int DG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
 constexpr int DG_B_BYTES = 256 * 64 * 2;        // 32 KB: W1^T, 256 columns x 64 outputs
-constexpr int DG_STAGES = 3;
+constexpr int DG_STAGES = 2;
 constexpr int DG_OFF_B = DG_A_BYTES;
-constexpr int DG_OFF_OUT = DG_OFF_B + DG_STAGES * DG_B_BYTES;   // 64 KB: one chunk of the output (128 positions x 4 squares x 64 channels)
-constexpr int DG_OUT_BYTES = 128 * 512;
+constexpr int DG_OFF_OUT = DG_OFF_B + DG_STAGES * DG_B_BYTES;   // one chunk of the output, staged as the 128 board blocks it becomes
+constexpr int DG_GROUP_STRIDE = 4 * 640 + 16;                   // [group of 4 positions][4 channel chunks][4 pos][10 files][16 B] (+16: bank spread)
+constexpr int DG_OUT_BYTES = 32 * DG_GROUP_STRIDE;
 constexpr int DG_OFF_BAR = DG_OFF_OUT + DG_OUT_BYTES;
 constexpr int DG_SMEM = DG_OFF_BAR + 128;
 constexpr int DG_THREADS = 192;
@@ -95,6 +96,10 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // the staged board blocks include the border files, which stay zero for the whole kernel
+    for (int i = tid; i < DG_OUT_BYTES / 16; i += DG_THREADS) reinterpret_cast<uint4*>(smem + DG_OFF_OUT)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    __syncthreads();
     const long long n_chunks = ((n + 127) >> 7) * 16;   // (position tile, one of its 16 chunks of 256 columns = 4 squares)
     const long long g_lo = n_chunks * blockIdx.x / gridDim.x, g_hi = n_chunks * (blockIdx.x + 1) / gridDim.x;
     constexpr uint32_t IDESC = make_idesc_f16(128, 256);
@@ -178,11 +183,13 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
                 tmem_ld_wait();
                 if (p + 1 < 8) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + (p + 1) * 32, vv[(p + 1) & 1]);
                 uint32_t (&v)[32] = vv[p & 1];
-                // Staged in shared memory as [position][32 pieces of 16 bytes], piece = square-in-chunk * 8 + channel
-                // chunk, XOR-swizzled with the position so that neither these row-wise writes nor the piece-wise
-                // reads below conflict.  Written straight from the accumulator rows, every warp store put 16 bytes
-                // on each of 32 different 128-byte lines: 2.1 M line requests, 22 of this kernel's 39 us.
-                uint8_t* srow = smem + DG_OFF_OUT + pr * 512;
+                // Block p is FILE p of the chunk's rank, 32 channels = four 16-byte pieces.  They are staged in shared memory
+                // exactly as the board blocks they become -- [group of 4 positions][channel chunk][4 positions][10 files][16 B],
+                // 640 contiguous bytes per (group, channel chunk) both here and in global memory -- and leave as 128 bulk
+                // copies of 640 bytes per chunk.  (Written straight from the accumulator rows every warp store put 16 bytes
+                // on each of 32 different 128-byte lines: 22 of 39 us; as 64-byte runs through per-thread stores still 17 of 28.)
+                uint8_t* sdst = smem + DG_OFF_OUT + (pr >> 2) * DG_GROUP_STRIDE + (pr & 3) * 160 + (p + 1) * 16;
+                const bool live = (tile << 7) + pr < n;         // rows beyond n must be ZERO boards: conv2's backward contracts whole units
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     unsigned w[4];
@@ -190,11 +197,10 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
                     for (int e = 0; e < 4; e++) {
                         // the value stays scaled (undone downstream)
                         const __half2 h2 = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * e]), __uint_as_float(v[g * 8 + 2 * e + 1]));
-                        const unsigned two = mcur[p] >> (g * 8 + 2 * e);
+                        const unsigned two = live ? mcur[p] >> (g * 8 + 2 * e) : 0u;
                         w[e] = *reinterpret_cast<const unsigned*>(&h2) & ((two & 1u ? 0xffffu : 0u) | (two & 2u ? 0xffff0000u : 0u));
                     }
-                    const int piece = (p >> 1) * 8 + (p & 1) * 4 + g;
-                    *reinterpret_cast<uint4*>(srow + ((piece ^ (pr & 31)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(sdst + g * 640) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             {
@@ -202,26 +208,24 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + ab);
                 chunk_no++;
-                // ---- copy-out: lanes = (channel chunk, square): four lanes write the 64 contiguous bytes of one
-                // (position, channel chunk, rank), a warp store covers 8 such runs instead of 32 separate lines
-                asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps: chunk staged
+                // ---- copy-out: thread = (group of 4 positions, channel chunk): one 640-byte block [4 pos][10 files] of the unit
+                fence_proxy_async();                                        // staged with generic stores, read by the bulk copies
+                asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps: chunk staged
                 {
-                    const int chk = lane >> 2, sqi = lane & 3, piece = sqi * 8 + chk;
-                    const int sq0 = ck * 4;                             // first square of the chunk: file 0 or 4 of one rank
-                    const long long off_lane = (long long)chk * 6400 + ((sq0 >> 3) + 1) * 640 + ((sq0 & 7) + sqi + 1) * 16;
-#pragma unroll 4
-                    for (int r = 0; r < 32; r++) {
-                        const int rowi = q * 32 + r;
-                        const long long rpos = (tile << 7) + rowi;
-                        const uint4 val = *reinterpret_cast<const uint4*>(smem + DG_OFF_OUT + rowi * 512 + ((piece ^ (rowi & 31)) << 4));
-                        // conv2-backward board of this position's group of four: [8 chunks][10 ranks][4 pos][10 files][8 halfs]
-                        if (rpos < n)
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dz2_boards) + (rpos >> 2) * 51200 + (int)(rpos & 3) * 160 + off_lane) = val;
+                    const int grp = pr >> 2, gg = pr & 3;
+                    const int rank = ck >> 1, chalf = ck & 1;
+                    if ((tile << 7) + grp * 4 < n) {
+                        uint8_t* dst = reinterpret_cast<uint8_t*>(dz2_boards) + (tile * 32 + grp) * 51200 + (chalf * 4 + gg) * 6400 + (rank + 1) * 640;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(dst), "r"(smem_u32(smem + DG_OFF_OUT + grp * DG_GROUP_STRIDE + gg * 640)), "r"(640) : "memory");
                     }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the copies have read the staging buffer
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");         // staging buffer free for the next chunk
+                asm volatile("bar.sync 1, 128;" ::: "memory");             // staging buffer free for the next chunk
             }
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");           // all board blocks written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();

@@ -208,13 +208,15 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
             for (int k8 = 0; k8 < 8; k8++) v[k8] = src[k8 * 64];
             *reinterpret_cast<uint4*>(fc1p + ((((long long)sq * 8 + kc) * 32 + (nn >> 3)) * 8 + (nn & 7)) * 8) = pack8_f16(v);
         } else if (t < 2 * PK_V3) {
-            // fc1tp[chunk 16][stage 4][kc 8][ng 32][n8][j8]: row n' = sq*64 + ch, K = fc1 output j
+            // fc1tp[chunk 16][stage 4][kc 8][ng 32][n8][j8], K = fc1 output j.  A chunk of 256 rows is one RANK and one HALF of
+            // the channels, row in chunk = file * 32 + channel in half: a 32-column accumulator block of the data gradient
+            // (fc_bwd_kernel.cu) is then one square, and the eight blocks of a chunk are the eight files of a board row.
             const long long u = t - PK_V3;
             const int sq = u & 63, ch = (u >> 6) & 63, jg = (int)(u >> 12);          // jg = sg*8 + kc
             const float* src = w.fc1_w + (long long)jg * 8 * 4096 + ch * 64 + sq;
 #pragma unroll
             for (int j8 = 0; j8 < 8; j8++) v[j8] = src[(long long)j8 * 4096];
-            const int np = sq * 64 + ch, ck = np >> 8, ng = (np >> 3) & 31, n8 = np & 7;
+            const int ck = (sq >> 3) * 2 + (ch >> 5), r256 = (sq & 7) * 32 + (ch & 31), ng = r256 >> 3, n8 = r256 & 7;
             *reinterpret_cast<uint4*>(fc1tp + (((((long long)ck * 32 + jg) * 32 + ng) * 8 + n8) * 8)) = pack8_f16(v);
         }
         return;
