@@ -253,9 +253,9 @@ conv_stack_kernel(const CdqBoard* __restrict__ boards, long long n, const Packed
                     o.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]), __uint_as_float(v[kc * 8 + 5]));
                     o.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]), __uint_as_float(v[kc * 8 + 7]));
                     *reinterpret_cast<uint4*>(dst + kc * CHUNK_BYTES) = o;
-                    if (act1_boards)   // training: keep ReLU(conv1) as rank-major boards [group of 4][10 ranks][4 chunks][4 pos][10 files][8 halfs]
-                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 2) * 25600 + (y + 1) * 2560 +
-                                                  kc * 640 + (int)(pos & 3) * ROW_BYTES + (r_x + 1) * CELL) = o;
+                    if (act1_boards)   // training: keep ReLU(conv1), position-contiguous [tile of 16][file][chunk][rank][16 pos][8 halfs]
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 4) * 65536 + r_x * 8192 + kc * 2048 +
+                                                  y * 256 + (int)(pos & 15) * CELL) = o;
                     if (dbg_act1 && pos < n)
                         *reinterpret_cast<uint4*>(dbg_act1 + (pos * 64 + y * 8 + r_x) * 32 + kc * 8) = o;
                 }

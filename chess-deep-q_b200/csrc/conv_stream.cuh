@@ -414,9 +414,11 @@ __device__ __forceinline__ void conv_stream_body(uint8_t* smem, const CdqBoard* 
                 u.z = relu_pack_f16(__uint_as_float(v[kc * 8 + 4]), __uint_as_float(v[kc * 8 + 5]));
                 u.w = relu_pack_f16(__uint_as_float(v[kc * 8 + 6]), __uint_as_float(v[kc * 8 + 7]));
                 *reinterpret_cast<uint4*>(dst + kc * CHUNK_B) = u;
-                if (act1_boards)   // training: ReLU(conv1) as zero-bordered boards for conv2's backward pass
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 2) * TB_GROUP + kc * TB_CHUNK +
-                                              (y + 1) * TB_RANK + (int)(pos & 3) * TB_ROW + (f + 1) * CELL) = u;
+                if (act1_boards)   // training: ReLU(conv1) for conv2's backward pass, POSITION-contiguous [tile of 16][file][chunk][rank]
+                                   // [16 positions][8 halfs]: 4 lines per warp store; a1_boards_kernel (train_kernels.cu) turns it
+                                   // into boards on the side stream (16 bytes straight into the boards were 32 lines per store)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(act1_boards) + (pos >> 4) * 65536 + f * 8192 + kc * 2048 +
+                                              y * 256 + (int)(pos & 15) * CELL) = u;
                 if (dbg_act1 && pos < n)
                     *reinterpret_cast<uint4*>(dbg_act1 + (pos * 64 + y * 8 + f) * 32 + kc * 8) = u;
             }

@@ -238,6 +238,27 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
     }
 }
 
+// ReLU(conv1) from the forward's position-contiguous dump [tile of 16][file 8][chunk 4][rank 8][16 positions][8 halfs] to the
+// zero-bordered boards conv2's backward fetches with one bulk copy per unit: [unit of 4 positions][10 ranks][4 chunks]
+// [4 positions][10 files][8 halfs].  One CTA per (tile, rank, chunk): 2 KB through shared memory, 256-byte runs in, 128-byte
+// runs out.  Runs on the side stream under the fc forward.
+__global__ void __launch_bounds__(128)
+a1_boards_kernel(const uint4* __restrict__ dump, uint4* __restrict__ boards) {
+    __shared__ uint4 cell[16][9];                       // [position][file], padded
+    const int kc = blockIdx.x & 3, y = (blockIdx.x >> 2) & 7;
+    const long long tile = blockIdx.x >> 5;
+    const int t = threadIdx.x;
+    {
+        const int f = t >> 4, p = t & 15;               // 16 consecutive threads = 256 contiguous bytes
+        cell[p][f] = dump[tile * 4096 + f * 512 + kc * 128 + y * 16 + p];
+    }
+    __syncthreads();
+    {
+        const int p = t >> 3, f = t & 7;                // 8 consecutive threads = the 8 interior files of a board row
+        boards[(tile * 4 + (p >> 2)) * 1600 + (y + 1) * 160 + kc * 40 + (p & 3) * 10 + f + 1] = cell[p][f];
+    }
+}
+
 // Adam (torch.optim.Adam defaults: no weight decay, no amsgrad); grads are pre-multiplied by grad_scale
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
@@ -266,7 +287,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 // ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
-    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_boards; __half* dz2_boards; unsigned* sched; unsigned* relu_mask; float* hidden; float* q; float* qn; float* dz1c;
+    __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_dump; __half* a1_boards; __half* dz2_boards; unsigned* sched; unsigned* relu_mask; float* hidden; float* q; float* qn; float* dz1c;
     size_t zero_from, zero_bytes;   // [a1_boards, dz2_boards]: borders must be zero, cleared every step
     size_t total;
 };
@@ -278,6 +299,7 @@ static TrainWs carve(void* base, long long n) {
     w.act2_tiles = (__half*)take((size_t)tiles << 20);
     w.act2_target = (__half*)take((size_t)tiles << 20);
     w.dz1h = (__half*)take((size_t)tiles << 16);
+    w.a1_dump = (__half*)take((size_t)tiles * 8 * 65536);      // ReLU(conv1) as the forward writes it (64 KB per 16 positions)
     w.zero_from = off;
     w.a1_boards = (__half*)take((size_t)groups * 51200);
     w.dz2_boards = (__half*)take((size_t)groups * 102400);
@@ -300,13 +322,14 @@ size_t train_workspace_bytes(long long n) { return n > 0 ? carve(nullptr, n).tot
 namespace {
 struct SideStream {
     cudaStream_t st = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, join2 = nullptr;
     int init() {
         if (st) return 0;
         CDQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CDQ_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         CDQ_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         CDQ_CUDA(cudaEventCreateWithFlags(&mid, cudaEventDisableTiming));
+        CDQ_CUDA(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
         return 0;
     }
 };
@@ -341,12 +364,19 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     const bool zero_in_pack = (loss_kind_flags & CDQ_TRAIN_REPACK) && (loss_kind_flags & CDQ_TRAIN_ZERO_LOSS);
     if ((loss_kind_flags & CDQ_TRAIN_ZERO_LOSS) && !zero_in_pack) CDQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st, zero_in_pack ? loss : nullptr))) return e;
-    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_boards, online_sms))) return e;
+    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_dump, online_sms))) return e;
     // ReLU(conv2)'s bit mask for the fc1 data gradient: side stream, after the target forward, under the online fc head
     CDQ_CUDA(cudaEventRecord(g_side.mid, st));
     CDQ_CUDA(cudaStreamWaitEvent(side, g_side.mid, 0));
     if ((e = launch_relu_mask(ws.act2_tiles, n, ws.relu_mask, side))) return e;
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
+    {   // ReLU(conv1) boards for conv2's backward: after the join the head waits for, needed only by conv2_bwd2
+        ProfileScope ps(KK_TRAIN, side);
+        const long long tiles16 = ((n + 127) >> 7) * 8;
+        a1_boards_kernel<<<(unsigned)(tiles16 * 32), 128, 0, side>>>(reinterpret_cast<const uint4*>(ws.a1_dump), reinterpret_cast<uint4*>(ws.a1_boards));
+        count_launch();
+    }
+    CDQ_CUDA(cudaEventRecord(g_side.join2, side));
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // ---- loss, tanh, fc2, fc1 bias
@@ -365,6 +395,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, side))) return e;
     CDQ_CUDA(cudaEventRecord(g_side.join, side));
     if ((e = launch_fc1_dgrad(ws.dz1h, ws.relu_mask, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
+    CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join2, 0));
     if ((e = launch_conv2_bwd(ws.dz2_boards, ws.a1_boards, net->p.w2tp, n, 1.f / scale, (float*)g.conv2_w, (float*)g.conv2_b,
                               ws.dz1c, ws.sched, st))) return e;
     {
