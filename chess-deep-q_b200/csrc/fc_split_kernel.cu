@@ -8,8 +8,8 @@
 // cluster of four CTAs:
 //   * CTA r contracts squares 16 r .. 16 r + 15 (768 KB of operands, 64 UMMAs of M = 128, N = 256, K = 16)
 //     into its own TMEM accumulator;
-//   * every CTA parks its 128 x 256 fp32 partial sums in its shared memory (the operand ring is dead by then),
-//     column-major, so that a warp reads 128 contiguous bytes per column;
+//   * every CTA parks its 128 x 256 fp32 partial sums in its shared memory (the operand ring is dead by then) as
+//     [4-column group][row][4 columns]: a warp reads 512 contiguous bytes per group, 16 bytes per lane;
 //   * after a cluster barrier CTA r owns fc1 outputs 64 r .. 64 r + 63: it adds the four partial sums through
 //     distributed shared memory (always in rank order 0, 1, 2, 3, so the bits do not depend on who adds),
 //     applies bias + ReLU, optionally keeps ReLU(fc1) for the backward pass, and reduces its slice of the fc2
@@ -54,6 +54,11 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_
 __device__ __forceinline__ float dsmem_ld(uint32_t addr) {
     float v;
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
@@ -134,7 +139,9 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j++) part[(c * 32 + j) * 128 + row] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; j += 4)
+                reinterpret_cast<float4*>(part)[((c * 32 + j) >> 2) * 128 + row] =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
         tc_fence_before();
     }
@@ -146,7 +153,7 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
         const long long pos = (tile << 7) + row;
         uint32_t pbase[FS_SPLIT];
 #pragma unroll
-        for (int k = 0; k < FS_SPLIT; k++) pbase[k] = dsmem_addr(smem_u32(part), (uint32_t)k) + (uint32_t)row * 4u;
+        for (int k = 0; k < FS_SPLIT; k++) pbase[k] = dsmem_addr(smem_u32(part), (uint32_t)k) + (uint32_t)row * 16u;
         float dot = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 8) {
@@ -154,7 +161,10 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
 #pragma unroll
             for (int k = 0; k < FS_SPLIT; k++)
 #pragma unroll
-                for (int j = 0; j < 8; j++) p[k][j] = dsmem_ld(pbase[k] + (uint32_t)(((int)rank * 64 + c0 + j) * 128 * 4));
+                for (int j = 0; j < 8; j += 4) {
+                    const float4 t4 = dsmem_ld4(pbase[k] + (uint32_t)((((int)rank * 64 + c0 + j) >> 2) * 128 * 16));
+                    p[k][j] = t4.x; p[k][j + 1] = t4.y; p[k][j + 2] = t4.z; p[k][j + 3] = t4.w;
+                }
             float h[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
