@@ -13,8 +13,10 @@
 //                     item per CTA the kernel's time was the latency chain of a single item -- 512 KB of W1^T
 //                     through a two-stage ring -- whatever the batch size)
 //                     dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq], written (still
-//                     scaled, fp16) straight into the zero-bordered boards conv_bwd2_kernel.cu consumes
-//                     M = 128 positions, N = 256 (4 squares), K = 256; W1^T tiles streamed by bulk copies
+//                     scaled, fp16) as the zero-bordered board blocks conv_bwd2_kernel.cu consumes
+//                     M = 128 positions, N = 256 (the 8 squares of one board rank x 32 channels), K = 256; W1^T tiles
+//                     streamed by bulk copies, the masked chunk leaves as 128 bulk copies of 640 bytes
+//  relu_mask_kernel   one bit per ReLU(conv2) output for the above (side stream, under the fc forward)
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
 //                     M = 2 x 128 outputs, N = 128 (16 squares x 8 channels), K = positions (split over CTAs)
 #include <cstdlib>
@@ -100,7 +102,7 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
     for (int i = tid; i < DG_OUT_BYTES / 16; i += DG_THREADS) reinterpret_cast<uint4*>(smem + DG_OFF_OUT)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     __syncthreads();
-    const long long n_chunks = ((n + 127) >> 7) * 16;   // (position tile, one of its 16 chunks of 256 columns = 4 squares)
+    const long long n_chunks = ((n + 127) >> 7) * 16;   // (position tile, one of its 16 chunks of 256 columns = one rank x one half of the channels)
     const long long g_lo = n_chunks * blockIdx.x / gridDim.x, g_hi = n_chunks * (blockIdx.x + 1) / gridDim.x;
     constexpr uint32_t IDESC = make_idesc_f16(128, 256);
 
