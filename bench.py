@@ -10,8 +10,13 @@ Under torchrun every rank evaluates its own 1M positions (weak scaling, no data-
   value       whole-job positions/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e         same metric through LeafEvaluator.evaluate_host: pinned HOST buffers in, host out
   roofline    dominant kernel: algorithmic FLOP per launch / mean launch time (CUDA events on the
-              launching stream, recorded inside the timed region) vs MEASURED_PEAKS.json
+              launching stream, recorded in a second pass of the same K steps) vs MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle port (C eval on all cores + torch-CPU fp32 CNN) on a bounded sample
+  cpu_baseline_python  the reference's Python path (evaluation.py's work in CPython + batch-1 torch-CPU CNN)
+  gpu_baseline  the reference's own module in torch-eager on the same B200 (fp32 and bf16 autocast), forward at
+              B = 1 ... 1M and DQNAgent.train()'s maths at B = 4 096, next to this repo's path at the same batch
+  dqn         second metric: the replay step as one CUDA graph (device-resident), .e2e = DQNAgent.train() from the
+              replay memory, .reference = torch-CPU, .parity = gradient-level data-parallel parity at world > 1
 --impl reference times that CPU port as the reference arm (the reference itself is Python over
 python-chess, which is not installable here).
 """
@@ -112,6 +117,171 @@ def cpu_port_throughput(n_sample, steps=1, passes=1):
     return n_sample * passes / mean, mean, os.cpu_count(), torch.get_num_threads()
 
 
+def reference_network_class():
+    """The reference's ChessQNetwork re-declared from its four nn layers (neural_network.py:16-37): the same
+    module torch would build from the reference file, which cannot travel to the GPU box."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class RefChessQNetwork(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(12, 32, kernel_size=3, padding=1)
+            self.conv2 = nn.Conv2d(32, 64, kernel_size=3, padding=1)
+            self.fc1 = nn.Linear(64 * 8 * 8, 256)
+            self.fc2 = nn.Linear(256, 1)
+
+        def forward(self, x):
+            x = F.relu(self.conv1(x))
+            x = F.relu(self.conv2(x))
+            x = x.view(-1, 64 * 8 * 8)
+            x = F.relu(self.fc1(x))
+            return self.fc2(x).tanh()
+
+    return RefChessQNetwork
+
+
+def _event_time_ms(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gpu_baseline(cdq, L, ev, net, boards, rew, dn):
+    """The reference's only GPU implementation -- its own module in torch-eager (cuDNN / cuBLAS) -- on THIS B200
+    (BASELINE.md 3.3-3.4): forward at B = 1 / 8 / 64 / 512 / 4 096 / 1 M in fp32 (torch defaults:
+    TF32 convolutions) and under bf16 autocast, inputs already on the device; the per-leaf call exactly as
+    mcts.py:216-219 makes it (host tensor -> .to(device) -> forward -> .item()); and DQNAgent.train()'s maths
+    (neural_network.py:232-246: two forwards, MSE, backward, torch.optim.Adam) at B = 4 096.  Next to each,
+    this repo's path at the same batch (cdq_leaf_eval = evaluation kernel + CNN; GraphedDQNStep)."""
+    import torch
+    import torch.nn.functional as F
+    Ref = reference_network_class()
+    ref = Ref().cuda()
+    ref.load_state_dict(net.state_dict())
+    tgt = Ref().cuda()
+    tgt.load_state_dict(net.state_dict())
+    rows = []
+    sizes = (1, 8, 64, 512, 4096, min(1 << 20, boards.shape[0]))
+    planes_all = cdq.boards_to_tensor_batch(boards[:sizes[-1]])
+    for B in sizes:
+        x = planes_all[:B]
+        iters = 200 if B <= 512 else 50 if B <= 4096 else 3
+        row = {"batch": B}
+        with torch.no_grad():
+            ms = _event_time_ms(lambda: ref(x), iters)
+            row["eager_fp32_us"] = ms * 1e3
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ms16 = _event_time_ms(lambda: ref(x), iters)
+            row["eager_bf16_autocast_us"] = ms16 * 1e3
+        b = boards[:B].contiguous()
+        ours = _event_time_ms(lambda: ev.evaluate_device(b), iters)
+        row["cdq_leaf_eval_us"] = ours * 1e3
+        row["eager_fp32_positions_per_s"] = B / (ms * 1e-3)
+        row["eager_bf16_positions_per_s"] = B / (ms16 * 1e-3)
+        row["cdq_positions_per_s"] = B / (ours * 1e-3)
+        row["speedup_vs_eager_fp32"] = ms / ours
+        row["speedup_vs_eager_bf16"] = ms16 / ours
+        rows.append(row)
+    del planes_all
+    # the per-leaf call of the reference's search (mcts.py:216-219), wall clock, one leaf at a time
+    host_x = cdq.boards_to_tensor_batch(boards[:1]).cpu()
+    with torch.no_grad():
+        for _ in range(20):
+            ref(host_x.to("cuda")).item()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            ref(host_x.to("cuda")).item()
+        per_leaf_us = (time.perf_counter() - t0) / 300 * 1e6
+    # DQNAgent.train()'s maths in torch-eager at B = 4 096
+    B = 4096
+    s_pl = cdq.boards_to_tensor_batch(boards[:B])
+    ns_pl = cdq.boards_to_tensor_batch(boards[1:B + 1])
+    r, d = rew[:B].contiguous(), dn[:B].contiguous()
+    train = {}
+    for mode in ("fp32", "bf16_autocast"):
+        ref.load_state_dict(net.state_dict())
+        opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                q = ref(s_pl).squeeze()
+                qn = tgt(ns_pl).squeeze().detach()
+                loss = F.mse_loss(q.float(), r + (1 - d) * 0.99 * qn.float())
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        ms = _event_time_ms(step, 30, warm=5)
+        train[mode] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3)}
+    return {"what": "reference ChessQNetwork / DQNAgent.train maths in torch-eager (cuDNN/cuBLAS) on the same B200, "
+                    "CUDA-event timed, inputs resident on the device",
+            "torch": torch.__version__, "forward": rows,
+            "per_leaf_call_as_mcts_py_216_219_us": per_leaf_us,
+            "per_leaf_call_positions_per_s": 1e6 / per_leaf_us,
+            "dqn_train_b4096": train}
+
+
+def python_path_baseline(n_single=1024, per_core=1024):
+    """the reference's Python path (evaluation.py's work in CPython over the restated
+    python-chess API + ChessQNetwork on torch-CPU at batch 1, mcts.py:216-219) on this box's host cores:
+    one process, then one process per core.  oracle/py_eval.py is the restatement (pinned bit for bit to the
+    reference's own scores in tests/test_oracle.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import py_eval
+    cores = os.cpu_count() or 1
+    params = O.init_params(42, 2.0)
+    boards = O.playouts(max(n_single, per_core * cores), seed=42)
+    v1, s1, _ = py_eval.python_path_throughput(boards[:n_single], params, processes=1)
+    vN, sN, _ = py_eval.python_path_throughput(boards[:per_core * cores], params, processes=cores)
+    e1, es1, _ = py_eval.python_path_throughput(boards[:n_single], None, processes=1)
+    return {"value": vN, "unit": UNIT, "cores": cores, "kind": "port",
+            "what": "Python path: evaluation.py's work in CPython over the restated python-chess API + torch-CPU fp32 CNN at batch 1",
+            "sample": "%d positions on %d processes, %.1f s" % (per_core * cores, cores, sN),
+            "single_process": {"value": v1, "sample": "%d positions, %.1f s" % (n_single, s1)},
+            "single_process_eval_only": {"value": e1, "sample": "%d positions, %.1f s" % (n_single, es1)}}
+
+
+def dqn_cpu_reference(steps=2, B=4096):
+    """DQNAgent.train()'s maths (neural_network.py:232-246) on torch-CPU fp32 with the reference module
+    re-declared from its layers: samples/s on this box's host cores."""
+    import torch
+    import torch.nn.functional as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    Ref = reference_network_class()
+    torch.manual_seed(42)
+    q, t = Ref(), Ref()
+    t.load_state_dict(q.state_dict())
+    opt = torch.optim.Adam(q.parameters(), lr=1e-3)
+    s = (torch.rand(B, 12, 8, 8) < 0.04).float()
+    ns = (torch.rand(B, 12, 8, 8) < 0.04).float()
+    r, d = torch.randn(B) * 0.01, (torch.rand(B) < 0.05).float()
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        cur = q(s).squeeze()
+        nxt = t(ns).squeeze().detach()
+        loss = F.mse_loss(cur, r + (1 - d) * 0.99 * nxt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        loss.item()
+        if i:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": B / sec, "unit": "samples/s", "ms_per_step": sec * 1e3, "cores": os.cpu_count(),
+            "torch_threads": torch.get_num_threads(), "kind": "reference maths on torch-CPU fp32, batch %d, %d steps" % (B, steps)}
+
+
 def workload_config(n):
     """The workload both arms are quoted on (BASELINE configs[1] at the default size)."""
     return {"workload": "BASELINE configs[1]: %d random-playout positions per GPU per step, "
@@ -137,7 +307,7 @@ def run_reference(args):
                              "sample": "%d positions/step: C oracle eval on %d threads + torch-CPU fp32 CNN (%d threads)"
                                        % (n_sample, cores, tthreads)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "cpu_baseline_python": python_path_baseline(), "dqn": {"reference": dqn_cpu_reference()}}
     print(json.dumps(line))
 
 
@@ -202,6 +372,7 @@ def main():
     ap.add_argument("--cpu-passes", type=int, default=10, help="passes over the CPU sample (about 10-15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dqn", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE configs[4]: device-resident throughput for 4K..16M positions per GPU (one JSON line)")
     args = ap.parse_args()
@@ -250,10 +421,9 @@ def main():
     if dist:
         dist.barrier()
 
-    # ---- timed region: K steps, device-timed, per-kernel events recorded inside it
+    # ---- timed region: K steps, device-timed, NOTHING else recorded inside it
     sampler = ClockSampler(local)
     sampler.start()
-    L.cdq_profile_enable(1)
     launches0 = L.cdq_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -266,7 +436,17 @@ def main():
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     launches = L.cdq_launch_count() - launches0
+    # ---- the same K steps once more with an event pair around every launch: per-kernel durations for the
+    #      roofline (kept out of the timed region: two event records per launch cost about 1 % there)
+    L.cdq_profile_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        out = step()
+    p1.record()
+    torch.cuda.synchronize()
     L.cdq_profile_enable(0)
+    ms_profiled = p0.elapsed_time(p1)
     kms = (cdq._lib.ctypes.c_double * 8)()
     kcnt = (cdq._lib.ctypes.c_uint64 * 8)()
     cdq._lib.check(L.cdq_profile_collect(kms, kcnt))
@@ -339,6 +519,7 @@ def main():
         dloss = gstep.global_loss()
         dqn = {"metric": "DQN samples/sec", "value": B * dsteps / (dms * 1e-3), "unit": "samples/s", "global_batch": B,
                "ms_per_step": dms / dsteps, "scaling": "strong", "loss": float(dloss.item()),
+               "tensor_bound_frac": (19154944.0 * B / world) / (dms / dsteps * 1e-3) / 1e12 / measured_peaks()["tflops"],
                "parallelism": ("dp%d: one CUDA graph per rank; gradients reduce-scattered, Adam and parameter all-gather "
                                "in one kernel over NVLink peer memory" % world) if world > 1 else
                               "single GPU, whole step as one CUDA graph"}
@@ -346,6 +527,50 @@ def main():
             if dist:
                 dist.barrier()
             opt.region.close()
+        if world > 1:
+            # data-parallel parity AT THIS WORLD SIZE, gradient level (lr = 0), even and uneven global batch
+            from chess_deep_q_b200.train import dp_parity_report
+            parity = []
+            for nb in (4096, 4099):
+                fb = torch.empty((nb + 1, 9), dtype=torch.int64, device="cuda")
+                cdq._lib.check(L.cdq_random_playouts(fb.data_ptr(), nb + 1, 777, 199, cdq._lib.stream_ptr()))   # same boards on every rank
+                fsc, ffl = cdq.evaluate_batch(fb[1:])
+                frew, fdn = (0.01 * torch.tanh(fsc / 10.0)).float(), ((ffl & 7) != 0).float()
+                base_sd = {k: v.detach().clone() for k, v in tgt.state_dict().items()}
+
+                def make_net():
+                    a, b = cdq.ChessQNetwork().cuda(), cdq.ChessQNetwork().cuda()
+                    a.load_state_dict(base_sd)
+                    b.load_state_dict(base_sd)
+                    return a, b
+                parity.append(dp_parity_report(make_net, fb[:nb].contiguous(), fb[1:].contiguous(), frew, fdn))
+            dqn["parity"] = {"ok": all(r["ok"] for r in parity), "max_rel": max(r["max_rel_vs_shard_sum"] for r in parity),
+                             "reports": parity}
+        elif n >= 10001:
+            # the path a user calls: DQNAgent.train() -- random.sample from the replay memory, gather into pinned
+            # staging, H2D, the graphed step, the loss back as a Python float (neural_network.py:218-252)
+            import random
+            random.seed(42)
+            agent = cdq.DQNAgent(batch_size=B)
+            agent.q_network.load_state_dict(tgt.state_dict())
+            agent.update_target_network()
+            hb = boards[:10001].cpu().numpy().view(np.uint64).reshape(-1).view(cdq.BOARD_DTYPE)
+            hsc, hfl = cdq.evaluate_batch(boards[1:10001])
+            hrew = (0.01 * torch.tanh(hsc / 10.0)).float().cpu().numpy()
+            hdn = ((hfl & 7) != 0).cpu().numpy()
+            for i in range(10000):
+                agent.memory.append((hb[i], None, float(hrew[i]), hb[i + 1], float(hdn[i])))
+            for _ in range(3):
+                agent.train()
+            t0 = time.perf_counter()
+            esteps = 50
+            for _ in range(esteps):
+                eloss = agent.train()
+            esec = time.perf_counter() - t0
+            dqn["e2e"] = {"value": B * esteps / esec, "unit": "samples/s", "ms_per_step": esec / esteps * 1e3,
+                          "h2d_bytes_per_step": B * (72 * 2 + 8), "d2h_bytes_per_step": 4, "loss": eloss,
+                          "what": "DQNAgent.train(): random.sample -> pinned staging -> H2D -> graphed step -> loss float"}
+            del agent
 
     if rank != 0:
         if dist:
@@ -376,19 +601,34 @@ def main():
                 "eval_kernel_hbm": {"achieved_GBps": n * args.steps * 84 / (kms[0] * 1e-3) / 1e9 if kms[0] else None,
                                     "peak_GBps": peaks["hbm"], "note": "84 B/position; integer-issue bound"}}
 
-    cpu = None
+    gpu_base = None
+    if not args.no_gpu_baseline and world == 1 and n >= 16384:
+        bsc, bfl = cdq.evaluate_batch(boards[1:4097])
+        gpu_base = gpu_baseline(cdq, L, ev, net, boards, (0.01 * torch.tanh(bsc / 10.0)).float(), ((bfl & 7) != 0).float())
+        if dqn:
+            gpu_base["dqn_train_b4096"]["cdq_graphed_step_ms"] = dqn["ms_per_step"]
+            for mode in ("fp32", "bf16_autocast"):
+                gpu_base["dqn_train_b4096"][mode]["speedup_of_cdq"] = gpu_base["dqn_train_b4096"][mode]["ms_per_step"] / dqn["ms_per_step"]
+
+    cpu = cpu_py = None
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
         v, sec, cores, tthreads = cpu_port_throughput(args.cpu_sample, passes=args.cpu_passes)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d passes over %d random-playout positions: C oracle eval on %d threads + torch-CPU fp32 CNN "
                          "(%d threads), %.1f s" % (args.cpu_passes, args.cpu_sample, cores, tthreads, sec)}
+        cpu_py = python_path_baseline()
+        if dqn:
+            dqn["reference"] = dqn_cpu_reference()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bitboards + f64 score; fp16 operands / fp32 accumulate CNN", "data": "synthetic",
             "config": workload_config(n),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * H2D_PER_POS, "d2h_bytes_per_step": n * D2H_PER_POS},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dqn": dqn}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "cpu_baseline_python": cpu_py, "gpu_baseline": gpu_base, "dqn": dqn,
+            "profiled_pass": {"ms_per_step": ms_profiled / args.steps,
+                              "note": "per-kernel event pairs are recorded in a second pass of the same K steps, not in the timed region"}}
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

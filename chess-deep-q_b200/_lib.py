@@ -13,6 +13,8 @@ c_void_p, c_int64, c_int, c_uint64, c_size_t = (ctypes.c_void_p, ctypes.c_int64,
 SIGNATURES = {
     "cdq_version": (c_int, []),
     "cdq_error_string": (ctypes.c_char_p, [c_int]),
+    "cdq_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "cdq_get_option": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int)]),
     "cdq_eval_terms": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cdq_attack_maps": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "cdq_encode_planes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
@@ -24,13 +26,18 @@ SIGNATURES = {
     "cdq_leaf_eval": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "cdq_leaf_eval_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cdq_host_ctx_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "cdq_host_ctx_destroy": (None, [c_void_p]),
+    "cdq_leaf_eval_host_ctx": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "cdq_host_release": (None, []),
     "cdq_train_workspace_bytes": (c_size_t, [c_int64]),
     "cdq_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                  ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  ctypes.c_double, ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdq_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.c_float, ctypes.c_float,
                               ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
     "cdq_dp_adam_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_float,
                                  ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
+    "cdq_dp_adam_status": (c_int, [c_void_p, c_void_p]),
     "cdq_ipc_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
     "cdq_ipc_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "cdq_ipc_close": (c_int, [c_void_p]),
@@ -80,6 +87,14 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def set_option(name, value):
+    """cdq_set_option: run-time switch (see include/cdq.h); returns the previous value."""
+    old = c_int()
+    check(lib().cdq_get_option(name.encode(), ctypes.byref(old)))
+    check(lib().cdq_set_option(name.encode(), int(value)))
+    return old.value
 
 
 def check(code):

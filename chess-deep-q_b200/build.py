@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcdq.so")
-SOURCES = ["abi.cu", "eval_kernel.cu", "playout_kernel.cu", "conv_kernel.cu", "conv_stream_kernel.cu", "pipe_kernel.cu", "fc_kernel.cu", "fc_split_kernel.cu", "fc_bwd_kernel.cu", "conv_bwd2_kernel.cu", "train_kernels.cu", "dp_adam_kernel.cu"]
+SOURCES = ["abi.cu", "eval_kernel.cu", "playout_kernel.cu", "conv_stream_kernel.cu", "pipe_kernel.cu", "fc_kernel.cu", "fc_split_kernel.cu", "fc_bwd_kernel.cu", "conv_bwd2_kernel.cu", "train_kernels.cu", "dp_adam_kernel.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v", "-diag-suppress", "177",

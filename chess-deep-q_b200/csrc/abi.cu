@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -34,25 +35,70 @@ ProfileScope::~ProfileScope() {
 constexpr long long FWD_CHUNK = 148 * 8 * 128;      // 148 SMs x 4 pairs of fc tiles = 148 x 64 conv tiles
 static inline long long tiles_of(long long n) { return (n + 127) / 128; }
 
-// With CDQ_PIPE=1, batches of at least this many positions go through the conv -> fc pipe kernel (one
-// launch, act2 stays in L2: 90 MB instead of 17 GB of DRAM traffic per 1M positions).  It is opt-in: under
+// With option "pipe" = 1 (CDQ_PIPE=1), batches of at least this many positions go through the conv -> fc pipe kernel
+// (one launch, act2 stays in L2: 90 MB instead of 17 GB of DRAM traffic per 1M positions).  It is opt-in: under
 // the board's power cap it is only 1-2 % faster than the two stand-alone kernels, and its persisting-L2
 // set-aside slows down the chunked host path that runs next to it (profiles/README.md, "pipe kernel").
 constexpr long long PIPE_MIN_POSITIONS = 512 * 1024;   // measured break-even is about 256 K (profiles/README.md)
-static bool pipe_enabled() {      // read on every call so that one process can A/B the two paths
-    const char* e = getenv("CDQ_PIPE");
-    return e && e[0] == '1';
+
+// ---- run-time switches: read from the environment once, changed afterwards only through cdq_set_option
+static std::atomic<int> g_opt[OPT_COUNT];
+static std::once_flag g_opt_once;
+static const char* const OPT_NAME[OPT_COUNT] = {"pipe", "fc_split", "host_ramp", "dp_timeout_s"};
+static const char* const OPT_ENV[OPT_COUNT] = {"CDQ_PIPE", "CDQ_FC_SPLIT", "CDQ_HOST_RAMP", "CDQ_DP_TIMEOUT_S"};
+static const int OPT_DEFAULT[OPT_COUNT] = {0, 1, 1, 600};
+static void init_options() {
+    std::call_once(g_opt_once, [] {
+        for (int k = 0; k < OPT_COUNT; k++) {
+            const char* e = getenv(OPT_ENV[k]);
+            g_opt[k].store(e && e[0] ? atoi(e) : OPT_DEFAULT[k], std::memory_order_relaxed);
+        }
+    });
+}
+int option(int which) {
+    init_options();
+    return g_opt[which].load(std::memory_order_relaxed);
 }
 
-static int check_device() {
-    static int state = 0; // 0 unknown, 1 ok, <0 error
-    if (state == 0) {
-        int dev = 0, major = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); state = CDQ_E_NODEVICE; return state; }
-        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-        state = (major == 10) ? 1 : CDQ_E_NODEVICE;
+// ---- per-device state
+namespace {
+struct DeviceState {
+    std::mutex mu;
+    unsigned once_mask = 0;
+    std::atomic<int> sms{0};
+    std::atomic<int> arch{0};       // 0 unknown, 1 sm_100, -1 anything else
+};
+DeviceState g_dev[MAX_DEVICES];
+} // namespace
+int current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev >= 0 && dev < MAX_DEVICES ? dev : -1;
+}
+std::mutex& device_mutex(int dev) { return g_dev[dev].mu; }
+unsigned& device_once_mask(int dev) { return g_dev[dev].once_mask; }
+int device_sm_count() {
+    const int dev = current_device();
+    if (dev < 0) return 0;
+    int sms = g_dev[dev].sms.load(std::memory_order_relaxed);
+    if (!sms) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        g_dev[dev].sms.store(sms, std::memory_order_relaxed);
     }
-    return state == 1 ? 0 : state;
+    return sms;
+}
+// the CURRENT device of the calling thread must be an sm_100 part; checked once per device
+static int check_device() {
+    const int dev = current_device();
+    if (dev < 0) return CDQ_E_NODEVICE;
+    int a = g_dev[dev].arch.load(std::memory_order_relaxed);
+    if (a == 0) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        a = major == 10 ? 1 : -1;
+        g_dev[dev].arch.store(a, std::memory_order_relaxed);
+    }
+    return a == 1 ? 0 : CDQ_E_NODEVICE;
 }
 } // namespace cdq
 
@@ -69,11 +115,27 @@ const char* cdq_error_string(int code) {
         case CDQ_E_NODEVICE: return "cdq: no sm_100 CUDA device (this library has no CPU fallback)";
         case CDQ_E_WORKSPACE: return "cdq: workspace too small (see cdq_workspace_bytes)";
         case CDQ_E_BADBOARD: return "cdq: malformed board record";
+        case CDQ_E_TIMEOUT: return "cdq: a data-parallel peer did not reach the optimizer step within the time limit";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "cdq: unknown error";
     }
 }
 
 uint64_t cdq_launch_count(void) { return g_launches.load(); }
+
+int cdq_set_option(const char* name, int value) {
+    if (!name) return CDQ_E_BADARG;
+    init_options();
+    for (int k = 0; k < OPT_COUNT; k++)
+        if (!strcmp(name, OPT_NAME[k])) { g_opt[k].store(value); return 0; }
+    return CDQ_E_BADARG;
+}
+int cdq_get_option(const char* name, int* value) {
+    if (!name || !value) return CDQ_E_BADARG;
+    init_options();
+    for (int k = 0; k < OPT_COUNT; k++)
+        if (!strcmp(name, OPT_NAME[k])) { *value = g_opt[k].load(); return 0; }
+    return CDQ_E_BADARG;
+}
 
 void cdq_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 
@@ -223,7 +285,7 @@ static int forward_chunks(const CdqNet* net, const CdqBoard* d_boards, int64_t n
     if (ws_bytes < cdq_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if ((uintptr_t)ws & 15) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
-    if (n >= PIPE_MIN_POSITIONS && !dbg_act1 && pipe_enabled())
+    if (n >= PIPE_MIN_POSITIONS && !dbg_act1 && option(OPT_PIPE) == 1)
         return launch_leaf_pipe(d_boards, n, net->p, d_value, d_flags, d_leaf, ws, st);
     release_persisting_l2();
     for (int64_t off = 0; off < n; off += FWD_CHUNK) {
@@ -247,6 +309,13 @@ int cdq_value_fwd(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float*
 int cdq_leaf_eval(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float* d_leaf, double* d_score,
                   uint32_t* d_flags, float* d_value_raw, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (n > 0 && (!d_leaf || !d_flags)) return CDQ_E_BADARG;
+    if (!net) {
+        // no network: _evaluate_position's heuristic branch, tanh(fast_evaluate_position(board) / 10) behind the
+        // terminal rules (mcts.py:202-210, 226-229) -- one launch of the evaluation kernel, no workspace
+        if (n < 0 || (n > 0 && !d_boards) || d_value_raw) return CDQ_E_BADARG;
+        if (int e = check_device()) return e;
+        return launch_eval_terms(d_boards, n, 0, nullptr, d_score, d_flags, (cudaStream_t)stream, d_leaf);
+    }
     if (int e = cdq_eval_terms(d_boards, n, 0, nullptr, d_score, d_flags, stream)) return e;
     return forward_chunks(net, d_boards, n, d_value_raw, d_flags, d_leaf, d_workspace, workspace_bytes, nullptr,
                           (cudaStream_t)stream);
@@ -265,16 +334,18 @@ size_t cdq_train_workspace_bytes(int64_t n) { return train_workspace_bytes(n); }
 
 int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
                       const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,
-                      const float* d_done, int64_t n, float gamma, int loss_kind, const CdqWeights* d_grads,
+                      const float* d_done, int64_t n, double mean_over, float gamma, int loss_kind, const CdqWeights* d_grads,
                       float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream) {
-    if (!net || !target_net || !net->loaded || !target_net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 ||
-        !d_states || !d_next_states || !d_reward || !d_done || !d_workspace ||
-        ((loss_kind & 0xff) != 0 && (loss_kind & 0xff) != 1) || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT | CDQ_TRAIN_REPACK | CDQ_TRAIN_ZERO_LOSS)))
+    const bool upstream = (loss_kind & 0xff) == CDQ_LOSS_UPSTREAM;      // no target network, no next states, no done flags
+    if (!net || !net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 || !d_states || !d_reward || !d_workspace ||
+        (!upstream && (!target_net || !target_net->loaded || !d_next_states || !d_done)) ||
+        (loss_kind & 0xff) > CDQ_LOSS_UPSTREAM || (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT | CDQ_TRAIN_REPACK | CDQ_TRAIN_ZERO_LOSS)))
         return CDQ_E_BADARG;
     if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
     if (int e = check_device()) return e;
     release_persisting_l2();
-    return train_fwd_bwd(net, target_net, *d_weights, d_states, d_next_states, d_reward, d_done, n, gamma, loss_kind,
+    return train_fwd_bwd(net, target_net, *d_weights, d_states, d_next_states, d_reward, d_done, n,
+                         mean_over > 0.0 ? mean_over : (double)n, gamma, loss_kind,
                          *d_grads, d_loss, d_workspace, (cudaStream_t)stream);
 }
 
@@ -286,20 +357,24 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
 }
 
 // ------------------------------------------------------------------ host-buffer path (e2e)
-namespace {
-struct HostPath {
+// A CdqHostCtx owns two streams and two sets of device buffers on the device that was current when it was
+// created; cdq_leaf_eval_host_ctx double-buffers chunks through them.  One call at a time per context (the
+// context's mutex serialises callers that share one); independent callers create their own contexts and run
+// concurrently.  cdq_leaf_eval_host keeps one lazily created context per device for callers that do not manage one.
+struct CdqHostCtx {
     static constexpr long long CHUNK = 2 * FWD_CHUNK;       // two forward chunks
     std::mutex mu;
-    bool ready = false;
-    cudaStream_t st[2];
-    CdqBoard* boards[2];
-    float* leaf[2];
-    double* score[2];
-    uint32_t* flags[2];
-    void* ws[2];
+    int dev = -1;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    CdqBoard* boards[2] = {nullptr, nullptr};
+    float* leaf[2] = {nullptr, nullptr};
+    double* score[2] = {nullptr, nullptr};
+    uint32_t* flags[2] = {nullptr, nullptr};
+    void* ws[2] = {nullptr, nullptr};
     size_t ws_bytes = 0;
     int init() {
-        if (ready) return 0;
+        dev = current_device();
+        if (dev < 0) return CDQ_E_NODEVICE;
         ws_bytes = cdq_workspace_bytes(CHUNK);
         for (int i = 0; i < 2; i++) {
             CDQ_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
@@ -309,41 +384,91 @@ struct HostPath {
             CDQ_CUDA(cudaMalloc(&flags[i], CHUNK * 4));
             CDQ_CUDA(cudaMalloc(&ws[i], ws_bytes));
         }
-        ready = true;
         return 0;
     }
+    void release() {
+        for (int i = 0; i < 2; i++) {
+            if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+            cudaFree(boards[i]); cudaFree(leaf[i]); cudaFree(score[i]); cudaFree(flags[i]); cudaFree(ws[i]);
+        }
+    }
 };
-HostPath g_host;
+
+int cdq_host_ctx_create(CdqHostCtx** out) {
+    if (!out) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    CdqHostCtx* c = new CdqHostCtx();
+    if (int e = c->init()) { c->release(); delete c; return e; }
+    *out = c;
+    return 0;
+}
+
+void cdq_host_ctx_destroy(CdqHostCtx* ctx) {
+    if (!ctx) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (ctx->dev >= 0) cudaSetDevice(ctx->dev);
+    ctx->release();
+    if (prev >= 0) cudaSetDevice(prev);
+    delete ctx;
+}
+
+int cdq_leaf_eval_host_ctx(CdqHostCtx* ctx, const CdqNet* net, const CdqBoard* h_boards, int64_t n, float* h_leaf,
+                           double* h_score, uint32_t* h_flags) {
+    if (!ctx || n < 0 || (n > 0 && (!h_boards || !h_leaf))) return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    if (current_device() != ctx->dev) return CDQ_E_BADARG;     // the context's buffers live on another device
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    // Chunks ramp up (1/8, 1/4, 1/2 of the full chunk, then full chunks): the first chunk's host-to-device copy is
+    // the one transfer nothing can hide, so it is kept short; from then on copies run under the other stream's kernels.
+    const bool ramp = option(OPT_HOST_RAMP) != 0;              // 0: full chunks from the start (A/B)
+    int c_idx = 0;
+    for (int64_t off = 0; off < n; c_idx++) {
+        const int s = c_idx & 1;
+        const int64_t cap = c_idx < 3 && ramp ? CdqHostCtx::CHUNK >> (3 - c_idx) : CdqHostCtx::CHUNK;
+        const int64_t c = (n - off) < cap ? (n - off) : cap;
+        cudaStream_t st = ctx->st[s];
+        // the slot's previous use (two chunks ago) is ordered before this one by the stream itself
+        CDQ_CUDA(cudaMemcpyAsync(ctx->boards[s], h_boards + off, c * sizeof(CdqBoard), cudaMemcpyHostToDevice, st));
+        if (int e = cdq_leaf_eval(net, ctx->boards[s], c, ctx->leaf[s], h_score ? ctx->score[s] : nullptr, ctx->flags[s], nullptr,
+                                  ctx->ws[s], ctx->ws_bytes, st))
+            return e;
+        CDQ_CUDA(cudaMemcpyAsync(h_leaf + off, ctx->leaf[s], c * 4, cudaMemcpyDeviceToHost, st));
+        if (h_score) CDQ_CUDA(cudaMemcpyAsync(h_score + off, ctx->score[s], c * 8, cudaMemcpyDeviceToHost, st));
+        if (h_flags) CDQ_CUDA(cudaMemcpyAsync(h_flags + off, ctx->flags[s], c * 4, cudaMemcpyDeviceToHost, st));
+        off += c;
+    }
+    CDQ_CUDA(cudaStreamSynchronize(ctx->st[0]));
+    CDQ_CUDA(cudaStreamSynchronize(ctx->st[1]));
+    return 0;
+}
+
+namespace {
+std::mutex g_default_ctx_mu;
+CdqHostCtx* g_default_ctx[MAX_DEVICES];
 } // namespace
 
 int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n, float* h_leaf, double* h_score,
                        uint32_t* h_flags) {
-    if (!net || n < 0 || (n > 0 && (!h_boards || !h_leaf))) return CDQ_E_BADARG;
+    if (n < 0 || (n > 0 && (!h_boards || !h_leaf))) return CDQ_E_BADARG;
     if (int e = check_device()) return e;
-    std::lock_guard<std::mutex> lock(g_host.mu);
-    if (int e = g_host.init()) return e;
-    // Chunks ramp up (1/8, 1/4, 1/2 of the full chunk, then full chunks): the first chunk's host-to-device copy is
-    // the one transfer nothing can hide, so it is kept short; from then on copies run under the other stream's kernels.
-    int c_idx = 0;
-    for (int64_t off = 0; off < n; c_idx++) {
-        const int s = c_idx & 1;
-        const char* ramp = getenv("CDQ_HOST_RAMP");     // "0": full chunks from the start (A/B)
-        const int64_t cap = c_idx < 3 && !(ramp && ramp[0] == '0') ? HostPath::CHUNK >> (3 - c_idx) : HostPath::CHUNK;
-        const int64_t c = (n - off) < cap ? (n - off) : cap;
-        cudaStream_t st = g_host.st[s];
-        // the slot's previous use (two chunks ago) is ordered before this one by the stream itself
-        CDQ_CUDA(cudaMemcpyAsync(g_host.boards[s], h_boards + off, c * sizeof(CdqBoard), cudaMemcpyHostToDevice, st));
-        if (int e = cdq_leaf_eval(net, g_host.boards[s], c, g_host.leaf[s], g_host.score[s], g_host.flags[s], nullptr,
-                                  g_host.ws[s], g_host.ws_bytes, st))
-            return e;
-        CDQ_CUDA(cudaMemcpyAsync(h_leaf + off, g_host.leaf[s], c * 4, cudaMemcpyDeviceToHost, st));
-        if (h_score) CDQ_CUDA(cudaMemcpyAsync(h_score + off, g_host.score[s], c * 8, cudaMemcpyDeviceToHost, st));
-        if (h_flags) CDQ_CUDA(cudaMemcpyAsync(h_flags + off, g_host.flags[s], c * 4, cudaMemcpyDeviceToHost, st));
-        off += c;
+    const int dev = current_device();
+    CdqHostCtx* ctx;
+    {
+        std::lock_guard<std::mutex> l(g_default_ctx_mu);
+        if (!g_default_ctx[dev])
+            if (int e = cdq_host_ctx_create(&g_default_ctx[dev])) return e;
+        ctx = g_default_ctx[dev];
     }
-    CDQ_CUDA(cudaStreamSynchronize(g_host.st[0]));
-    CDQ_CUDA(cudaStreamSynchronize(g_host.st[1]));
-    return 0;
+    return cdq_leaf_eval_host_ctx(ctx, net, h_boards, n, h_leaf, h_score, h_flags);
+}
+
+void cdq_host_release(void) {
+    std::lock_guard<std::mutex> l(g_default_ctx_mu);
+    for (int d = 0; d < MAX_DEVICES; d++) {
+        cdq_host_ctx_destroy(g_default_ctx[d]);
+        g_default_ctx[d] = nullptr;
+    }
 }
 
 } // extern "C"

@@ -20,7 +20,6 @@ struct PackedNet {
     const float* fc2_b;
 };
 
-int device_sm_count();
 int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me = nullptr);   // fp32 parameters -> all of p
 int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream_t st);   // 1 bit per ReLU(conv2) output, dgrad's order
 int launch_fc1_dgrad(const __half* dz1h, const unsigned* relu_mask, const __half* fc1tp, long long n, __half* dz2_boards,
@@ -30,8 +29,6 @@ int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __
 int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float inv_scale, float* g_fc1_w, cudaStream_t st);
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                       cudaStream_t st, __half* act1_boards = nullptr, int max_ctas = 0);
-int launch_conv_stack_v1(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
-                         cudaStream_t st, __half* act1_boards);
 // conv stack + fc head as one persistent kernel with an L2-resident hand-over (pipe_kernel.cu)
 size_t pipe_workspace_bytes();
 void release_persisting_l2();   // undo the pipe kernel's L2 persistence window before other work
@@ -55,8 +52,8 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 struct CdqNet;
 namespace cdq {
 int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
-                  const CdqBoard* next_states, const float* reward, const float* done, long long n, float gamma,
-                  int loss_kind, const CdqWeights& g, float* loss, void* ws_base, cudaStream_t st);
+                  const CdqBoard* next_states, const float* reward, const float* done, long long n, double mean_over,
+                  float gamma, int loss_kind, const CdqWeights& g, float* loss, void* ws_base, cudaStream_t st);
 }
 
 // what the opaque C handle points to

@@ -2,9 +2,34 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <mutex>
 #include "../../include/cdq.h"
 
 namespace cdq {
+
+// ---- per-device state.  Nothing in the library assumes "the device that was current first": the SM count, the
+// one-time cudaFuncSetAttribute calls, the training side stream and the host-path buffers are all keyed by the
+// CURRENT device of the calling thread, so one process may drive several GPUs.
+constexpr int MAX_DEVICES = 64;
+int current_device();                 // cudaGetDevice; -1 without a device
+int device_sm_count();                // of the current device (cached per device)
+std::mutex& device_mutex(int dev);
+unsigned& device_once_mask(int dev);
+enum OnceSlot { ONCE_CONV_STREAM, ONCE_FC_PAIRS, ONCE_FC_SPLIT, ONCE_PIPE, ONCE_FC1_WGRAD, ONCE_FC1_DGRAD, ONCE_CONV2_BWD,
+                ONCE_CONV1_WGRAD, ONCE_TREE, ONCE_FWD2, ONCE_SPARE0, ONCE_SPARE1 };
+template <class F>
+inline void once_per_device(int slot, F&& f) {      // e.g. raising a kernel's dynamic shared memory limit
+    const int dev = current_device();
+    if (dev < 0) return;
+    std::lock_guard<std::mutex> l(device_mutex(dev));
+    unsigned& m = device_once_mask(dev);
+    if (!((m >> slot) & 1u)) { f(); m |= 1u << slot; }
+}
+
+// ---- run-time switches (cdq_set_option / cdq_get_option).  Each is initialised ONCE from its environment variable
+// when the library is first used; no call path reads the environment afterwards.
+enum Option { OPT_PIPE, OPT_FC_SPLIT, OPT_HOST_RAMP, OPT_DP_TIMEOUT_S, OPT_COUNT };
+int option(int which);
 
 // every kernel launch made by the library bumps this (bench.py reports it as gpu_launches)
 void count_launch(int k = 1);
@@ -28,7 +53,7 @@ struct ProfileScope {
 
 // launchers implemented in the .cu files
 int launch_eval_terms(const CdqBoard* boards, long long n, int ignore_checkmate, int* terms, double* score,
-                      unsigned* flags, cudaStream_t st);
+                      unsigned* flags, cudaStream_t st, float* heuristic_leaf = nullptr);
 int launch_attack_maps(const CdqBoard* boards, long long n, unsigned long long* maps, cudaStream_t st);
 int launch_encode_planes(const CdqBoard* boards, long long n, float* planes, cudaStream_t st);
 int launch_random_playouts(CdqBoard* boards, long long n, unsigned long long seed, int max_plies, cudaStream_t st);

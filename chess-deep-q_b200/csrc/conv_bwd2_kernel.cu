@@ -258,11 +258,7 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
 
 int launch_conv2_bwd(const __half* dz2_boards, const __half* a1_boards, const __half* w2tp, long long n, float inv_scale,
                      float* g_w2, float* g_b2, float* dz1c, unsigned* sched, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(cb2::conv2_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb2::SMEM);
-        attr_set = true;
-    }
+    once_per_device(ONCE_CONV2_BWD, [] { cudaFuncSetAttribute(cb2::conv2_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb2::SMEM); });
     const long long units = ((n + 127) >> 7) * 32;      // groups of 4 positions
     const int sms = device_sm_count();
     ProfileScope ps(KK_CONV2_BWD, st);

@@ -24,13 +24,7 @@ extern "C" int cdq_debug_set_trace(long long* d_buf) {
 int launch_conv_stack(const CdqBoard* boards, long long n, const PackedNet& net, __half* act2, __half* dbg_act1,
                       cudaStream_t st, __half* act1_boards, int max_ctas) {
     if (n == 0) return 0;
-    static const bool use_v1 = getenv("CDQ_CONV_V1") != nullptr;   // A/B switch, see conv_kernel.cu
-    if (use_v1) return launch_conv_stack_v1(boards, n, net, act2, dbg_act1, st, act1_boards);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(cs::conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cs::SMEM);
-        attr_set = true;
-    }
+    once_per_device(ONCE_CONV_STREAM, [] { cudaFuncSetAttribute(cs::conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cs::SMEM); });
     const long long tiles = ((n + 127) >> 7) * (128 / cs::TILE_POS);
     const int sms = device_sm_count();
     unsigned grid = (unsigned)(tiles < sms ? tiles : sms);

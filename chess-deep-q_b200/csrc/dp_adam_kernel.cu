@@ -17,6 +17,7 @@
 //     stores: "my gradients are complete" before the reduction, "my stores have landed" after it.
 // With W = 1 the same kernel is the plain fused Adam step with a device-side step counter, which
 // is what lets the whole training step live in one CUDA graph (no host-computed bias correction).
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include "common.cuh"
@@ -25,9 +26,16 @@
 namespace cdq {
 
 constexpr int DP_THREADS = 512;
-#ifndef CDQ_DP_SPIN_LIMIT
-#define CDQ_DP_SPIN_LIMIT (1u << 24)   // a peer that never arrives traps this rank instead of hanging the GPU
-#endif
+// Waiting for a peer is bounded by WALL CLOCK (%globaltimer), not by an iteration count: ranks legitimately arrive
+// seconds apart (a checkpoint write on rank 0, a first-step graph capture, a GC pause).  The limit is the option
+// "dp_timeout_s" (CDQ_DP_TIMEOUT_S, default 600 s).  A wait that runs out does NOT trap (a trap poisons the CUDA
+// context of every rank): the kernel sets grid_bar[2], skips the update of its slice, still completes its own
+// arrival protocol, and the host reports CDQ_E_TIMEOUT from cdq_dp_adam_status.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -37,22 +45,25 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// every CTA waits until all W ranks have published `epoch` in this rank's flag row
-__device__ __forceinline__ void wait_peers(const unsigned* my_flags, int world, unsigned epoch) {
+// every CTA waits until all W ranks have published `epoch` in this rank's flag row; true = the wait ran out
+__device__ __forceinline__ bool wait_peers(const unsigned* my_flags, int world, unsigned epoch, unsigned long long deadline,
+                                           unsigned* err) {
+    int late = 0;
     if (threadIdx.x < world) {
         unsigned spins = 0;
         while ((int)(ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {
-            if (++spins > CDQ_DP_SPIN_LIMIT) __trap();
+            if ((++spins & 63u) == 0 && globaltimer_ns() > deadline) { late = 1; atomicExch(err, 1u); break; }
         }
     }
-    __syncthreads();
+    return __syncthreads_or(late) != 0;
 }
 
 __global__ void __launch_bounds__(DP_THREADS)
 dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ m, float* __restrict__ v,
                long long n_chunks, int* __restrict__ d_step, unsigned* __restrict__ grid_bar, float lr, float b1, float b2,
-               float eps) {
+               float eps, unsigned long long timeout_ns) {
     __shared__ float s_bc[2];
+    const unsigned long long deadline = globaltimer_ns() + timeout_ns;
     // both counters are read by every thread before block 0 bumps them at the very end
     const int step = *d_step + 1;                      // Adam's t (bias correction); reset by load_state_dict
     const unsigned gen = grid_bar[1] + 1u;             // launch generation of this group: never reset
@@ -63,11 +74,11 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
     }
     // ---- A: this rank's gradients are complete (stream order); tell every peer, wait for all of them
     if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch - 1);
-    wait_peers(peers.flags[rank], world, epoch - 1);
+    const bool late = wait_peers(peers.flags[rank], world, epoch - 1, deadline, grid_bar + 2);
     const float bc1 = s_bc[0], bc2_sqrt = s_bc[1], inv_world = 1.f / (float)world;
 
-    // ---- reduce-scatter + Adam + all-gather on this rank's slice
-    const long long lo = n_chunks * rank / world, hi = n_chunks * (rank + 1) / world;
+    // ---- reduce-scatter + Adam + all-gather on this rank's slice (skipped when a peer's gradients never arrived)
+    const long long lo = n_chunks * rank / world, hi = late ? 0 : n_chunks * (rank + 1) / world;
     for (long long c = lo + (long long)blockIdx.x * DP_THREADS + threadIdx.x; c < hi; c += (long long)gridDim.x * DP_THREADS) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int p = 0; p < world; p++) {
@@ -101,16 +112,14 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
         const unsigned target = gen * gridDim.x;                 // grid_bar[0] is never reset
         atomicAdd(grid_bar, 1u);
         if (blockIdx.x == 0) {
-            unsigned spins = 0;
-            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) {
-                if (++spins > CDQ_DP_SPIN_LIMIT) __trap();
-            }
+            // co-resident CTAs of THIS launch (cooperative grid): always arrive, no time limit needed
+            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) { }
             __threadfence_system();
         }
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
-    wait_peers(peers.flags[rank], world, epoch);
+    wait_peers(peers.flags[rank], world, epoch, deadline, grid_bar + 2);
     if (blockIdx.x == 0 && threadIdx.x == 0) { *d_step = step; grid_bar[1] = gen; }
 }
 
@@ -162,10 +171,7 @@ adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float*
         const unsigned target = gen * gridDim.x;
         atomicAdd(grid_bar, 1u);
         if (blockIdx.x == 0) {
-            unsigned spins = 0;
-            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) {
-                if (++spins > CDQ_DP_SPIN_LIMIT) __trap();
-            }
+            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) { }   // co-resident CTAs of this cooperative launch
             *d_step = step;
             grid_bar[1] = gen;
         }
@@ -181,10 +187,12 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
     if (world == 1) {
         // block 0 waits for the arrival of all others, so the grid must be co-resident: cooperative launch,
         // at most what the occupancy calculator says fits (4 CTAs of 512 threads per SM at 32 registers)
-        static int per_sm = 0;
+        static std::atomic<int> per_sm_cached{0};      // a property of the kernel and the architecture (sm_100 only)
+        int per_sm = per_sm_cached.load(std::memory_order_relaxed);
         if (!per_sm) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_single_kernel, DP_THREADS, 0) != cudaSuccess || per_sm < 1)
                 per_sm = 1;
+            per_sm_cached.store(per_sm, std::memory_order_relaxed);
         }
         if (grid > sms * per_sm) grid = sms * per_sm;
         if (grid < 1) grid = 1;
@@ -199,7 +207,8 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
     if (grid > sms) grid = sms;          // all CTAs must be co-resident: block 0 waits for the others
     if (grid < 1) grid = 1;
     ProfileScope ps(KK_ADAM, st);
-    void* args[] = {(void*)&peers, &rank, &world, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
+    unsigned long long timeout_ns = (unsigned long long)(option(OPT_DP_TIMEOUT_S) > 0 ? option(OPT_DP_TIMEOUT_S) : 1) * 1000000000ull;
+    void* args[] = {(void*)&peers, &rank, &world, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps, &timeout_ns};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)dp_adam_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
     count_launch();
     return (int)e;
@@ -236,12 +245,21 @@ int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, f
         return CDQ_E_BADARG;
     for (int p = 0; p < world; p++)
         if (!peers->params[p] || !peers->grads[p] || !peers->flags[p]) return CDQ_E_BADARG;
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return CDQ_E_NODEVICE; }
+    int dev = current_device(), major = 0;
+    if (dev < 0) return CDQ_E_NODEVICE;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (major != 10) return CDQ_E_NODEVICE;
     return launch_dp_adam(*peers, rank, world, d_m, d_v, n_params_padded, d_step, d_grid_bar, lr, beta1, beta2, eps,
                           (cudaStream_t)stream);
+}
+
+
+int cdq_dp_adam_status(const uint32_t* d_grid_bar, void* stream) {
+    if (!d_grid_bar) return CDQ_E_BADARG;
+    uint32_t err = 0;
+    CDQ_CUDA(cudaMemcpyAsync(&err, d_grid_bar + 2, sizeof(err), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CDQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return err ? CDQ_E_TIMEOUT : 0;
 }
 
 } // extern "C"

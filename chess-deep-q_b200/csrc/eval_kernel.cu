@@ -150,9 +150,13 @@ __device__ __forceinline__ void stage_records(const CdqBoard* __restrict__ board
     __syncthreads();
 }
 
+// HEURISTIC_LEAF instantiates the no-network leaf rule as a second kernel so that the hot instantiation
+// (the one cdq_leaf_eval launches in front of the CNN) keeps its register count and code footprint.
+template <bool HEURISTIC_LEAF>
 __global__ void __launch_bounds__(EVAL_THREADS)
 eval_terms_kernel(const CdqBoard* __restrict__ boards, long long n, int ignore_checkmate,
-                  int* __restrict__ terms, double* __restrict__ score, unsigned* __restrict__ flags) {
+                  int* __restrict__ terms, double* __restrict__ score, unsigned* __restrict__ flags,
+                  float* __restrict__ heuristic_leaf) {
     __shared__ __align__(16) u64 srec[EVAL_THREADS * 9];
     const long long base = (long long)blockIdx.x * EVAL_THREADS;
     stage_records<EVAL_THREADS>(boards, n, base, srec);
@@ -163,6 +167,16 @@ eval_terms_kernel(const CdqBoard* __restrict__ boards, long long n, int ignore_c
     evaluate_position(p, ignore_checkmate, o);
     if (score) score[i] = o.score;
     if (flags) flags[i] = o.flags;
+    if (HEURISTIC_LEAF) {
+        // _evaluate_position without a network (mcts.py:202-210, 226-229): the terminal rules, else
+        // tanh(fast_evaluate_position(board) / 10) -- fp64 like math.tanh, rounded to the fp32 leaf array
+        const unsigned term = o.flags & CDQ_F_TERM_MASK;
+        float v;
+        if (term == CDQ_TERM_CHECKMATE) v = (o.flags & CDQ_F_WHITE_TO_MOVE) ? -1.f : 1.f;
+        else if (term != CDQ_TERM_NONE) v = 0.f;
+        else v = (float)tanh(o.score / 10.0);
+        heuristic_leaf[i] = v;
+    }
     if (terms) {
         int4* t4 = reinterpret_cast<int4*>(terms + i * CDQ_NTERMS);
 #pragma unroll
@@ -238,11 +252,14 @@ int launch_attack_maps(const CdqBoard* boards, long long n, unsigned long long* 
 }
 
 int launch_eval_terms(const CdqBoard* boards, long long n, int ignore_checkmate, int* terms, double* score,
-                      unsigned* flags, cudaStream_t st) {
+                      unsigned* flags, cudaStream_t st, float* heuristic_leaf) {
     if (n == 0) return 0;
     const long long blocks = (n + EVAL_THREADS - 1) / EVAL_THREADS;
     ProfileScope ps(KK_EVAL, st);
-    eval_terms_kernel<<<(unsigned)blocks, EVAL_THREADS, 0, st>>>(boards, n, ignore_checkmate, terms, score, flags);
+    if (heuristic_leaf)
+        eval_terms_kernel<true><<<(unsigned)blocks, EVAL_THREADS, 0, st>>>(boards, n, ignore_checkmate, terms, score, flags, heuristic_leaf);
+    else
+        eval_terms_kernel<false><<<(unsigned)blocks, EVAL_THREADS, 0, st>>>(boards, n, ignore_checkmate, terms, score, flags, nullptr);
     count_launch();
     return (int)cudaGetLastError();
 }

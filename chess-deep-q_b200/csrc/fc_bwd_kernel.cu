@@ -331,12 +331,10 @@ fc1_wgrad_kernel(const __half* __restrict__ dz1h, const __half* __restrict__ act
 
 int launch_fc1_dgrad(const __half* dz1h, const unsigned* relu_mask, const __half* fc1tp, long long n, __half* dz2_boards,
                      cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    once_per_device(ONCE_FC1_DGRAD, [] {
         cudaFuncSetAttribute(fc1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
         cudaFuncSetAttribute(fc1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-        attr_set = true;
-    }
+    });
     const long long chunks = ((n + 127) >> 7) * 16;     // work items: (tile, 256-column chunk), contiguous ranges per CTA
     const int sms = device_sm_count();
     ProfileScope ps(KK_FC1_DGRAD, st);
@@ -347,12 +345,10 @@ int launch_fc1_dgrad(const __half* dz1h, const unsigned* relu_mask, const __half
 }
 
 int launch_fc1_wgrad(const __half* dz1h, const __half* act2, long long n, float inv_scale, float* g_fc1_w, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    once_per_device(ONCE_FC1_DGRAD, [] {
         cudaFuncSetAttribute(fc1_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
         cudaFuncSetAttribute(fc1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-        attr_set = true;
-    }
+    });
     const long long tiles = (n + 127) >> 7;
     // K (positions) split: more splits = more CTAs but one epilogue (32 768 elements of atomics) and one prologue each
     static const int max_splits = [] { const char* e = getenv("CDQ_WGRAD_SPLITS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 2; }();

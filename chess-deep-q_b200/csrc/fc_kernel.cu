@@ -1,24 +1,15 @@
 // fc_kernel.cu -- K2b: fc1 (4096 -> 256) + ReLU + fc2 (256 -> 1) + tanh on the conv stack's output,
 // plus the weight repacking kernel (fp32 PyTorch layouts -> fp16 UMMA tiles).
 //
-// fc_head_kernel is a warp-specialised tcgen05 GEMM: M = 128 positions x N = 256 x K = 4096 per
-// tile, both operands fetched by 1-D bulk async copies (TMA engine, UBLKCP) from pre-tiled global
-// buffers through a 4-stage mbarrier ring, accumulators double-buffered in TMEM (2 x 256 columns).
-// The epilogue applies bias + ReLU and the 256 -> 1 fc2 dot product per TMEM lane (= per position),
-// tanh, and optionally the leaf post-processing of mcts.py:196-232.
-// Algorithmic work: 2 097 664 FLOP/position; reads 8 KB/position of act2.
+// The body of one tile (fc_head.cuh, also the fc role of pipe_kernel.cu) is a warp-specialised tcgen05 GEMM:
+// M = 128 positions x N = 256 x K = 4096, both operands fetched by 1-D bulk async copies (TMA engine, UBLKCP)
+// from pre-tiled global buffers through an mbarrier ring, accumulators in TMEM.  The epilogue applies bias + ReLU
+// and the 256 -> 1 fc2 dot product per TMEM lane (= per position), tanh, and optionally the leaf
+// post-processing of mcts.py:196-232.  Algorithmic work: 2 097 664 FLOP/position; reads 8 KB/position of act2.
 #include <cstdlib>
 #include "fc_head.cuh"
 
 namespace cdq {
-
-__global__ void __launch_bounds__(FC_THREADS, 1)
-fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net,
-               float* __restrict__ value, const unsigned* __restrict__ flags, float* __restrict__ leaf,
-               float* __restrict__ hidden /* optional [n][256] ReLU(fc1), kept for the backward pass */) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    fc_head_body<false>(smem, act2, n, net, value, flags, leaf, hidden, (int)blockIdx.x, (int)gridDim.x, cs::PipeCtl{});
-}
 
 // ------------------------------------------------------------------------------------------
 // fc_head_pairs_kernel: the same GEMM with TWO position tiles per weight stage.  One tile per stage moves 16 KB of
@@ -28,7 +19,7 @@ fc_head_kernel(const __half* __restrict__ act2, long long n, const PackedNet net
 // and ONE B (64 KB, three stages), the two 128 x 256 accumulators fill all 512 TMEM columns, and a pair costs
 // 4 MB: a third less operand traffic per tile.  The accumulators are single buffered, so the tensor pipe waits
 // while the epilogue drains them (16 TMEM loads per pair); the producer keeps prefetching meanwhile.  Same UMMAs
-// in the same K order per tile as fc_head_kernel, so the values are bit-identical.
+// in the same K order per tile as the single-tile body, so the values are bit-identical to the pipe kernel's.
 constexpr int FCP_STAGES = 3;
 constexpr int FCP_STAGE_BYTES = 2 * FC_A_BYTES + FC_B_BYTES;
 constexpr int FCP_OFF_VEC = FCP_STAGES * FCP_STAGE_BYTES;
@@ -76,7 +67,7 @@ fc_head_pairs_kernel(const __half* __restrict__ act2, long long n, const PackedN
                 const bool two = 2 * p + 1 < n_tiles;
                 const uint8_t* a_tile = reinterpret_cast<const uint8_t*>(act2) + (p << 21);
                 for (int s = 0; s < 64; s++, it++) {
-                    const int sq = ((s & 7) << 3) | (s >> 3);          // the K order of fc_head_kernel (file-major)
+                    const int sq = ((s & 7) << 3) | (s >> 3);          // the K order of fc_head.cuh (file-major)
                     const int st = it % FCP_STAGES;
                     mbar_wait(empty + st, ((it / FCP_STAGES) & 1) ^ 1);
                     uint8_t* sa = smem + st * FCP_STAGE_BYTES;
@@ -278,43 +269,16 @@ int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st
     return (int)cudaGetLastError();
 }
 
-int device_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
-}
-
 int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
                    float* leaf, float* hidden, cudaStream_t st) {
     if (n == 0) return 0;
     const long long tiles = (n + 127) / 128;
     if (tiles <= FC_SPLIT_MAX_TILES && fc_split_enabled()) return launch_fc_head_split(act2, n, net, value, flags, leaf, hidden, st);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(fc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM);
-        attr_set = true;
-    }
+    once_per_device(ONCE_FC_PAIRS, [] { cudaFuncSetAttribute(fc_head_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FCP_SMEM); });
     const int sms = device_sm_count();
-    const char* pe = getenv("CDQ_FC_PAIRS");             // "0": one tile per weight stage (A/B)
-    if (!(pe && pe[0] == '0')) {
-        static bool pattr = false;
-        if (!pattr) {
-            cudaFuncSetAttribute(fc_head_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FCP_SMEM);
-            pattr = true;
-        }
-        const long long pairs = (tiles + 1) / 2;
-        ProfileScope ps(KK_FC, st);
-        fc_head_pairs_kernel<<<(unsigned)(pairs < sms ? pairs : sms), FC_THREADS, FCP_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
-        count_launch();
-        return (int)cudaGetLastError();
-    }
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    const long long pairs = (tiles + 1) / 2;
     ProfileScope ps(KK_FC, st);
-    fc_head_kernel<<<grid, FC_THREADS, FC_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
+    fc_head_pairs_kernel<<<(unsigned)(pairs < sms ? pairs : sms), FC_THREADS, FCP_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
     count_launch();
     return (int)cudaGetLastError();
 }

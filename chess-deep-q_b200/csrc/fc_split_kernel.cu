@@ -204,18 +204,11 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-bool fc_split_enabled() {      // read on every call so that one process can A/B the two kernels
-    const char* e = getenv("CDQ_FC_SPLIT");
-    return !(e && e[0] == '0');
-}
+bool fc_split_enabled() { return option(OPT_FC_SPLIT) != 0; }     // cdq_set_option("fc_split", 0): A/B against the persistent kernel
 
 int launch_fc_head_split(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
                          float* leaf, float* hidden, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(fc_head_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
-        attr_set = true;
-    }
+    once_per_device(ONCE_FC_SPLIT, [] { cudaFuncSetAttribute(fc_head_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM); });
     const long long tiles = (n + 127) / 128;
     ProfileScope ps(KK_FC, st);
     fc_head_split_kernel<<<(unsigned)(tiles * FS_SPLIT), FC_THREADS, FS_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);

@@ -77,11 +77,7 @@ static int pipe_conv_ctas(int sms) {
 int launch_leaf_pipe(const CdqBoard* boards, long long n, const PackedNet& net, float* value, const unsigned* flags,
                      float* leaf, void* ws, cudaStream_t st) {
     if (n == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(leaf_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
-        attr_set = true;
-    }
+    once_per_device(ONCE_PIPE, [] { cudaFuncSetAttribute(leaf_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM); });
     const int sms = device_sm_count();
     cs::PipeCtl pipe;
     pipe.ring = (uint8_t*)ws;

@@ -26,7 +26,7 @@ namespace cdq {
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const float* __restrict__ reward,
                 const float* __restrict__ done, const float* __restrict__ hidden, const float* __restrict__ fc2_w,
-                long long n, float gamma, int loss_kind, float scale, __half* __restrict__ dz1h,
+                long long n, float inv_n /* 1 / mean_over */, float gamma, int loss_kind, float scale, __half* __restrict__ dz1h,
                 float* __restrict__ g_fc2_w, float* __restrict__ g_fc2_b, float* __restrict__ g_fc1_b,
                 float* __restrict__ loss) {
     __shared__ float s_gw[8][256];
@@ -36,17 +36,19 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
     float gw[8], gb1[8], gb = 0.f, ls = 0.f, w2[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { gw[i] = 0.f; gb1[i] = 0.f; w2[i] = fc2_w[lane * 8 + i]; }
-    const float inv_n = 1.f / (float)n;
     const long long n_pad = ((n + 127) >> 7) << 7;
     for (long long b = (long long)blockIdx.x * 8 + warp; b < n_pad; b += (long long)gridDim.x * 8) {
         uint4 packed = make_uint4(0, 0, 0, 0);
         if (b < n) {
             const float qv = q[b];
-            const float y = reward[b] + (1.f - done[b]) * gamma * qn[b];      // neural_network.py:238
-            const float d = qv - y;
             float dl;                                                          // d loss / d q
-            if (loss_kind == 0) { ls += d * d; dl = 2.f * d; }                 // F.mse_loss (neural_network.py:241)
-            else { const float ad = fabsf(d); ls += ad < 1.f ? 0.5f * d * d : ad - 0.5f; dl = fminf(1.f, fmaxf(-1.f, d)); }
+            if (loss_kind == CDQ_LOSS_UPSTREAM) { dl = reward[b]; ls += dl * qv; }      // caller supplies d loss / d q (autograd)
+            else {
+                const float y = reward[b] + (1.f - done[b]) * gamma * qn[b];   // neural_network.py:238
+                const float d = qv - y;
+                if (loss_kind == 0) { ls += d * d; dl = 2.f * d; }             // F.mse_loss (neural_network.py:241)
+                else { const float ad = fabsf(d); ls += ad < 1.f ? 0.5f * d * d : ad - 0.5f; dl = fminf(1.f, fmaxf(-1.f, d)); }
+            }
             const float dz2 = dl * inv_n * (1.f - qv * qv);                    // through tanh
             gb += dz2;
             const float4 h0 = *reinterpret_cast<const float4*>(hidden + b * 256 + lane * 8);
@@ -333,16 +335,21 @@ struct SideStream {
         return 0;
     }
 };
-SideStream g_side;
+SideStream g_sides[MAX_DEVICES];      // one per device: the stream and its events belong to the device they were created on
+std::mutex g_side_mu[MAX_DEVICES];    // serialises the ENQUEUE of concurrent training calls on one device (they share the events)
 } // namespace
 
 int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
-                  const CdqBoard* next_states, const float* reward, const float* done, long long n, float gamma,
-                  int loss_kind_flags, const CdqWeights& g /* gradient outputs, pre-zeroed */, float* loss, void* ws_base,
-                  cudaStream_t st) {
+                  const CdqBoard* next_states, const float* reward, const float* done, long long n, double mean_over,
+                  float gamma, int loss_kind_flags, const CdqWeights& g /* gradient outputs, pre-zeroed */, float* loss,
+                  void* ws_base, cudaStream_t st) {
     TrainWs ws = carve(ws_base, n);
     const int loss_kind = loss_kind_flags & 0xff;
     int e;
+    const int dev = current_device();
+    if (dev < 0) return CDQ_E_NODEVICE;
+    std::lock_guard<std::mutex> side_lock(g_side_mu[dev]);
+    SideStream& g_side = g_sides[dev];
     if ((e = g_side.init())) return e;
     cudaStream_t side = g_side.st;
     // borders of the board-shaped buffers must be zero; their interiors are rewritten every step
@@ -358,13 +365,16 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     // so it gets the larger share (CDQ_TRAIN_CONV_SPLIT = percent of the SMs for the online network, default 50: measured flat between 50 and 61, profiles/conv_split_sweep.sh).
     static const int online_pct = [] { const char* e = getenv("CDQ_TRAIN_CONV_SPLIT"); const int v = e ? atoi(e) : 0; return v >= 20 && v <= 80 ? v : 50; }();
     const int online_sms = device_sm_count() * online_pct / 100, target_sms = device_sm_count() - online_sms;
-    if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, target_sms))) return e;
-    if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
+    const bool upstream = loss_kind == CDQ_LOSS_UPSTREAM;     // no target network: d loss / d q comes from the caller
+    if (!upstream) {
+        if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, target_sms))) return e;
+        if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
+    }
     // the online network's fp16 tiles are rebuilt from the fp32 parameters next to the target forward
     const bool zero_in_pack = (loss_kind_flags & CDQ_TRAIN_REPACK) && (loss_kind_flags & CDQ_TRAIN_ZERO_LOSS);
     if ((loss_kind_flags & CDQ_TRAIN_ZERO_LOSS) && !zero_in_pack) CDQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     if ((loss_kind_flags & CDQ_TRAIN_REPACK) && (e = launch_pack_weights(w, net->p, st, zero_in_pack ? loss : nullptr))) return e;
-    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_dump, online_sms))) return e;
+    if ((e = launch_conv_stack(states, n, net->p, ws.act2_tiles, nullptr, st, ws.a1_dump, upstream ? 0 : online_sms))) return e;
     // ReLU(conv2)'s bit mask for the fc1 data gradient: side stream, after the target forward, under the online fc head
     CDQ_CUDA(cudaEventRecord(g_side.mid, st));
     CDQ_CUDA(cudaStreamWaitEvent(side, g_side.mid, 0));
@@ -380,12 +390,14 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // ---- loss, tanh, fc2, fc1 bias
-    const float scale = 64.f * (float)n;      // lift into fp16's normal range; undone in the fp32 epilogues
+    // lift into fp16's normal range; undone in the fp32 epilogues (upstream mode: the caller normalises max|dl| to 1)
+    const float scale = upstream ? 64.f : 64.f * (float)mean_over;
     {
         ProfileScope ps(KK_HEAD_BWD, st);
         const long long n_pad = ((n + 127) >> 7) << 7;
         const unsigned blocks = (unsigned)(n_pad / 8 < 1184 ? n_pad / 8 : 1184);
-        head_bwd_kernel<<<blocks, 256, 0, st>>>(ws.q, ws.qn, reward, done, ws.hidden, w.fc2_w, n, gamma, loss_kind, scale, ws.dz1h,
+        head_bwd_kernel<<<blocks, 256, 0, st>>>(ws.q, ws.qn, reward, done, ws.hidden, w.fc2_w, n, upstream ? 1.f : (float)(1.0 / mean_over),
+                                                gamma, loss_kind, scale, ws.dz1h,
                                                 (float*)g.fc2_w, (float*)g.fc2_b, (float*)g.fc1_b, loss);
         count_launch();
     }
@@ -401,11 +413,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     {
         // ---- conv1: weight + bias gradient by scatter over the one-hot input
         ProfileScope ps(KK_CONV1_WGRAD, st);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM);
-            attr_set = true;
-        }
+        once_per_device(ONCE_CONV1_WGRAD, [] { cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM); });
         const long long want = (n + C1W_SLOTS - 1) / C1W_SLOTS;     // one CTA of 18 warps per SM
         const unsigned blocks = (unsigned)(want < device_sm_count() ? want : device_sm_count());
         conv1_wgrad_kernel<<<blocks, C1W_THREADS, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);

@@ -11,9 +11,11 @@ from .neural_network import _Workspace
 class LeafEvaluator:
     """Batched replacement for per-leaf `_evaluate_position`: leaf value = -1/+1 on checkmate (from
     white's point of view, mcts.py:202-203), 0 on stalemate / insufficient material / threefold
-    repetition (:205-210), else clamp(net(board), -1, 1) (:213-221)."""
+    repetition (:205-210), else clamp(net(board), -1, 1) (:213-221).  neural_net = None is the
+    reference's heuristic branch (:226-229): tanh(fast_evaluate_position(board) / 10) behind the same
+    terminal rules, computed by the evaluation kernel alone."""
 
-    def __init__(self, neural_net):
+    def __init__(self, neural_net=None):
         self.net = neural_net
         self._ws = _Workspace()
         self.total_positions_evaluated = 0  # mcts.py:28
@@ -27,8 +29,13 @@ class LeafEvaluator:
         out = {"leaf": torch.empty(n, dtype=torch.float32, device=dev),
                "score": torch.empty(n, dtype=torch.float64, device=dev),
                "flags": torch.empty(n, dtype=torch.int32, device=dev)}
+        if want_raw and self.net is None:
+            raise _lib.CdqError("want_raw needs a network: without one the leaf value is tanh(score / 10)")
         raw = torch.empty(n, dtype=torch.float32, device=dev) if want_raw else None
-        if n:
+        if n and self.net is None:
+            _lib.check(_lib.lib().cdq_leaf_eval(None, d.data_ptr(), n, out["leaf"].data_ptr(), out["score"].data_ptr(),
+                                                out["flags"].data_ptr(), None, None, 0, _lib.stream_ptr()))
+        elif n:
             ws = self._ws.get(n, dev)
             _lib.check(_lib.lib().cdq_leaf_eval(self.net.net_handle(), d.data_ptr(), n, out["leaf"].data_ptr(),
                                                 out["score"].data_ptr(), out["flags"].data_ptr(),
@@ -52,7 +59,7 @@ class LeafEvaluator:
         if out is None:
             out = {"leaf": np.empty(n, np.float32), "score": np.empty(n, np.float64), "flags": np.empty(n, np.uint32)}
         ptr = lambda a: a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data  # noqa: E731
-        handle = self.net.net_handle()
+        handle = self.net.net_handle() if self.net is not None else None
         torch.cuda.current_stream().synchronize()  # weights may have been repacked on this stream
         _lib.check(_lib.lib().cdq_leaf_eval_host(handle, src, n, ptr(out["leaf"]),
                                                  ptr(out["score"]), ptr(out["flags"])))
@@ -60,12 +67,12 @@ class LeafEvaluator:
         return out
 
 
-def evaluate_positions(boards, neural_net):
+def evaluate_positions(boards, neural_net=None):
     """Batch form of _evaluate_position: -> fp32 [n] leaf values (CUDA tensor)."""
     return LeafEvaluator(neural_net).evaluate_device(boards)["leaf"]
 
 
-def evaluate_position(board, neural_net, device=None):
+def evaluate_position(board, neural_net=None, device=None):
     """Drop-in for ParallelRussianDollMCTS._evaluate_position(board, neural_net, device) -> float."""
     return float(evaluate_positions(board, neural_net)[0].item())
 

@@ -18,6 +18,7 @@ assert NPARAMS == 1071073
 NPARAMS_PAD = (NPARAMS + 3) // 4 * 4      # flat buffers are padded to whole 16-byte chunks (padding stays 0)
 
 LOSS_MSE, LOSS_HUBER = 0, 1
+LOSS_UPSTREAM = 2          # CDQ_LOSS_UPSTREAM: backward of the forward alone, d loss / d q supplied by the caller (autograd)
 REPACK = 0x200             # CDQ_TRAIN_REPACK: the call re-packs the online network from the fp32 parameters
 ZERO_LOSS = 0x400          # CDQ_TRAIN_ZERO_LOSS: the call zeroes the loss accumulator itself
 WS_PERSISTENT = 0x100      # CDQ_TRAIN_WS_PERSISTENT: the workspace is ours, zero-filled once, reused every step
@@ -130,7 +131,7 @@ class FusedAdam:
         """peer_group: False = plain buffers (single GPU, or NCCL all-reduce through step(grad_scale));
         True / a ProcessGroup = parameters and gradients live in a CUDA-IPC PeerRegion so that
         step_fused() runs the one-kernel reduce-scatter + Adam + all-gather over NVLink."""
-        dev = _lib.require_cuda()
+        dev = next(network.parameters()).device      # state_dict()/load_state_dict() work anywhere; stepping needs the B200
         self.network = network
         self.region = None
         if peer_group is not False:
@@ -144,13 +145,28 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
         self._d_step = torch.zeros(1, dtype=torch.int32, device=dev)       # device copy of step_count (step_fused)
-        self._grid_bar = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._grid_bar = torch.zeros(4, dtype=torch.int32, device=dev)   # arrivals, generation, time-out flag, reserved
         self._flags = torch.zeros(64, dtype=torch.int32, device=dev)        # flag row of the world = 1 case
         self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": 0, "amsgrad": False,
                               "params": list(range(len(PARAM_ORDER)))}]
+        self._link_param_grads()
+
+    def _link_param_grads(self):
+        """Every parameter's .grad is a view of the flat gradient buffer, so `loss.backward()` through
+        ChessQNetwork's autograd surface accumulates where step() reads.  A .grad that was replaced
+        (module.zero_grad(set_to_none=True), a fresh tensor assigned by the caller) is copied in and
+        re-linked."""
+        params = dict(self.network.named_parameters())
+        for name, view in self.grad_views().items():
+            p = params[name]
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
 
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
+        self.network._cdq_grads_dirty = False
 
     def grad_views(self):
         return {n: self.grad[o:o + s].view(sh) for n, o, s, sh in zip(PARAM_ORDER, PARAM_OFFSETS, PARAM_SIZES, PARAM_SHAPES)}
@@ -181,6 +197,8 @@ class FusedAdam:
 
     def step(self, grad_scale=1.0):
         g = self.param_groups[0]
+        self._link_param_grads()
+        self.network._cdq_grads_dirty = True     # unlike step_fused, this leaves the gradients in place (torch semantics)
         self.step_count += 1
         self._d_step.fill_(self.step_count)
         _lib.check(_lib.lib().cdq_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
@@ -257,12 +275,22 @@ def _weights_struct(tensors):
     return _lib.CdqWeights(*[t.data_ptr() for t in tensors])
 
 
+def _mean_over(n, global_batch, world):
+    """cdq_train_fwd_bwd's normaliser: every rank divides by global_batch / world, so the 1/world average of the
+    per-rank sums is the mean over the global batch whatever the shard sizes (0 = this call's own n)."""
+    return float(global_batch) / world if global_batch else 0.0
+
+
 def dqn_train_step(q_network, target_network, optimizer, states, next_states, rewards, dones, gamma=0.99,
-                   loss_kind=LOSS_MSE, group=None):
+                   loss_kind=LOSS_MSE, group=None, global_batch=None):
     """One replay step on device tensors: states/next_states packed boards int64 [n,9], rewards and
     dones fp32 [n].  Returns the loss (fp32 CUDA tensor, mean over the GLOBAL batch when
-    torch.distributed is initialised)."""
+    torch.distributed is initialised; pass global_batch when the shards are not all the same size)."""
     n = states.shape[0]
+    world = 1
+    if global_batch:
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     dev = states.device
     params = dict(q_network.named_parameters())
     weights = _weights_struct([params[k] for k in PARAM_ORDER])
@@ -273,8 +301,8 @@ def dqn_train_step(q_network, target_network, optimizer, states, next_states, re
     loss.zero_()
     _lib.check(_lib.lib().cdq_train_fwd_bwd(
         q_network.net_handle(), target_network.net_handle(), ctypes.byref(weights), states.data_ptr(),
-        next_states.data_ptr(), rewards.data_ptr(), dones.data_ptr(), n, float(gamma), int(loss_kind),
-        ctypes.byref(grads), loss.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        next_states.data_ptr(), rewards.data_ptr(), dones.data_ptr(), n, _mean_over(n, global_batch, world), float(gamma),
+        int(loss_kind), ctypes.byref(grads), loss.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     scale = allreduce_mean_scale(optimizer.grad, group)
     optimizer.step(grad_scale=scale)
     out = loss.clone()
@@ -290,12 +318,15 @@ class GraphedDQNStep:
     reduction over the peer group, Adam, parameter broadcast -- as ONE CUDA graph per rank
     (about 15 kernels; launched eagerly from Python they cost more host time than device time at
     batch 4 096).  Inputs are copied into static device buffers, so shapes are fixed at construction.
-    Under a peer group (FusedAdam(peer_group=True)) every rank holds `batch` = its shard."""
+    Under a peer group (FusedAdam(peer_group=True)) every rank holds `batch` = its shard; pass
+    global_batch when the shards are not all the same size, so that the step is the mean over the
+    global batch (neural_network.py:241) and not the mean of the shard means."""
 
-    def __init__(self, q_network, target_network, optimizer, batch, gamma=0.99, loss_kind=LOSS_MSE):
+    def __init__(self, q_network, target_network, optimizer, batch, gamma=0.99, loss_kind=LOSS_MSE, global_batch=None):
         dev = _lib.require_cuda()
         self.q_network, self.target_network, self.optimizer = q_network, target_network, optimizer
         self.batch, self.gamma, self.loss_kind = int(batch), float(gamma), int(loss_kind)
+        self.mean_over = _mean_over(self.batch, global_batch, optimizer.world)
         self.states = torch.zeros((self.batch, 9), dtype=torch.int64, device=dev)
         self.next_states = torch.zeros((self.batch, 9), dtype=torch.int64, device=dev)
         self.rewards = torch.zeros(self.batch, dtype=torch.float32, device=dev)
@@ -314,7 +345,7 @@ class GraphedDQNStep:
         _lib.check(_lib.lib().cdq_train_fwd_bwd(
             self.q_network.raw_handle(), self.target_network.net_handle(), ctypes.byref(weights),
             self.states.data_ptr(), self.next_states.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
-            self.batch, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK | ZERO_LOSS, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
+            self.batch, self.mean_over, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK | ZERO_LOSS, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
             self.ws.numel(), _lib.stream_ptr()))
         self.optimizer.step_fused()
 
@@ -326,6 +357,8 @@ class GraphedDQNStep:
 
     def run(self):
         """One step on the current contents of the static buffers; returns the local loss tensor."""
+        if getattr(self.q_network, "_cdq_grads_dirty", False):
+            self.optimizer.zero_grad()         # an eager backward / step() in between left gradients behind; the step accumulates
         if self.graph is None:
             self._body()                       # eager once: function attributes, lazy tables
             torch.cuda.synchronize()
@@ -350,10 +383,112 @@ class GraphedDQNStep:
         return self.run()
 
     def global_loss(self):
-        """Loss averaged over all ranks of the peer group (equal shards)."""
+        """Loss over the global batch: the average over the ranks of the peer group (exact for equal shards, and
+        for unequal ones when global_batch was given)."""
         out = self.loss.clone()
         if self.optimizer.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out)
             out /= self.optimizer.world
         return out
+
+
+def dp_parity_report(make_net, states, next_states, rewards, dones, gamma=0.99, real_steps=2):
+    """Data-parallel parity of the replay step, measured at gradient level ("N-GPU ==
+    1-GPU to fp32 reduction-order noise").  Call on EVERY rank of an initialised NCCL group with the
+    same full batch; make_net() -> (q_network, target_network) builds identical replicas.  Checks
+
+      a. the gradient the fused kernel reduces (read back as Adam's first moment after ONE step with
+         lr = 0: exp_avg = (1 - beta1) * g) against the rank-ordered sum of the shard gradients computed
+         eagerly on private replicas and gathered with NCCL             -> max_rel_vs_shard_sum (<= 1e-5)
+      b. that sum against the gradient of the whole batch on ONE GPU    -> max_rel_vs_full_batch (<= 1e-3)
+      c. the loss over `real_steps` real steps (lr = 1e-3) against the single-GPU step (<= 1e-4 relative)
+      d. that all replicas hold identical parameter bits afterwards.
+
+    Relative errors are max |a - b| / max |b| per parameter tensor, maximised over the tensors.
+    Shards come from shard_range (uneven when the batch does not divide).  Returns a dict (same on all ranks)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = states.shape[0]
+    lo, hi = shard_range(n, rank, world)
+    sl = slice(lo, hi)
+    L = _lib.lib()
+
+    def eager_gradient(net, tgt, s, ns, r, d, mean_over):
+        opt = FusedAdam(net, lr=0.0)
+        opt.zero_grad()
+        params = dict(net.named_parameters())
+        weights = _weights_struct([params[k] for k in PARAM_ORDER])
+        gv = opt.grad_views()
+        grads = _weights_struct([gv[k] for k in PARAM_ORDER])
+        m = s.shape[0]
+        ws = torch.zeros(L.cdq_train_workspace_bytes(m), dtype=torch.uint8, device=s.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=s.device)
+        _lib.check(L.cdq_train_fwd_bwd(net.net_handle(), tgt.net_handle(), ctypes.byref(weights), s.data_ptr(), ns.data_ptr(),
+                                       r.data_ptr(), d.data_ptr(), m, mean_over, float(gamma), LOSS_MSE, ctypes.byref(grads),
+                                       loss.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        return opt.grad.clone(), loss
+
+    def max_rel(a, b):
+        worst = 0.0
+        for o, sz in zip(PARAM_OFFSETS, PARAM_SIZES):
+            ref = b[o:o + sz]
+            worst = max(worst, float((a[o:o + sz] - ref).abs().max() / ref.abs().max().clamp_min(1e-30)))
+        return worst
+
+    s, ns, r, d = states[sl].contiguous(), next_states[sl].contiguous(), rewards[sl].contiguous(), dones[sl].contiguous()
+    # --- expected: shard gradients (mean_over = n / world) gathered, summed in rank order, scaled like the kernel
+    g_shard, _ = eager_gradient(*make_net(), s, ns, r, d, n / world)
+    gathered = [torch.empty_like(g_shard) for _ in range(world)]
+    dist.all_gather(gathered, g_shard)
+    g_sum = torch.zeros_like(g_shard)
+    for g in gathered:
+        g_sum += g
+    g_sum *= 1.0 / world
+    # --- single GPU, whole batch
+    g_full, _ = eager_gradient(*make_net(), states, next_states, rewards, dones, 0.0)
+    # --- a: ONE fused data-parallel step with lr = 0; the reduced gradient is Adam's first moment / (1 - beta1)
+    qa, ta = make_net()
+    opt_a = FusedAdam(qa, lr=0.0, peer_group=True)
+    step_a = GraphedDQNStep(qa, ta, opt_a, batch=hi - lo, gamma=gamma, global_batch=n)
+    step_a.load(s, ns, r, d)
+    step_a.run()
+    torch.cuda.synchronize()
+    m_dp, _ = opt_a._gathered_state()
+    expect_m = g_sum * (1.0 - opt_a.param_groups[0]["betas"][0])
+    rel_shard = max_rel(m_dp, expect_m)
+    rel_full = max_rel(g_sum, g_full)
+    status_a = L.cdq_dp_adam_status(opt_a._grid_bar.data_ptr(), _lib.stream_ptr())
+    dist.barrier()
+    opt_a.region.close()
+    # --- c, d: real steps against the single-GPU step
+    qb, tb = make_net()
+    opt_b = FusedAdam(qb, lr=1e-3, peer_group=True)
+    step_b = GraphedDQNStep(qb, tb, opt_b, batch=hi - lo, gamma=gamma, global_batch=n)
+    step_b.load(s, ns, r, d)
+    q1, t1 = make_net()
+    opt_1 = FusedAdam(q1, lr=1e-3)
+    step_1 = GraphedDQNStep(q1, t1, opt_1, batch=n, gamma=gamma)
+    step_1.load(states, next_states, rewards, dones)
+    loss_rel = 0.0
+    for _ in range(real_steps):
+        step_b.run()
+        l_dp = float(step_b.global_loss().item())
+        l_1 = float(step_1.run().item())
+        loss_rel = max(loss_rel, abs(l_dp - l_1) / max(abs(l_1), 1e-30))
+    torch.cuda.synchronize()
+    flat = opt_b.flat.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([1.0 if torch.equal(flat, ref) else 0.0], device=flat.device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    stats = torch.tensor([rel_shard, rel_full, loss_rel, float(status_a != 0)], dtype=torch.float64, device=flat.device)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    opt_b.region.close()
+    rel_shard, rel_full, loss_rel, timed_out = [float(x) for x in stats.tolist()]
+    identical = bool(same.item() == 1.0)
+    return {"ok": bool(rel_shard <= 1e-5 and rel_full <= 1e-3 and loss_rel <= 1e-4 and identical and not timed_out),
+            "world": world, "global_batch": n, "shards": [shard_range(n, k, world)[1] - shard_range(n, k, world)[0] for k in range(world)],
+            "max_rel_vs_shard_sum": rel_shard, "max_rel_vs_full_batch": rel_full, "loss_rel": loss_rel,
+            "replicas_identical": identical, "bars": {"vs_shard_sum": 1e-5, "vs_full_batch": 1e-3, "loss_rel": 1e-4}}

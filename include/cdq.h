@@ -10,8 +10,14 @@
  *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - return value: 0 = ok, >0 = cudaError_t, <0 = CDQ_E_* below;
- *   - no global mutable state except lazily-initialised read-only device tables, so calls are
- *     re-entrant (the reference is called from a thread pool, mcts.py:77);
+ *   - every device-pointer entry point works on the CURRENT device of the calling thread and keeps no state
+ *     between calls except per-device caches (SM count, kernel attributes), so calls from a thread pool
+ *     (the reference's callers, mcts.py:77) and on several devices of one process are safe.  Two exceptions,
+ *     both serialised internally: cdq_train_fwd_bwd shares one side stream and its events per device (the
+ *     ENQUEUE of concurrent training calls on one device is mutually exclusive; the work itself overlaps only
+ *     as far as that side stream allows), and a CdqHostCtx runs one cdq_leaf_eval_host_ctx at a time;
+ *   - run-time switches are read from the environment ONCE, at first use, and changed afterwards only through
+ *     cdq_set_option;
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  */
 #ifndef CDQ_H
@@ -31,6 +37,7 @@ extern "C" {
 #define CDQ_E_NODEVICE (-2) /* no CUDA device / wrong architecture (needs sm_100)      */
 #define CDQ_E_WORKSPACE (-3)/* workspace smaller than cdq_workspace_bytes(n)           */
 #define CDQ_E_BADBOARD (-4) /* a record has >1 king per colour or overlapping boards   */
+#define CDQ_E_TIMEOUT (-5)  /* a data-parallel peer never reached cdq_dp_adam_step       */
 
 /* ---- PackedBoard: the wire format (72 bytes, little endian) -------------------------
  * Everything evaluation.py / board_to_tensor / ChessQNetwork read from a python-chess
@@ -114,6 +121,15 @@ typedef struct CdqNet CdqNet;
 int cdq_version(void);
 const char* cdq_error_string(int code);
 
+/* Run-time switches, initialised once from the environment variable in brackets:
+ *   "pipe"         [CDQ_PIPE, 0]          1: batches >= 512 K positions run conv + fc as one kernel (act2 stays in L2)
+ *   "fc_split"     [CDQ_FC_SPLIT, 1]      0: small batches use the persistent fc kernel instead of the cluster split-K one
+ *   "host_ramp"    [CDQ_HOST_RAMP, 1]     0: cdq_leaf_eval_host starts with full chunks
+ *   "dp_timeout_s" [CDQ_DP_TIMEOUT_S, 600] wall-clock limit of cdq_dp_adam_step's wait for its peers
+ * Unknown names return CDQ_E_BADARG. */
+int cdq_set_option(const char* name, int value);
+int cdq_get_option(const char* name, int* value);
+
 /* Replaces evaluation.fast_evaluate_position (evaluation.py:30-229) for a batch.
  * Any of d_terms / d_score / d_flags may be NULL.  ignore_checkmate as evaluation.py:30. */
 int cdq_eval_terms(const CdqBoard* d_boards, int64_t n, int ignore_checkmate,
@@ -144,15 +160,27 @@ int cdq_value_fwd(const CdqNet* net, const CdqBoard* d_boards, int64_t n, float*
 
 /* Replaces ParallelRussianDollMCTS._evaluate_position (mcts.py:196-232) plus the handcrafted
  * score for a batch: d_leaf[i] = -1/+1 checkmate, 0 draw, else clamp(net value, -1, 1);
- * d_score / d_flags as cdq_eval_terms.  d_value_raw (optional) = unclamped network output. */
+ * d_score / d_flags as cdq_eval_terms.  d_value_raw (optional) = unclamped network output.
+ * net == NULL is the reference's `neural_net is None` branch (mcts.py:226-229): behind the same terminal
+ * rules d_leaf[i] = tanh(fast_evaluate_position(board) / 10), computed in fp64 and rounded to fp32 (CUDA's
+ * tanh against libm's: compared to 1e-6, not bit for bit); no workspace is needed, d_value_raw must be NULL. */
 int cdq_leaf_eval(const CdqNet* net, const CdqBoard* d_boards, int64_t n,
                   float* d_leaf, double* d_score, uint32_t* d_flags, float* d_value_raw,
                   void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* Host-buffer convenience used by the Python drop-ins and bench `e2e`: copies h_boards to the
- * device (pinned or pageable), runs cdq_leaf_eval, copies results back, synchronises. */
+/* Host-buffer path used by the Python drop-ins and bench `e2e`: copies h_boards to the device (pinned or
+ * pageable) in double-buffered chunks on two streams, runs cdq_leaf_eval, copies results back, synchronises.
+ * A CdqHostCtx owns the streams and device buffers (about 2.5 GB) on the device that was current at creation;
+ * one call at a time per context, any number of contexts.  cdq_leaf_eval_host uses one lazily created context
+ * per device (callers sharing it are serialised); cdq_host_release frees those. */
+typedef struct CdqHostCtx CdqHostCtx;
+int cdq_host_ctx_create(CdqHostCtx** out);
+void cdq_host_ctx_destroy(CdqHostCtx* ctx);
+int cdq_leaf_eval_host_ctx(CdqHostCtx* ctx, const CdqNet* net, const CdqBoard* h_boards, int64_t n,
+                           float* h_leaf, double* h_score, uint32_t* h_flags);
 int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
                        float* h_leaf, double* h_score, uint32_t* h_flags);
+void cdq_host_release(void);
 
 /* ---- DQN replay training step (replaces DQNAgent.train, neural_network.py:218-252) ----
  * cdq_train_fwd_bwd: q = net(states), q' = target_net(next_states), y = r + (1-done)*gamma*q',
@@ -160,21 +188,31 @@ int cdq_leaf_eval_host(const CdqNet* net, const CdqBoard* h_boards, int64_t n,
  * backward through the whole network.  d_weights = the fp32 master parameters (PyTorch layouts) that
  * `net` was packed from; d_grads = where to ACCUMULATE the gradients (same layouts; zero them first);
  * *d_loss is accumulated too (zero it first).  A terminal next_state is the all-zero board
- * (neural_network.py:215).  After an N-rank data-parallel step, sum the gradients over ranks and
- * pass grad_scale = 1/N to cdq_adam_step.  OR loss_kind with CDQ_TRAIN_WS_PERSISTENT when d_workspace
+ * (neural_network.py:215).  mean_over: the loss and its gradients are sums over the n samples of THIS call divided
+ * by mean_over; <= 0 means n (F.mse_loss's mean, the single-GPU case).  In an N-rank data-parallel step over a
+ * global batch of B samples every rank passes mean_over = B / N, whatever its own shard size, so that the
+ * 1/N average of the per-rank results (grad_scale = 1/N in cdq_adam_step, or cdq_dp_adam_step's own) is the
+ * mean over the global batch also when B does not divide evenly.  OR loss_kind with CDQ_TRAIN_WS_PERSISTENT when d_workspace
  * is the same buffer as in the previous call with the same n AND was zero-filled before its first
  * use: the call then skips re-zeroing the (never written) borders of its board-shaped buffers.
  * The target network's forward and fc1's weight gradient run on an internal side stream, forked
  * from and joined to `stream` with events (graph-capture safe).
  * cdq_adam_step: torch.optim.Adam defaults (neural_network.py:65) over one flat fp32 buffer. */
+#define CDQ_LOSS_MSE 0
+#define CDQ_LOSS_HUBER 1
+/* loss_kind 2: the backward pass of ChessQNetwork.forward alone, for torch.autograd (the reference calls
+ * loss.backward() on whatever it builds from the network's output, neural_network.py:244-246).  d_reward holds
+ * d loss / d q per sample, normalised by the caller so that max |.| <= 1 (gradients travel between kernels as
+ * fp16); target_net, d_next_states and d_done are ignored (may be NULL); *d_loss accumulates sum(q * dq). */
+#define CDQ_LOSS_UPSTREAM 2
 #define CDQ_TRAIN_WS_PERSISTENT 0x100
 #define CDQ_TRAIN_REPACK 0x200 /* re-pack `net` from d_weights inside the call (next to the target forward) */
 #define CDQ_TRAIN_ZERO_LOSS 0x400 /* *d_loss is zeroed inside the call (no separate fill launch in a captured step) */
 size_t cdq_train_workspace_bytes(int64_t n);
 int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
                       const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,
-                      const float* d_done, int64_t n, float gamma, int loss_kind, const CdqWeights* d_grads,
-                      float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
+                      const float* d_done, int64_t n, double mean_over, float gamma, int loss_kind,
+                      const CdqWeights* d_grads, float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
 int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n_params, int step,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
@@ -186,11 +224,15 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
  * order, so all replicas get identical bits), scales by 1/world, updates its slice of d_m / d_v
  * (optimizer state is sharded: only the owned slice of those arrays is meaningful), writes the new
  * parameters into every rank's parameter buffer and zeroes the consumed gradients on every rank.
- * *d_step (device int32, Adam's t) is incremented by the call; d_grid_bar = 2 zero-initialised
- * device uint32 that belong to this group and are never reset.  n_params_padded = parameter count
+ * *d_step (device int32, Adam's t) is incremented by the call; d_grid_bar = 4 zero-initialised
+ * device uint32 that belong to this group and are never reset ([0] arrivals, [1] launch generation,
+ * [2] sticky time-out flag, [3] reserved).  n_params_padded = parameter count
  * rounded up to a multiple of 4 (padding elements stay zero).  world = 1 is the single-GPU fused
  * Adam step with a device-side step counter (CUDA-graph friendly).  All ranks must call it once
- * per step; a peer that never arrives traps the waiting kernel (no silent hang). */
+ * per step and reach it within option "dp_timeout_s" of wall clock (default 600 s) of each other: a rank
+ * whose wait runs out skips its update, sets d_grid_bar[2] and returns normally -- nothing traps, the CUDA
+ * context stays usable -- and cdq_dp_adam_status (synchronises `stream`) reports CDQ_E_TIMEOUT; parameters
+ * and optimizer state are then undefined and must be reloaded from a checkpoint. */
 #define CDQ_MAX_RANKS 8
 typedef struct CdqDpPeers {
     float* params[CDQ_MAX_RANKS];
@@ -199,6 +241,7 @@ typedef struct CdqDpPeers {
 } CdqDpPeers;
 int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, float* d_v, int64_t n_params_padded,
                      int32_t* d_step, uint32_t* d_grid_bar, float lr, float beta1, float beta2, float eps, void* stream);
+int cdq_dp_adam_status(const uint32_t* d_grid_bar, void* stream);
 /* CUDA IPC plumbing for the above: allocate a zeroed device region and export its 64-byte handle;
  * map a peer's handle; unmap; free. */
 int cdq_ipc_alloc(size_t bytes, void** d_ptr, void* handle64);

@@ -142,11 +142,20 @@ def attack_maps(boards):
     return out
 
 
-def leaf_value(flags, net_value):
-    """mcts.py:196-232: terminal short-circuits, else clamp(net, -1, 1).  `flags` as cdq.h."""
-    flags = np.asarray(flags)
-    v = np.clip(np.asarray(net_value, np.float32), -1.0, 1.0)
-    # checkmate: -1 if white to move else +1.  Turn is not in flags; callers pass it via boards.
+def leaf_values(boards, flags, score=None, net_value=None):
+    """_evaluate_position (mcts.py:196-232) for a batch: checkmate -> -1.0 if white is to move else +1.0
+    (:202-203); stalemate / insufficient material / threefold repetition -> 0.0 (:205-210); else
+    clamp(net value, -1, 1) (:213-221) or, without a network, math.tanh(score / 10) (:226-229).
+    `flags` as cdq.h (low three bits = CDQ_TERM_*), turn from the boards' meta bit 0."""
+    import math
+    flags = np.asarray(flags).astype(np.uint32)
+    term = flags & 7
+    white = (np.asarray(boards)["meta"] & 1).astype(bool)
+    if net_value is not None:
+        v = np.clip(np.asarray(net_value, np.float32).reshape(-1), -1.0, 1.0).astype(np.float64)
+    else:
+        v = np.array([math.tanh(float(x) / 10.0) for x in np.asarray(score)], np.float64)
+    v = np.where(term == 1, np.where(white, -1.0, 1.0), np.where(term != 0, 0.0, v))
     return v
 
 
@@ -191,25 +200,77 @@ def net_forward(params, planes, return_acts=False):
     return out.numpy()
 
 
-def dqn_step_reference(params, target_params, states_planes, next_planes, reward, done, gamma=0.99, huber=False):
+def _fp16_emulation():
+    """Autograd helpers that restate WHERE the CUDA training path rounds to fp16:
+    rq = round an operand (weights, stored activations) to fp16 in the forward pass, identity backward;
+    gq(x, scale) = identity forward, the gradient flowing back through x is rounded to fp16 after being
+    multiplied by `scale` (gradients travel between the kernels as fp16 scaled by 64 n)."""
+    import torch
+
+    class RQ(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x.half().float()
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    class GQ(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, scale):
+            ctx.scale = scale
+            return x.view_as(x)
+
+        @staticmethod
+        def backward(ctx, g):
+            return (g * ctx.scale).half().float() / ctx.scale, None
+
+    return RQ.apply, GQ.apply
+
+
+def dqn_step_reference(params, target_params, states_planes, next_planes, reward, done, gamma=0.99, huber=False,
+                       fp16_operands=False, upstream=None):
     """Restatement of DQNAgent.train()'s maths (neural_network.py:232-245) with fp32 torch-CPU
-    autograd: returns (loss float, {name: gradient ndarray})."""
+    autograd: returns (loss float, {name: gradient ndarray}).
+
+    fp16_operands=True restates the CUDA path's arithmetic instead of the reference's: conv / fc1
+    weights and conv1's bias, ReLU(conv1) and ReLU(conv2) rounded to fp16 where the kernels store them
+    as fp16 operands, fp32 accumulation, and the two inter-kernel gradients (fc1's and conv2's
+    pre-activation gradients) rounded to fp16 at scale 64 n.  What is left between this and the kernels
+    is fp32 summation order, so gradients can be compared element by element at ~1e-3 relative.
+    upstream: instead of the DQN loss, backpropagate sum(q * upstream) (CDQ_LOSS_UPSTREAM)."""
     import torch
     import torch.nn.functional as F
+    n = len(states_planes)
+    rq, gq = _fp16_emulation()
+    ident = lambda x, *a: x  # noqa: E731
+    r_, g_ = (rq, gq) if fp16_operands else (ident, ident)
+    scale = 64.0 * (1.0 if upstream is not None else float(n))
 
-    def fwd(t, x):
-        a1 = F.relu(F.conv2d(x, t["conv1.weight"], t["conv1.bias"], padding=1))
-        a2 = F.relu(F.conv2d(a1, t["conv2.weight"], t["conv2.bias"], padding=1))
-        h = F.relu(F.linear(a2.reshape(-1, 4096), t["fc1.weight"], t["fc1.bias"]))
+    def fwd(t, x, train):
+        z1 = F.conv2d(x, r_(t["conv1.weight"]), r_(t["conv1.bias"]), padding=1)
+        a1 = r_(F.relu(z1))
+        z2 = F.conv2d(a1, r_(t["conv2.weight"]), t["conv2.bias"], padding=1)
+        if train:
+            z2 = g_(z2, scale)
+        a2 = r_(F.relu(z2))
+        z3 = F.linear(a2.reshape(-1, 4096), r_(t["fc1.weight"]), t["fc1.bias"])
+        if train:
+            z3 = g_(z3, scale)
+        h = F.relu(z3)
         return torch.tanh(F.linear(h, t["fc2.weight"], t["fc2.bias"]))
 
     t = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
-    tt = {k: torch.tensor(v) for k, v in target_params.items()}
-    q = fwd(t, torch.as_tensor(states_planes)).squeeze()
-    with torch.no_grad():
-        qn = fwd(tt, torch.as_tensor(next_planes)).squeeze()
-    y = torch.as_tensor(reward) + (1 - torch.as_tensor(done)) * gamma * qn
-    loss = F.huber_loss(q, y) if huber else F.mse_loss(q, y)
+    q = fwd(t, torch.as_tensor(states_planes), True).reshape(-1)
+    if upstream is not None:
+        loss = (q * torch.as_tensor(upstream, dtype=torch.float32)).sum()
+    else:
+        tt = {k: torch.tensor(v) for k, v in target_params.items()}
+        with torch.no_grad():
+            qn = fwd(tt, torch.as_tensor(next_planes), False).reshape(-1)
+        y = torch.as_tensor(reward) + (1 - torch.as_tensor(done)) * gamma * qn
+        loss = F.huber_loss(q, y) if huber else F.mse_loss(q, y)
     loss.backward()
     return float(loss.detach()), {k: v.grad.numpy().copy() for k, v in t.items()}
 

@@ -25,7 +25,7 @@ for n in [1, 2, 3, 4, 5, 16, 17, 203, 256]:
     grads = _weights_struct([gv[k] for k in PARAM_ORDER])
     ws, loss = _scratch.get(n, sd.device)
     opt.zero_grad(); loss.zero_()
-    _lib.check(_lib.lib().cdq_train_fwd_bwd(q_net.net_handle(), t_net.net_handle(), ctypes.byref(weights), sd.data_ptr(), nsd.data_ptr(), rd.data_ptr(), dd.data_ptr(), n, 0.99, 0, ctypes.byref(grads), loss.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    _lib.check(_lib.lib().cdq_train_fwd_bwd(q_net.net_handle(), t_net.net_handle(), ctypes.byref(weights), sd.data_ptr(), nsd.data_ptr(), rd.data_ptr(), dd.data_ptr(), n, 0.0, 0.99, 0, ctypes.byref(grads), loss.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     torch.cuda.synchronize()
     out = ["n=%d loss %.3e/%.3e" % (n, float(loss.item()), float(ref_loss))]
     for k in PARAM_ORDER:

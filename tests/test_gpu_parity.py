@@ -197,13 +197,13 @@ def test_value_ragged_batch_sizes(cdq, oracle, n):
     assert np.abs(v - ref).max() <= 1e-3
 
 
-def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle, monkeypatch):
+def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle):
     """The stream conv kernel hands tiles between five warp roles through ~50 mbarriers; a missing
     fence or a slot reused too early would show up as run-to-run or placement-dependent bits.
     Twelve repetitions and evaluations of shifted sub-ranges (other tile / CTA assignment, other
     ring phases) must reproduce every value bit for bit.  Batches of at most 8 192 positions take
     the cluster split-K fc kernel (fc_split_kernel.cu), whose fp32 summation order differs from the
-    persistent kernel's: with CDQ_FC_SPLIT=0 they must reproduce the large batch's bits as well,
+    persistent kernel's: with option "fc_split" = 0 they must reproduce the large batch's bits as well,
     with the split kernel they must agree to fp32 rounding and be bitwise stable among themselves."""
     n = 200_000
     d = _dev_playouts(cdq, n, seed=9)
@@ -216,11 +216,13 @@ def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle, monkeypatch):
         for off, cnt in [(17, 70_001), (12_345, 132_608), (99_999, 100_001), (777, 8193)]:
             v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
             assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
-        monkeypatch.setenv("CDQ_FC_SPLIT", "0")
-        for off, cnt in small:
-            v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
-            assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
-        monkeypatch.delenv("CDQ_FC_SPLIT")
+        old = cdq._lib.set_option("fc_split", 0)
+        try:
+            for off, cnt in small:
+                v = net.forward_packed(d[off:off + cnt].contiguous()).reshape(-1)
+                assert torch.equal(v, ref[off:off + cnt]), (off, cnt)
+        finally:
+            cdq._lib.set_option("fc_split", old)
         split_ref = net.forward_packed(d[:8192].contiguous()).reshape(-1).clone()
         assert (split_ref - ref[:8192]).abs().max().item() <= 5e-6      # |value| up to 0.99 with these weights
         for _ in range(12):
@@ -230,8 +232,8 @@ def test_value_bitwise_stable_across_runs_and_offsets(cdq, oracle, monkeypatch):
             assert torch.equal(v, split_ref[off:off + cnt]), (off, cnt)
 
 
-def test_pipe_kernel_equals_two_kernel_path(cdq, oracle, monkeypatch):
-    """With CDQ_PIPE=1 large batches run conv and fc as one persistent kernel with an L2-resident
+def test_pipe_kernel_equals_two_kernel_path(cdq, oracle):
+    """With option "pipe" = 1 (CDQ_PIPE=1) large batches run conv and fc as one persistent kernel with an L2-resident
     hand-over (pipe_kernel.cu); the default is the two stand-alone kernels.  Same tiles, same MMAs, same
     epilogues: leaf values, raw values, scores and flags must agree bit for bit, for sizes around
     the ring (64 tiles of 128 positions) and the role split."""
@@ -239,30 +241,84 @@ def test_pipe_kernel_equals_two_kernel_path(cdq, oracle, monkeypatch):
     ev = cdq.LeafEvaluator(net)
     for n in (524_288, 540_001, 64 * 128 * 67 + 5):
         d = _dev_playouts(cdq, n, seed=n)
-        monkeypatch.setenv("CDQ_PIPE", "0")
-        a = ev.evaluate_device(d, want_raw=True)
-        monkeypatch.setenv("CDQ_PIPE", "1")
-        b = ev.evaluate_device(d, want_raw=True)
-        c = ev.evaluate_device(d, want_raw=True)
+        old = cdq._lib.set_option("pipe", 0)
+        try:
+            a = ev.evaluate_device(d, want_raw=True)
+            cdq._lib.set_option("pipe", 1)
+            b = ev.evaluate_device(d, want_raw=True)
+            c = ev.evaluate_device(d, want_raw=True)
+        finally:
+            cdq._lib.set_option("pipe", old)
         for k in ("leaf", "value", "score", "flags"):
             assert torch.equal(a[k], b[k]), (n, k)
             assert torch.equal(b[k], c[k]), (n, k)
 
 
-def test_fc_pairs_kernel_equals_single_tile_kernel(cdq, oracle, monkeypatch):
-    """Large batches run the fc head with two position tiles per weight stage (fc_head_pairs_kernel);
-    CDQ_FC_PAIRS=0 selects one tile per stage.  Same UMMAs in the same K order per tile: bit-identical
-    values, for even and odd tile counts and a ragged last tile."""
+def test_leaf_eval_without_a_network_is_the_heuristic_branch(cdq, oracle, eval_golden):
+    """mcts.py:226-229: `neural_net is None` -> tanh(fast_evaluate_position(board) / 10) behind the terminal
+    rules of :202-210.  Device fp64 tanh against libm's math.tanh: 1e-6 after rounding to the fp32 leaf
+    array (SURVEY 8b's tolerance class); terminal values exact; host path == device path."""
+    g = eval_golden
+    ev = cdq.LeafEvaluator(None)
+    out = ev.evaluate_device(g["boards"])
+    leaf = _np(out["leaf"]).astype(np.float64)
+    assert np.array_equal(_np(out["score"]), g["score"])
+    want = oracle.leaf_values(g["boards"], g["terminal"], score=g["score"])
+    term = g["terminal"] != 0
+    assert np.array_equal(leaf[term], want[term])
+    assert np.abs(leaf - want).max() <= 1e-6
+    boards = oracle.playouts(5000, seed=4)
+    _, sc, fl = oracle.evaluate(boards, nthreads=0)
+    out = ev.evaluate_device(boards)
+    assert np.abs(_np(out["leaf"]).astype(np.float64) - oracle.leaf_values(boards, fl, score=sc)).max() <= 1e-6
+    host = ev.evaluate_host(boards)
+    assert np.array_equal(host["leaf"], _np(out["leaf"])) and np.array_equal(host["score"], sc)
+    assert cdq.evaluate_position(boards[:1]) == pytest.approx(float(oracle.leaf_values(boards[:1], fl[:1], score=sc[:1])[0]), abs=1e-6)
+    with pytest.raises(cdq._lib.CdqError):
+        ev.evaluate_device(boards, want_raw=True)
+
+
+def test_host_contexts_are_independent_and_options_round_trip(cdq, oracle):
+    """cdq_host_ctx_*: two explicit contexts used from two threads at once give the results of the
+    default per-device context; cdq_set_option / cdq_get_option round-trip and reject unknown names."""
+    import ctypes
+    import threading
+    L = cdq._lib.lib()
     net, _ = _make_net(cdq, oracle, 2.0)
-    ev = cdq.LeafEvaluator(net)
-    for n in (65 * 128, 66 * 128 + 77, 300_001):
-        d = _dev_playouts(cdq, n, seed=n)
-        monkeypatch.setenv("CDQ_FC_PAIRS", "0")
-        a = ev.evaluate_device(d, want_raw=True)
-        monkeypatch.delenv("CDQ_FC_PAIRS")
-        b = ev.evaluate_device(d, want_raw=True)
-        for k in ("leaf", "value", "score", "flags"):
-            assert torch.equal(a[k], b[k]), (n, k)
+    boards = oracle.playouts(70_000, seed=12)
+    ref = cdq.LeafEvaluator(net).evaluate_host(boards)
+    handle = net.net_handle()
+    torch.cuda.synchronize()
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            ctx = ctypes.c_void_p()
+            cdq._lib.check(L.cdq_host_ctx_create(ctypes.byref(ctx)))
+            leaf = np.empty(len(boards), np.float32)
+            score = np.empty(len(boards), np.float64)
+            flags = np.empty(len(boards), np.uint32)
+            for _ in range(3):
+                cdq._lib.check(L.cdq_leaf_eval_host_ctx(ctx, handle, boards.ctypes.data, len(boards), leaf.ctypes.data,
+                                                        score.ctypes.data, flags.ctypes.data))
+            L.cdq_host_ctx_destroy(ctx)
+            results[i] = (leaf, score, flags)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    for leaf, score, flags in results:
+        assert np.array_equal(leaf, ref["leaf"]) and np.array_equal(score, ref["score"]) and np.array_equal(flags, ref["flags"])
+    old = cdq._lib.set_option("host_ramp", 0)
+    assert old == 1 and cdq._lib.set_option("host_ramp", 1) == 0
+    assert L.cdq_set_option(b"no_such_option", 1) == -1
+    L.cdq_host_release()
+    again = cdq.LeafEvaluator(net).evaluate_host(boards)      # the default context is rebuilt on demand
+    assert np.array_equal(again["leaf"], ref["leaf"])
 
 
 def test_repack_after_weight_update(cdq, oracle):

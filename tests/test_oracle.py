@@ -129,3 +129,23 @@ def test_eval_matches_reference_on_arbitrary_positions(oracle):
     has = g["has_terms"]
     assert has.sum() > 200
     assert np.array_equal(terms[has][:, :23], g["terms"][has][:, :23])
+
+
+def test_python_path_restatement_reproduces_the_reference_scores(oracle, eval_golden):
+    """oracle/py_eval.py (the Python-path CPU baseline of bench.py) against the scores recorded from the
+    reference's unmodified evaluation.py: bit for bit, with and without ignore_checkmate; its plane
+    encoding against the reference's board_to_tensor planes."""
+    import py_eval
+    g = eval_golden
+    idx = list(range(0, 60)) + list(range(60, len(g["boards"]), 23))
+    for i in idx:
+        if g["boards"][i]["meta"] & (1 << 16):
+            continue                                    # rep3 comes from history, which a record does not carry
+        b = py_eval.unpack_board(g["boards"][i])
+        assert py_eval.fast_evaluate_position(b) == g["score"][i], i
+        assert py_eval.fast_evaluate_position(b, ignore_checkmate=True) == g["score_ignore_checkmate"][i], i
+    planes = oracle.encode_planes(g["boards"][:40])
+    for i in range(40):
+        assert np.array_equal(py_eval.board_to_planes(py_eval.unpack_board(g["boards"][i])), planes[i])
+    v, sec, scores = py_eval.python_path_throughput(g["boards"][100:132], processes=2)
+    assert np.array_equal(scores, g["score"][100:132]) and v > 0
