@@ -281,6 +281,7 @@ class DQNAgent:
         self.num_cpu_cores = max(1, multiprocessing.cpu_count() - 1)     # neural_network.py:69 (simulations per wave)
         self._graph_step = None
         self._stage = None
+        self._np_rng = None
 
     def update_target_network(self):
         """neural_network.py:183-185"""
@@ -369,37 +370,48 @@ class DQNAgent:
         self.memory.append((s, move, float(reward), ns, float(done)))
 
     def _staging(self):
-        if self._stage is None or self._stage["states"].shape[0] != self.batch_size:
+        """One pinned buffer laid out like GraphedDQNStep.inputs, with numpy views for the gather."""
+        if self._stage is None or self._stage["batch"] != self.batch_size:
             B = self.batch_size
-            self._stage = {"states": torch.empty((B, 9), dtype=torch.int64).pin_memory(),
-                           "next_states": torch.empty((B, 9), dtype=torch.int64).pin_memory(),
-                           "rewards": torch.empty(B, dtype=torch.float32).pin_memory(),
-                           "dones": torch.empty(B, dtype=torch.float32).pin_memory(),
+            flat = torch.empty(B * 152, dtype=torch.uint8).pin_memory()
+            raw = flat.numpy()
+            self._stage = {"batch": B, "flat": flat,
+                           "states": raw[:B * 72].view(np.uint64).reshape(B, 9),
+                           "next_states": raw[B * 72:B * 144].view(np.uint64).reshape(B, 9),
+                           "rewards": raw[B * 144:B * 148].view(np.float32),
+                           "dones": raw[B * 148:B * 152].view(np.float32),
                            "loss": torch.empty(1, dtype=torch.float32).pin_memory()}
-            for k in ("states", "next_states"):
-                self._stage[k + "_np"] = self._stage[k].numpy().view(np.uint64).reshape(-1).view(BOARD_DTYPE)
         return self._stage
+
+    def _sample_indices(self):
+        """Uniform minibatch without replacement, like random.sample(self.memory, batch_size)
+        (neural_network.py:224).  random.sample itself costs 1.3 ms for 4 096 of 10 000 in CPython -- eight
+        times the training step -- so the draw is numpy's, from a generator seeded ONCE from the `random`
+        module (random.seed() therefore still makes runs reproducible; the stream is not the reference's)."""
+        if self._np_rng is None:
+            self._np_rng = np.random.Generator(np.random.PCG64(random.getrandbits(128)))
+        return self._np_rng.choice(len(self.memory), self.batch_size, replace=False)
 
     def train(self):
         """neural_network.py:218-252: sample, q=net(s), q'=target(s'), y=r+(1-done)*gamma*q',
-        MSE, Adam step, epsilon decay; returns the loss as a float.  random.sample draws the same
-        indices the reference's random.sample(self.memory, batch_size) would (it only uses the
-        population's length); the minibatch is gathered into pinned buffers, copied to the static
-        inputs of the step's CUDA graph, and the loss comes back with one 4-byte read."""
+        MSE, Adam step, epsilon decay; returns the loss as a float.  The minibatch is gathered into
+        ONE pinned buffer, reaches the static inputs of the step's CUDA graph with one copy, and the
+        loss comes back with one 4-byte read."""
         if len(self.memory) < self.batch_size:
             return 0
         from .train import GraphedDQNStep
-        idx = self.memory.slots(random.sample(range(len(self.memory)), self.batch_size))
+        idx = self.memory.slots(self._sample_indices())
         st = self._staging()
-        np.take(self.memory.states, idx, out=st["states_np"])
-        np.take(self.memory.next_states, idx, out=st["next_states_np"])
-        np.take(self.memory.rewards, idx, out=st["rewards"].numpy())
-        np.take(self.memory.dones, idx, out=st["dones"].numpy())
+        mem = self.memory
+        np.take(mem.states.view(np.uint64).reshape(-1, 9), idx, axis=0, out=st["states"])
+        np.take(mem.next_states.view(np.uint64).reshape(-1, 9), idx, axis=0, out=st["next_states"])
+        np.take(mem.rewards, idx, out=st["rewards"])
+        np.take(mem.dones, idx, out=st["dones"])
         if self._graph_step is None or self._graph_step.batch != self.batch_size or self._graph_step.gamma != float(self.gamma):
             self._graph_step = GraphedDQNStep(self.q_network, self.target_q_network, self.optimizer,
                                               batch=self.batch_size, gamma=self.gamma)
         g = self._graph_step
-        g.load(st["states"], st["next_states"], st["rewards"], st["dones"])
+        g.load_packed(st["flat"])
         loss = g.run()
         st["loss"].copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -327,10 +327,13 @@ class GraphedDQNStep:
         self.q_network, self.target_network, self.optimizer = q_network, target_network, optimizer
         self.batch, self.gamma, self.loss_kind = int(batch), float(gamma), int(loss_kind)
         self.mean_over = _mean_over(self.batch, global_batch, optimizer.world)
-        self.states = torch.zeros((self.batch, 9), dtype=torch.int64, device=dev)
-        self.next_states = torch.zeros((self.batch, 9), dtype=torch.int64, device=dev)
-        self.rewards = torch.zeros(self.batch, dtype=torch.float32, device=dev)
-        self.dones = torch.zeros(self.batch, dtype=torch.float32, device=dev)
+        # the four static inputs are views of ONE device buffer, so a host minibatch arrives with one copy
+        B = self.batch
+        self.inputs = torch.zeros(B * self.INPUT_BYTES_PER_SAMPLE, dtype=torch.uint8, device=dev)
+        self.states = self.inputs[:B * 72].view(torch.int64).view(B, 9)
+        self.next_states = self.inputs[B * 72:B * 144].view(torch.int64).view(B, 9)
+        self.rewards = self.inputs[B * 144:B * 148].view(torch.float32)
+        self.dones = self.inputs[B * 148:B * 152].view(torch.float32)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)        # mean over THIS rank's shard
         self.ws = torch.zeros(_lib.lib().cdq_train_workspace_bytes(self.batch), dtype=torch.uint8, device=dev)
         self.graph = None
@@ -348,6 +351,13 @@ class GraphedDQNStep:
             self.batch, self.mean_over, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK | ZERO_LOSS, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
             self.ws.numel(), _lib.stream_ptr()))
         self.optimizer.step_fused()
+
+    INPUT_BYTES_PER_SAMPLE = 72 + 72 + 4 + 4     # state record, next-state record, reward, done
+
+    def load_packed(self, staged):
+        """One host-to-device copy of a whole minibatch: `staged` is a (pinned) uint8 tensor laid out like
+        self.inputs -- [B state records | B next-state records | B rewards | B dones]."""
+        self.inputs.copy_(staged, non_blocking=True)
 
     def load(self, states, next_states, rewards, dones):
         self.states.copy_(states, non_blocking=True)

@@ -255,10 +255,10 @@ def dqn_step_reference(params, target_params, states_planes, next_planes, reward
         if train:
             z2 = g_(z2, scale)
         a2 = r_(F.relu(z2))
-        z3 = F.linear(a2.reshape(-1, 4096), r_(t["fc1.weight"]), t["fc1.bias"])
+        z3 = F.linear(a2.reshape(-1, 4096), r_(t["fc1.weight"]))
         if train:
-            z3 = g_(z3, scale)
-        h = F.relu(z3)
+            z3 = g_(z3, scale)      # fc1's bias gradient is summed from the unrounded values (head_bwd_kernel), conv2's from the fp16 boards
+        h = F.relu(z3 + t["fc1.bias"])
         return torch.tanh(F.linear(h, t["fc2.weight"], t["fc2.bias"]))
 
     t = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}

@@ -249,15 +249,26 @@ def test_graphed_step_equals_eager_step(cdq, oracle, eval_golden, train_golden):
     assert np.abs(va - vb).max() <= 1e-6
 
 
-def _elementwise_rel_check(name, g, ref, rel=2e-3, floor=1e-3):
-    """Every element with |ref| > floor * max|ref| within `rel` relative; the rest within rel * floor * max|ref| absolute."""
-    m = np.abs(ref).max()
-    big = np.abs(ref) > floor * m
-    err = np.abs(g - ref)
-    worst_rel = float((err[big] / np.abs(ref[big])).max()) if big.any() else 0.0
-    worst_abs = float(err[~big].max()) if (~big).any() else 0.0
-    assert worst_rel <= rel, (name, "relative", worst_rel)
-    assert worst_abs <= rel * floor * m * 4 + 1e-12, (name, "absolute", worst_abs, m)
+def _elementwise_check(name, g, ref, max_bar=5e-4, p99_bar=2e-4, rel_p99_bar=1e-2):
+    """Every element of one gradient tensor against the fp16-operand oracle.  Normalised by max|ref| of the
+    tensor: worst element <= 5e-4, 99th percentile <= 2e-4 (measured <= 2.3e-4 / 8e-5, against 4e-3 ... 1e-1 for
+    the fp32 comparison: profiles/r2_grad_parity_probe.txt).  Per element RELATIVE error where |ref| > 1e-3 max|ref|:
+    99th percentile <= 1e-2 (measured <= 4.7e-3).  No tighter per-element relative bar exists for this arithmetic: a
+    ReLU input within fp32 summation-order noise of zero flips its 0/1 backward mask between two correct
+    evaluations and moves one term of a sum, which is O(1e-4 max|g|) absolute on elements that are themselves
+    1e-3 max|g| -- the outliers are exactly those (99.9 % of fc1.weight's 1M elements agree to 1.5e-5 relative)."""
+    g, ref = g.reshape(-1), ref.reshape(-1)
+    m = float(np.abs(ref).max())
+    if m == 0.0:
+        assert float(np.abs(g).max()) == 0.0, name
+        return
+    err = np.abs(g - ref) / m
+    assert float(err.max()) <= max_bar, (name, "max", float(err.max()))
+    assert float(np.quantile(err, 0.99)) <= p99_bar, (name, "p99", float(np.quantile(err, 0.99)))
+    big = np.abs(ref) > 1e-3 * m
+    if big.sum() >= 100:
+        rel = np.abs(g - ref)[big] / np.abs(ref)[big]
+        assert float(np.quantile(rel, 0.99)) <= rel_p99_bar, (name, "relative p99", float(np.quantile(rel, 0.99)))
 
 
 @pytest.mark.parametrize("n,scale", [(4096, 2.0), (203, 2.0), (17, 3.0), (1, 1.0)])
@@ -265,8 +276,8 @@ def test_every_gradient_element_matches_the_fp16_operand_oracle(cdq, oracle, n, 
     """The fp32 comparison above mixes two things: the fp16 operand rounding the design chose and
     possible kernel bugs.  oracle.dqn_step_reference(fp16_operands=True) restates exactly where the
     CUDA path rounds (weights, ReLU(conv1), ReLU(conv2), the two inter-kernel gradients at scale
-    64 n), so what is left is fp32 summation order: EVERY element of EVERY gradient tensor with
-    |g| > 1e-3 max|g| must agree to 2e-3 relative (measured ~1e-4), also for ragged batches."""
+    64 n), so what is left is fp32 summation order (and the ReLU masks it can flip): EVERY element of EVERY
+    gradient tensor is checked (_elementwise_check), also for ragged batches; the loss to 1e-5 relative."""
     from chess_deep_q_b200.train import FusedAdam, PARAM_ORDER
     boards = oracle.playouts(n + 1, seed=1000 + n)
     _, sc, fl = oracle.evaluate(boards[1:], nthreads=0)
@@ -278,10 +289,10 @@ def test_every_gradient_element_matches_the_fp16_operand_oracle(cdq, oracle, n, 
     loss = float(_run_step(cdq, q_net, t_net, opt, boards[:n], boards[1:], r, d).item())
     ref_loss, ref = oracle.dqn_step_reference(p, pt, oracle.encode_planes(boards[:n]), oracle.encode_planes(boards[1:]),
                                               r, d, fp16_operands=True)
-    assert loss == pytest.approx(ref_loss, rel=1e-4, abs=1e-9)
+    assert loss == pytest.approx(ref_loss, rel=1e-5, abs=1e-9)
     gv = opt.grad_views()
     for k in PARAM_ORDER:
-        _elementwise_rel_check(k, gv[k].cpu().numpy(), ref[k])
+        _elementwise_check(k, gv[k].cpu().numpy(), ref[k])
 
 
 def test_autograd_surface_of_the_forward(cdq, oracle):
@@ -305,12 +316,14 @@ def test_autograd_surface_of_the_forward(cdq, oracle):
     loss = F.mse_loss(q, target)
     loss.backward()
     up = (2.0 / n) * (q.detach() - target).reshape(-1).cpu().numpy()
-    for fp16, rel in ((True, 2e-3), (False, None)):
-        _, ref = oracle.dqn_step_reference(p, None, oracle.encode_planes(boards), None, None, None, fp16_operands=fp16, upstream=up)
+    for fp16 in (True, False):
+        gmax = float(np.abs(up).max())          # the autograd Function normalises the upstream gradient before the fp16 kernels
+        _, ref = oracle.dqn_step_reference(p, None, oracle.encode_planes(boards), None, None, None, fp16_operands=fp16, upstream=up / gmax)
+        ref = {k: v * gmax for k, v in ref.items()}
         for k, prm in zip(PARAM_ORDER, net._params()):
             g = prm.grad.cpu().numpy()
             if fp16:
-                _elementwise_rel_check(k, g, ref[k], rel=rel)
+                _elementwise_check(k, g, ref[k])
             else:
                 assert np.abs(g - ref[k]).max() <= 1e-1 * np.abs(ref[k]).max() + 1e-9, k
     before = net.fc2.bias.detach().clone()
@@ -356,11 +369,12 @@ def test_dqn_agent_train_is_the_graphed_step_and_matches_the_eager_one(cdq, orac
     a, b = agents
     assert len(a.memory) == 300 and a.memory[7][1] == 7 and len(list(a.memory)) == 300
     to_dev = cdq.board_utils.to_device
+    random.seed(100)
     for it in range(3):
-        random.seed(100 + it)
         la = a.train()
-        random.seed(100 + it)
-        idx = b.memory.slots(random.sample(range(len(b.memory)), b.batch_size))
+        if it == 0:
+            random.seed(100)
+        idx = b.memory.slots(b._sample_indices())
         lb = float(dqn_train_step(b.q_network, b.target_q_network, b.optimizer, to_dev(b.memory.states[idx]),
                                   to_dev(b.memory.next_states[idx]), torch.from_numpy(b.memory.rewards[idx]).cuda(),
                                   torch.from_numpy(b.memory.dones[idx]).cuda(), b.gamma).item())
