@@ -47,6 +47,13 @@ SIGNATURES = {
     "cdq_expand_weighted": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cdq_sample_children": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "cdq_forest_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "cdq_forest_destroy": (None, [c_void_p]),
+    "cdq_forest_set_games": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "cdq_forest_set_active": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cdq_forest_search": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_float, ctypes.c_float, c_int, c_void_p]),
+    "cdq_forest_advance": (c_int, [c_void_p, c_void_p]),
+    "cdq_forest_view": (c_int, [c_void_p, c_void_p]),
     "cdq_launch_count": (c_uint64, []),
     "cdq_profile_enable": (None, [c_int]),
     "cdq_profile_collect": (c_int, [c_void_p, c_void_p]),
@@ -57,6 +64,18 @@ SIGNATURES = {
 
 class CdqWeights(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class CdqForestConfig(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n_games", "workers", "depth", "width", "max_iterations")]
+
+
+class CdqForestView(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n_games", "workers", "depth", "width", "max_nodes")] + \
+               [(k, c_void_p) for k in ("game_boards", "game_halfmove_clock", "game_ply", "game_active", "game_status",
+                                        "game_history_len", "best_move", "best_visits", "root_children", "edge_move",
+                                        "edge_visits", "edge_value", "node_children", "node_count", "leaf_boards",
+                                        "leaf_values", "leaf_depth", "positions_evaluated")]
 
 
 MAX_RANKS = 8

@@ -8,144 +8,10 @@
 // (counter-based splitmix64 keyed by (seed, i, ply)); stops early when there is no legal move or
 // the material is insufficient.  Reference context: games cap at 200 plies (chess_ai.py:117) and
 // the reference seeds everything with 42 (main.py:19-21).
-#include "bitboard.cuh"
+#include "movegen.cuh"
 #include "common.cuh"
 
 namespace cdq {
-
-__device__ __forceinline__ u64 mix64(u64 z) {
-    z += 0x9e3779b97f4a7c15ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-
-__device__ __forceinline__ int nth_bit(u64 b, int k) {
-    for (int i = 0; i < k; i++) b &= b - 1;
-    return lsb_sq(b);
-}
-
-enum { MV_NORMAL = 0, MV_CASTLE_K = 1, MV_CASTLE_Q = 2, MV_EP = 3, MV_DOUBLE = 4 };
-enum { PT_P = 0, PT_N = 1, PT_B = 2, PT_R = 3, PT_Q = 4, PT_K = 5 };
-
-struct SelectVisitor {
-    int r;           // index of the wanted move among the remaining classes
-    bool found = false;
-    int from = 0, to = 0, promo = -1, special = MV_NORMAL;
-    u64 occ;
-    bool white;
-
-    __device__ SelectVisitor(int r_, u64 occ_, bool w) : r(r_), occ(occ_), white(w) {}
-
-    __device__ __forceinline__ bool pick(u64 t, int mult, int& sq, int& sub) {
-        if (found) return false;
-        const int c = popc(t) * mult;
-        if (r >= c) { r -= c; return false; }
-        sq = nth_bit(t, r / mult);
-        sub = r % mult;
-        found = true;
-        return true;
-    }
-    template <int D> __device__ __forceinline__ void slide(u64 t) {
-        int sq, sub;
-        if (!pick(t, 1, sq, sub)) return;
-        to = sq;
-        const int delta = Dir<D>::left ? Dir<D>::s : -Dir<D>::s;
-        int f = sq - delta;
-        while (!((occ >> f) & 1)) f -= delta; // origin = first piece behind the target
-        from = f;
-    }
-    template <int J> __device__ __forceinline__ void knight(u64 t) {
-        int sq, sub;
-        if (!pick(t, 1, sq, sub)) return;
-        to = sq; from = sq - knight_delta(J);
-    }
-    u64 king_bb = 0;
-    __device__ __forceinline__ void king(u64 t) {
-        int sq, sub;
-        if (!pick(t, 1, sq, sub)) return;
-        to = sq; from = lsb_sq(king_bb);
-    }
-    __device__ __forceinline__ void pawn_to(u64 t, int delta, int sp) {
-        const u64 last = RANK_1 | RANK_8;
-        int sq, sub;
-        if (pick(t & ~last, 1, sq, sub)) { to = sq; from = sq - delta; special = sp; return; }
-        if (pick(t & last, 4, sq, sub)) { to = sq; from = sq - delta; promo = PT_Q - sub; }
-    }
-    __device__ __forceinline__ void pawn_push(u64 s, u64 d) {
-        pawn_to(s, white ? 8 : -8, MV_NORMAL);
-        pawn_to(d, white ? 16 : -16, MV_DOUBLE);
-    }
-    template <int D> __device__ __forceinline__ void pawn_cap(u64 t) {
-        pawn_to(t, Dir<D>::left ? Dir<D>::s : -Dir<D>::s, MV_NORMAL);
-    }
-    __device__ __forceinline__ void castle(bool k, bool q) {
-        int sq, sub;
-        const int e = white ? 4 : 60;
-        if (pick(k ? 1ull : 0ull, 1, sq, sub)) { from = e; to = e + 2; special = MV_CASTLE_K; return; }
-        if (pick(q ? 1ull : 0ull, 1, sq, sub)) { from = e; to = e - 2; special = MV_CASTLE_Q; }
-    }
-    __device__ __forceinline__ void ep(u64 caps, int epsq) {
-        int sq, sub;
-        if (pick(caps, 1, sq, sub)) { from = sq; to = epsq; special = MV_EP; }
-    }
-};
-
-__device__ __forceinline__ u64& type_board(Pos& p, int t) {
-    switch (t) {
-        case PT_P: return p.P; case PT_N: return p.N; case PT_B: return p.B;
-        case PT_R: return p.R; case PT_Q: return p.Q; default: return p.K;
-    }
-}
-
-// Board.push for standard chess on the packed representation (keeps castling rights clean).
-__device__ __forceinline__ void apply_move(Pos& p, const SelectVisitor& m) {
-    const bool white = p.meta & CDQ_META_TURN_WHITE;
-    const int us = white ? 1 : 0, them = us ^ 1;
-    const u64 fb = 1ull << m.from, tb = 1ull << m.to;
-    int pt = PT_K;
-    if (p.P & fb) pt = PT_P; else if (p.N & fb) pt = PT_N; else if (p.B & fb) pt = PT_B;
-    else if (p.R & fb) pt = PT_R; else if (p.Q & fb) pt = PT_Q;
-    // captured piece (if any) leaves
-    p.P &= ~tb; p.N &= ~tb; p.B &= ~tb; p.R &= ~tb; p.Q &= ~tb; p.K &= ~tb;
-    p.co[them] &= ~tb;
-    // mover
-    type_board(p, pt) &= ~fb;
-    p.co[us] &= ~fb;
-    type_board(p, m.promo >= 0 ? m.promo : pt) |= tb;
-    p.co[us] |= tb;
-    if (m.special == MV_EP) {
-        const u64 cap = white ? (tb >> 8) : (tb << 8);
-        p.P &= ~cap; p.co[them] &= ~cap;
-    } else if (m.special == MV_CASTLE_K || m.special == MV_CASTLE_Q) {
-        const int base = white ? 0 : 56;
-        const u64 rf = 1ull << (base + (m.special == MV_CASTLE_K ? 7 : 0));
-        const u64 rt = 1ull << (base + (m.special == MV_CASTLE_K ? 5 : 3));
-        p.R = (p.R & ~rf) | rt;
-        p.co[us] = (p.co[us] & ~rf) | rt;
-    }
-    // meta: flip turn, clear ep, update rights
-    u64 meta = p.meta;
-    meta ^= CDQ_META_TURN_WHITE;
-    meta &= ~(CDQ_META_EP_MASK << CDQ_META_EP_SHIFT);
-    if (m.special == MV_DOUBLE) meta |= (u64)((white ? m.from + 8 : m.from - 8) + 1) << CDQ_META_EP_SHIFT;
-    const u64 touched = fb | tb;
-    if (touched & (1ull << 7)) meta &= ~CDQ_META_CASTLE_WK;
-    if (touched & (1ull << 0)) meta &= ~CDQ_META_CASTLE_WQ;
-    if (touched & (1ull << 63)) meta &= ~CDQ_META_CASTLE_BK;
-    if (touched & (1ull << 56)) meta &= ~CDQ_META_CASTLE_BQ;
-    if (pt == PT_K) meta &= white ? ~(CDQ_META_CASTLE_WK | CDQ_META_CASTLE_WQ) : ~(CDQ_META_CASTLE_BK | CDQ_META_CASTLE_BQ);
-    p.meta = meta;
-}
-
-__device__ __forceinline__ Pos start_position() {
-    Pos p;
-    p.P = 0x00ff00000000ff00ull; p.N = 0x4200000000000042ull; p.B = 0x2400000000000024ull;
-    p.R = 0x8100000000000081ull; p.Q = 0x0800000000000008ull; p.K = 0x1000000000000010ull;
-    p.co[1] = 0xffffull; p.co[0] = 0xffff000000000000ull;
-    p.meta = CDQ_META_TURN_WHITE | CDQ_META_CASTLE_WK | CDQ_META_CASTLE_WQ | CDQ_META_CASTLE_BK | CDQ_META_CASTLE_BQ;
-    return p;
-}
 
 __global__ void __launch_bounds__(128)
 random_playouts_kernel(CdqBoard* __restrict__ boards, long long n, u64 seed, int max_plies) {
@@ -168,44 +34,6 @@ random_playouts_kernel(CdqBoard* __restrict__ boards, long long n, u64 seed, int
         apply_move(p, sv);
     }
     store_pos(p, reinterpret_cast<u64*>(boards) + i * 9);
-}
-
-// Sampling weight of a move, categorize_moves (evaluation.py:232-339): first matching category of
-// capture of a more valuable piece 10, gives check 9, equal capture 8, moves a threatened piece 7,
-// develops a minor piece 6, capture of a less valuable piece 5, to d4/e4/d5/e5 4, castling or a king
-// move from its back rank 3, pawn move 2, other 1.  (An en-passant capture lands on an empty square
-// and is therefore not a "capture" there.)
-__device__ __forceinline__ int piece_value_at(const Pos& p, u64 b) {
-    if (p.P & b) return 1;
-    if ((p.N | p.B) & b) return 3;
-    if (p.R & b) return 5;
-    if (p.Q & b) return 9;
-    return 0;   // king (PIECE_VALUES, evaluation.py:8-15)
-}
-__device__ __forceinline__ int move_category_weight(const Pos& p, const Pos& child, const SelectVisitor& m, u64 att_opp, bool white) {
-    const u64 fb = 1ull << m.from, tb = 1ull << m.to;
-    const u64 occ = p.co[0] | p.co[1];
-    if (occ & tb) {
-        const int vt = piece_value_at(p, tb), vf = piece_value_at(p, fb);
-        return vt > vf ? 10 : (vt == vf ? 8 : 5);
-    }
-    {   // gives check: the child's side to move is attacked on its king square
-        const u64 cocc = child.co[0] | child.co[1];
-        const Props cq = make_props(~cocc);
-        const u64 att_us = white ? attack_map<1>(child, cq) : attack_map<0>(child, cq);
-        if (att_us & child.K & child.co[white ? 0 : 1]) return 9;
-    }
-    if (att_opp & fb) return 7;
-    const int fr = m.from >> 3, ff = m.from & 7;
-    if (((p.N | p.B) & fb) && fr == (white ? 0 : 7) && (ff == 1 || ff == 2 || ff == 5 || ff == 6)) return 6;
-    if (tb & 0x0000001818000000ull) return 4;
-    if (p.K & fb) {
-        const int d = ff - (m.to & 7);
-        if (d > 1 || d < -1) return 3;
-        if (fr == (white ? 0 : 7)) return 3;
-    }
-    if (p.P & fb) return 2;
-    return 1;
 }
 
 // All legal successors of each position (side to move), the building block of a batched tree

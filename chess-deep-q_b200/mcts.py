@@ -78,19 +78,26 @@ def evaluate_position(board, neural_net=None, device=None):
 
 
 # ---------------------------------------------------------------------------------------------
-# batched-leaf Russian Doll MCTS.  Same tree policy as the reference
-# (ParallelRussianDollMCTS, mcts.py:14-194: UCB with the annealed exploration weight, unexplored
-# children first, running-mean backup with a sign flip per ply, best move = most visited root
-# child, depth limit = len(samples_per_level), children per node = samples_per_level[0]), but the
-# simulations advance level by level in waves of `num_workers` (the reference's thread count): every
-# level of a wave costs one device expansion (cdq_expand) and the wave's leaves cost one
-# cdq_leaf_eval, instead of one batch-1 network call per simulation under the GIL.
-# Children are sampled like select_weighted_moves does, on the device: tactical weights of
-# categorize_moves from cdq_expand_weighted, the weighted draw without replacement from
-# cdq_sample_children (row f2).  Differences, stated: nodes are keyed by
-# their 72-byte record instead of a FEN; positions inside a search carry no move history (rep3 = 0).
+# the Russian Doll MCTS itself, device resident (csrc/tree_kernel.cu).  Same tree policy as the
+# reference (ParallelRussianDollMCTS, mcts.py:14-194: UCB with the annealed exploration weight, unexplored children
+# first, running-mean backup with a sign flip per ply, best move = most visited root child, depth limit =
+# len(samples_per_level), children per node = samples_per_level[0] sampled like select_weighted_moves from
+# categorize_moves' weights), but trees, selection, expansion, Board.push, repetition bookkeeping and backup all live on
+# the GPU for any number of concurrent games: the simulations advance level by level in waves of `num_workers` (the
+# reference's thread count), a wave's leaves of ALL games are ONE cdq_leaf_eval, and the host synchronises once per
+# search.  Differences from the reference, stated: nodes are keyed by a 64-bit hash of what a FEN holds (position,
+# halfmove clock, move number) instead of the FEN string; random draws are counter-based hashes, so move-level parity
+# with the reference is statistical while leaf values and tree statistics are exact against the host restatement
+# (tests/test_gpu_forest.py).
 import math
 import random as _random
+
+
+def _decode_move(code):
+    """forest move code -> (from_square, to_square, promotion piece type 2..5 or None) in python-chess numbering"""
+    code = int(code)
+    promo = (code >> 12) & 15
+    return code & 63, (code >> 6) & 63, (promo if promo else None)       # (promotion type + 1) - 1 + 1: PT_N = 1 -> KNIGHT = 2
 
 
 def move_from_records(parent, child):
@@ -117,179 +124,192 @@ def move_uci(parent, child):
     return name(f) + name(t) + ("" if p is None else " nbrq"[p])
 
 
+def history_records(board):
+    """What the device needs of a python-chess board's past for is_repetition (mcts.py:151,209): the positions BEFORE
+    the current one back to the last irreversible move, oldest first, as packed records; plus halfmove clock and ply.
+    Boards without a move stack (packed records, FEN-built boards) have no history."""
+    from .board_utils import pack_board
+    hmc = int(getattr(board, "halfmove_clock", 0) or 0)
+    ply = int(board.ply()) if hasattr(board, "ply") else 0
+    recs = []
+    if getattr(board, "move_stack", None) and hasattr(board, "is_irreversible"):
+        b = board.copy()
+        while b.move_stack and len(recs) < 255:
+            mv = b.pop()
+            if b.is_irreversible(mv):
+                break
+            recs.append(pack_board(b))
+        recs.reverse()
+    return (np.concatenate(recs) if recs else np.zeros(0, BOARD_DTYPE)), hmc, ply
+
+
+class DeviceForest:
+    """Host handle of a CdqForest (include/cdq.h): `n_games` games and their search trees in device memory."""
+
+    HIST_MAX = 256
+
+    def __init__(self, n_games, workers=8, samples_per_level=None, max_iterations=50):
+        self.device = _lib.require_cuda()
+        widths = list(samples_per_level or [21, 13, 8, 5, 3, 2, 1])
+        self.n_games, self.workers, self.depth, self.width = int(n_games), int(workers), len(widths), int(widths[0])
+        self.max_iterations = int(max_iterations)
+        cfg = _lib.CdqForestConfig(self.n_games, self.workers, self.depth, self.width, self.max_iterations)
+        import ctypes
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().cdq_forest_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        v = _lib.CdqForestView()
+        _lib.check(_lib.lib().cdq_forest_view(h, ctypes.byref(v)))
+        self._view = v
+        T, W, N, E = self.n_games, self.workers, v.max_nodes, v.max_nodes * self.width
+        self.max_nodes = v.max_nodes
+        t = self._tensor
+        self.game_boards = t(v.game_boards, (T, 9), torch.int64)
+        self.game_halfmove_clock = t(v.game_halfmove_clock, (T,), torch.int32)
+        self.game_ply = t(v.game_ply, (T,), torch.int32)
+        self.game_status = t(v.game_status, (T,), torch.int32)
+        self.game_history_len = t(v.game_history_len, (T,), torch.int32)
+        self.best_move = t(v.best_move, (T,), torch.int32)
+        self.best_visits = t(v.best_visits, (T,), torch.int32)
+        self.root_children = t(v.root_children, (T,), torch.int32)
+        self.edge_move = t(v.edge_move, (T, N, self.width), torch.int32)
+        self.edge_visits = t(v.edge_visits, (T, N, self.width), torch.int32)
+        self.edge_value = t(v.edge_value, (T, N, self.width), torch.float64)
+        self.node_children = t(v.node_children, (T, N), torch.int32)
+        self.node_count = t(v.node_count, (T,), torch.int32)
+        self.leaf_boards = t(v.leaf_boards, (T, W, 9), torch.int64)
+        self.leaf_values = t(v.leaf_values, (T, W), torch.float32)
+        self.leaf_depth = t(v.leaf_depth, (T, W), torch.int32)
+        self.positions_evaluated = t(v.positions_evaluated, (T,), torch.int64)
+
+    def _tensor(self, ptr, shape, dtype):
+        from .train import _DevicePtr
+        n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        return torch.as_tensor(_DevicePtr(ptr, max(n, 1)), device=self.device)[:n].view(dtype).view(*shape)
+
+    def close(self):
+        if self._h is not None:
+            torch.cuda.synchronize()
+            _lib.lib().cdq_forest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_games(self, boards, seeds, halfmove_clock=None, ply=None, history=None, active=None):
+        """boards: n_games records; seeds: n_games uint64; history: list of record arrays (positions before the current
+        one since the last irreversible move, oldest first) or None."""
+        dev = self.device
+        d = to_device(boards)
+        assert d.shape[0] == self.n_games
+        i32 = lambda a: None if a is None else torch.as_tensor(np.asarray(a, dtype=np.int32)).to(dev)  # noqa: E731
+        d_seeds = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64).copy()).to(dev)
+        d_hmc, d_ply, d_active = i32(halfmove_clock), i32(ply), i32(active)
+        d_hist = d_len = None
+        stride = 0
+        if history is not None and any(len(h) for h in history):
+            stride = max(1, min(self.HIST_MAX, max(len(h) for h in history)))
+            buf = np.zeros((self.n_games, stride), BOARD_DTYPE)
+            lens = np.zeros(self.n_games, np.int32)
+            for g, h in enumerate(history):
+                h = as_records(h)[-stride:] if len(h) else h
+                buf[g, :len(h)] = h
+                lens[g] = len(h)
+            d_hist = torch.from_numpy(buf.view(np.uint64).reshape(self.n_games, stride, 9).view(np.int64)).to(dev)
+            d_len = torch.from_numpy(lens).to(dev)
+        p = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+        _lib.check(_lib.lib().cdq_forest_set_games(self._h, d.data_ptr(), p(d_hmc), p(d_ply), p(d_hist), p(d_len), stride,
+                                                   d_seeds.data_ptr(), p(d_active), _lib.stream_ptr()))
+
+    def set_active(self, active):
+        a = torch.as_tensor(np.asarray(active, dtype=np.int32)).to(self.device)
+        _lib.check(_lib.lib().cdq_forest_set_active(self._h, a.data_ptr(), _lib.stream_ptr()))
+
+    def search(self, neural_net=None, iterations=None, exploration_weight=1.0, training_progress=0.0, max_moves=200):
+        """One search per active game; asynchronous (results are in the view tensors once the stream has run)."""
+        it = self.max_iterations if iterations is None else int(iterations)
+        handle = neural_net.net_handle() if neural_net is not None else None
+        _lib.check(_lib.lib().cdq_forest_search(self._h, handle, it, float(exploration_weight), float(training_progress),
+                                                int(max_moves), _lib.stream_ptr()))
+
+    def advance(self):
+        _lib.check(_lib.lib().cdq_forest_advance(self._h, _lib.stream_ptr()))
+
+
+_forest_cache = {}
+
+
+def _cached_forest(n_games, workers, samples_per_level, iterations):
+    key = (torch.cuda.current_device(), n_games, workers, len(samples_per_level), samples_per_level[0], iterations)
+    f = _forest_cache.get(key)
+    if f is None:
+        if len(_forest_cache) >= 4:
+            _forest_cache.pop(next(iter(_forest_cache))).close()
+        f = _forest_cache[key] = DeviceForest(n_games, workers, samples_per_level, iterations)
+    return f
+
+
 class BatchedRussianDollMCTS:
+    """Constructor of ParallelRussianDollMCTS (mcts.py:15-31) plus a seed; search() runs on the device forest."""
+
     def __init__(self, board, iterations=20, exploration_weight=1.0, samples_per_level=None, num_workers=None,
-                 rng=None):
+                 rng=None, seed=None):
         self.root = as_records(board)[:1].copy()
+        self.history, self.halfmove_clock, self.ply = (np.zeros(0, BOARD_DTYPE), 0, None)
+        if hasattr(board, "occupied_co"):
+            self.history, self.halfmove_clock, self.ply = history_records(board)
         self.iterations = iterations
         self.exploration_weight = exploration_weight
         self.samples_per_level = samples_per_level or [21, 13, 8, 5, 3, 2, 1]
         self.num_workers = num_workers or 8       # simulations per wave (mcts.py:20: min(8, cpu_count))
         self.rng = rng or _random.Random()
-        self.children = {}          # key -> BOARD_DTYPE array of sampled children
-        self.N = {}                 # key -> visit counts per child
-        self.Q = {}                 # key -> running-mean values per child
-        self.U = {}                 # key -> indices of the children no simulation has taken yet
+        self.seed = self.rng.getrandbits(64) if seed is None else int(seed)
         self.total_positions_evaluated = 0
-        self.last_leaves = None     # (records, leaf values) of the last search, for inspection/tests
-
-    @staticmethod
-    def _key(rec):
-        return rec.tobytes()
-
-    @staticmethod
-    def _device_expand(recs, seeds, width):
-        """Successors (cdq_expand_weighted), terminal flags (cdq_eval_terms) and the weighted sample of
-        `width` children per node (cdq_sample_children = select_weighted_moves, evaluation.py:342-366)
-        for a batch of nodes of any number of trees: three launches, and only the sampled children
-        (width x 72 B per node instead of 128 x 73 B) come back to the host."""
-        d = to_device(recs)
-        n, maxc = len(recs), 128
-        dev = d.device
-        kids = torch.empty((n, maxc, 9), dtype=torch.int64, device=dev)
-        counts = torch.empty(n, dtype=torch.int32, device=dev)
-        flags = torch.empty(n, dtype=torch.int32, device=dev)
-        wts = torch.empty((n, maxc), dtype=torch.uint8, device=dev)
-        sel = torch.empty((n, width, 9), dtype=torch.int64, device=dev)
-        sel_counts = torch.empty(n, dtype=torch.int32, device=dev)
-        d_seeds = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(dev)
-        L, st = _lib.lib(), _lib.stream_ptr()
-        _lib.check(L.cdq_expand_weighted(d.data_ptr(), n, maxc, kids.data_ptr(), counts.data_ptr(), wts.data_ptr(), st))
-        _lib.check(L.cdq_eval_terms(d.data_ptr(), n, 0, None, None, flags.data_ptr(), st))
-        _lib.check(L.cdq_sample_children(kids.data_ptr(), counts.data_ptr(), wts.data_ptr(), n, maxc, width,
-                                         d_seeds.data_ptr(), sel.data_ptr(), sel_counts.data_ptr(), st))
-        sel_h = sel.cpu().numpy().view(np.uint64).reshape(n, width, 9)
-        return sel_h, sel_counts.cpu().numpy(), flags.cpu().numpy()
-
-    @classmethod
-    def _expand_many(cls, requests):
-        """requests: (tree, record) pairs.  Nodes a tree has not expanded yet are expanded and sampled
-        with ONE batch of device calls for all trees; every node gets a 64-bit sampling seed drawn
-        from its own tree's RNG, in request order."""
-        todo, seen = [], set()
-        for tree, rec in requests:
-            key = cls._key(rec)
-            if key in tree.children or (id(tree), key) in seen:
-                continue
-            seen.add((id(tree), key))
-            todo.append((tree, key, rec))
-        if not todo:
-            return
-        width = todo[0][0].samples_per_level[0]
-        assert all(t.samples_per_level[0] == width for t, _, _ in todo), "trees searched together share the child width"
-        seeds = [t.rng.getrandbits(64) for t, _, _ in todo]
-        sel_h, sel_counts, flags = cls._device_expand(np.array([r for _, _, r in todo], dtype=BOARD_DTYPE), seeds, width)
-        recs = sel_h.view(BOARD_DTYPE).reshape(len(todo), width)         # views into one batch array, no copies
-        n_all, q_all = np.zeros((len(todo), width), np.int64), np.zeros((len(todo), width), np.float64)
-        for i, (tree, key, _) in enumerate(todo):
-            c = 0 if int(flags[i]) & 0x40 else int(sel_counts[i])      # insufficient material: game over
-            tree.children[key] = recs[i, :c]
-            tree.N[key] = n_all[i, :c]
-            tree.Q[key] = q_all[i, :c]
-            tree.U[key] = list(range(c))
-
-    def _expand(self, records):
-        """Expand a batch of not-yet-expanded nodes on the device (mcts.py:166-194)."""
-        self._expand_many([(self, r) for r in records])
-
-    def _select(self, key, training_progress, current_move, max_moves):
-        """mcts.py:34-67: a random child that no simulation has taken yet, else the UCB argmax.  The
-        never-taken children of a node are a list that shrinks as simulations claim them (also within
-        a wave, before its back-up), so simultaneous simulations spread over unexplored children like
-        the reference's threads do."""
-        fresh = self.U[key]
-        if fresh:
-            k = self.rng.randrange(len(fresh))
-            fresh[k], fresh[-1] = fresh[-1], fresh[k]
-            return fresh.pop()
-        counts = self.N[key]
-        if len(counts) == 0:
-            return None
-        total = int(counts.sum())
-        if total == 0:
-            return self.rng.randrange(len(counts))
-        alpha = 1 + training_progress
-        beta = current_move / max_moves if max_moves > 0 else 0.5
-        eff = self.exploration_weight * (1.0 - 0.5 * alpha * beta)
-        log_total = math.log(total + 1e-10)
-        nk = counts + 1e-10
-        # as written in the reference: the running mean Q is divided by N once more (mcts.py:61-62)
-        ucb = self.Q[key] / nk + eff * np.sqrt(log_total / nk)
-        return int(np.argmax(ucb))
+        self.root_moves = self.root_visits = self.root_values = None     # statistics of the root after search()
 
     def search(self, neural_net=None, device=None, training_progress=0.0, current_move=0, max_moves=200,
                evaluator=None):
         """-> (best child record, (from, to, promotion)) or (None, None) when the root has no move."""
-        ev = evaluator or LeafEvaluator(neural_net)
-        return search_many([self], ev, training_progress, [current_move], max_moves)[0]
+        net = neural_net if neural_net is not None else (evaluator.net if evaluator is not None else None)
+        return search_many([self], net, training_progress, [current_move], max_moves)[0]
 
 
-def search_many(trees, evaluator, training_progress=0.0, current_moves=None, max_moves=200):
-    """Run the searches of several trees (e.g. one per concurrent self-play game) in lockstep: every
-    level of a wave costs ONE device expansion and every wave ONE leaf evaluation for all trees
-    together, so the batch the GPU sees grows with the number of games.  Each tree keeps its own
-    statistics and RNG, so its result is what `tree.search()` alone would have produced."""
-    current_moves = current_moves or [0] * len(trees)
-    BatchedRussianDollMCTS._expand_many([(t, t.root[0]) for t in trees])
-    iterations = max(t.iterations for t in trees)
-    workers = trees[0].num_workers
-    leaves_of, values_of = [[] for _ in trees], [[] for _ in trees]
-    # The reference runs `num_workers` simulations concurrently (mcts.py:77) and backs each one up
-    # as it finishes; here a wave of `num_workers` simulations descends level by level together and
-    # is backed up before the next wave selects, so UCB sees the same amount of feedback.
-    for first in range(0, iterations, workers):
-        waves = []
-        for t in trees:
-            wave = max(0, min(t.num_workers, t.iterations - first))
-            waves.append([{"rec": t.root[0], "path": [], "alive": True} for _ in range(wave)])
-        depth_limit = max(len(t.samples_per_level) for t in trees)
-        for depth in range(depth_limit):
-            live = [[s for s in sims if s["alive"]] if depth < len(t.samples_per_level) else []
-                    for t, sims in zip(trees, waves)]
-            if not any(live):
-                break
-            BatchedRussianDollMCTS._expand_many([(t, s["rec"]) for t, ls in zip(trees, live) for s in ls])
-            for t, ls, cm in zip(trees, live, current_moves):
-                for s in ls:
-                    key = t._key(s["rec"])
-                    a = t._select(key, training_progress, cm + depth, max_moves)
-                    if a is None:
-                        s["alive"] = False
-                        continue
-                    s["path"].append((key, a))
-                    s["rec"] = t.children[key][a]
-        batch = [s["rec"] for sims in waves for s in sims]
-        if not batch:
-            continue
-        values = evaluator.evaluate_host(np.array(batch, dtype=BOARD_DTYPE))["leaf"]
-        pos = 0
-        for ti, (t, sims) in enumerate(zip(trees, waves)):
-            if not sims:
-                continue
-            v = values[pos:pos + len(sims)]
-            pos += len(sims)
-            t.total_positions_evaluated += len(sims)
-            leaves_of[ti].append(np.array([s["rec"] for s in sims], dtype=BOARD_DTYPE))
-            values_of[ti].append(v.copy())
-            for s, x in zip(sims, v):                           # mcts.py:158-164
-                value = float(x)
-                for key, a in reversed(s["path"]):
-                    t.N[key][a] += 1
-                    t.Q[key][a] += (value - t.Q[key][a]) / t.N[key][a]
-                    value = -value
+def search_many(trees, neural_net, training_progress=0.0, current_moves=None, max_moves=200):
+    """The searches of several trees (e.g. one per concurrent self-play game) as ONE device forest: every level of a
+    wave is one kernel for all trees, every wave one cdq_leaf_eval.  A tree's result depends only on its own seed and
+    position, so it is what `tree.search()` alone produces.  `neural_net` may be a LeafEvaluator (its net is used)."""
+    if isinstance(neural_net, LeafEvaluator):
+        neural_net = neural_net.net
+    t0 = trees[0]
+    assert all(t.num_workers == t0.num_workers and t.iterations == t0.iterations and
+               list(t.samples_per_level) == list(t0.samples_per_level) and t.exploration_weight == t0.exploration_weight
+               for t in trees), "trees searched together share workers, iterations, widths and exploration weight"
+    current_moves = list(current_moves) if current_moves is not None else [0] * len(trees)
+    forest = _cached_forest(len(trees), min(32, t0.num_workers), list(t0.samples_per_level), t0.iterations)
+    plies = [t.ply if t.ply is not None else cm for t, cm in zip(trees, current_moves)]
+    forest.set_games(np.concatenate([t.root for t in trees]), [t.seed for t in trees],
+                     halfmove_clock=[t.halfmove_clock for t in trees], ply=plies, history=[t.history for t in trees])
+    forest.search(neural_net, t0.iterations, t0.exploration_weight, training_progress, max_moves)
+    forest.advance()
+    best = forest.best_move.cpu().numpy().view(np.uint32)
+    kids = forest.game_boards.cpu().numpy().view(np.uint64).reshape(-1).view(BOARD_DTYPE)
+    nroot = forest.root_children.cpu().numpy()
+    moves = forest.edge_move[:, 0].cpu().numpy().view(np.uint32)
+    visits = forest.edge_visits[:, 0].cpu().numpy()
+    values = forest.edge_value[:, 0].cpu().numpy()
+    evaluated = forest.positions_evaluated.cpu().numpy()
     out = []
-    for ti, t in enumerate(trees):
-        if leaves_of[ti]:
-            t.last_leaves = (np.concatenate(leaves_of[ti]), np.concatenate(values_of[ti]))
-        root_key = t._key(t.root[0])
-        kids = t.children[root_key]
-        if len(kids) == 0:
+    for i, t in enumerate(trees):
+        t.total_positions_evaluated += int(evaluated[i])
+        c = int(nroot[i])
+        t.root_moves, t.root_visits, t.root_values = moves[i, :c].copy(), visits[i, :c].copy(), values[i, :c].copy()
+        if best[i] == 0xffffffff:
             out.append((None, None))
-            continue
-        counts = t.N[root_key]
-        best = int(np.argmax(counts)) if counts.any() else t.rng.randrange(len(kids))
-        child = kids[best:best + 1].copy()
-        out.append((child, move_from_records(t.root[0], child[0])))
+        else:
+            out.append((kids[i:i + 1].copy(), _decode_move(best[i])))
     return out
 
 
@@ -301,69 +321,82 @@ def _startpos():
     return start
 
 
+def annealed_search_parameters(training_progress):
+    """DQNAgent._get_mcts_move (neural_network.py:150-163): iterations, exploration weight and per-level widths."""
+    f = 1 - 0.3 * training_progress
+    return (int(50 + 150 * training_progress), max(1.6 * (1 - 0.5 * training_progress), 0.8),
+            [max(21, int(25 * f)), max(13, int(15 * f)), max(8, int(10 * f)), max(5, int(7 * f)),
+             max(3, int(5 * f)), max(2, int(3 * f)), max(1, int(2 * f))])
+
+
 def self_play_games(neural_net, n_games, max_moves=200, iterations=50, samples_per_level=None, seeds=None,
-                    training_progress=0.0):
-    """`n_games` self-play games (chess_ai.py:117-250) advanced ply by ply in lockstep, their searches
-    batched by search_many: one device expansion per tree level and one leaf evaluation per wave for
-    ALL games.  Game i uses RNG seed seeds[i] and is move for move the game self_play_game(seed =
-    seeds[i]) plays alone.  -> list of (positions, scores)."""
+                    training_progress=0.0, exploration_weight=1.0, num_workers=8, agent=None, train_every=1, start=None,
+                    on_ply=None):
+    """`n_games` self-play games (OptimizedChessAI.self_play_game, chess_ai.py:117-250) advanced ply by ply in lockstep
+    on ONE device forest: per ply one search for all games (one host synchronisation), the moves are played on the
+    device, and one batched evaluation of the new positions gives the display score, the reward and the terminal flags
+    (chess_ai.py:161,174-184).  With `agent` (a DQNAgent) every played move is stored as a transition
+    (chess_ai.py:187: state before, move, reward, state after, done) and the network is trained once per stored
+    transition as soon as the replay memory holds a batch (chess_ai.py:190-192; train_every = n trains once per n
+    transitions).  Game i uses seed seeds[i] and is move for move the game it plays alone.
+    -> list of dicts(positions, scores, moves, rewards, result_flags, losses)."""
     from .evaluation import evaluate_batch
     seeds = list(seeds) if seeds is not None else list(range(42, 42 + n_games))
-    rngs = [_random.Random(s) for s in seeds]
-    ev = LeafEvaluator(neural_net)
-    widths = samples_per_level or [21, 13, 8, 5, 3, 2, 1]
-    positions = [[_startpos()] for _ in range(n_games)]
-    scores = [[] for _ in range(n_games)]
-    active = list(range(n_games))
+    widths = list(samples_per_level or [21, 13, 8, 5, 3, 2, 1])
+    forest = _cached_forest(n_games, num_workers, widths, iterations)
+    begin = np.concatenate([_startpos()] * n_games) if start is None else as_records(start)
+    forest.set_games(begin, seeds)
+    positions = [[begin[g:g + 1].copy()] for g in range(n_games)]
+    scores, moves, rewards, losses = ([[] for _ in range(n_games)] for _ in range(4))
+    flags_of = [0] * n_games
+    active = np.ones(n_games, bool)
+    score0, flags0 = evaluate_batch(begin)
+    active &= (flags0.cpu().numpy() & 0x70) == 0          # `while not self.board.is_game_over()` (chess_ai.py:141)
+    pending = 0
     for ply in range(max_moves):
-        if not active:
+        if not active.any():
             break
-        cur = np.concatenate([positions[g][-1] for g in active])
-        score, flags = evaluate_batch(cur)
+        forest.set_active(active.astype(np.int32))
+        forest.search(neural_net, iterations, exploration_weight, training_progress, max_moves)
+        forest.advance()
+        score, flags = evaluate_batch(forest.game_boards)                    # same stream: after the moves were played
+        rec = forest.game_boards.cpu().numpy().view(np.uint64).reshape(-1).view(BOARD_DTYPE)     # the ply's one synchronisation
+        status = forest.game_status.cpu().numpy()
+        best = forest.best_move.cpu().numpy().view(np.uint32)
         score_h, flags_h = score.cpu().numpy(), flags.cpu().numpy()
-        still, trees = [], []
-        for k, g in enumerate(active):
-            scores[g].append(float(score_h[k]))
-            if int(flags_h[k]) & 0x70:          # checkmate / stalemate / insufficient material
+        for g in np.nonzero(active)[0]:
+            if not status[g] & 1:                       # `if move is None: break` (chess_ai.py:148-149)
+                active[g] = False
                 continue
-            still.append(g)
-            trees.append(BatchedRussianDollMCTS(positions[g][-1], iterations=iterations, samples_per_level=widths,
-                                                rng=rngs[g]))
-        if not trees:
-            active = []
-            break
-        results = search_many(trees, ev, training_progress, [ply] * len(trees), max_moves)
-        active = []
-        for g, (child, _) in zip(still, results):
-            if child is None:
-                continue
-            positions[g].append(child)
-            active.append(g)
-    return [(np.concatenate(positions[g]), scores[g]) for g in range(n_games)]
+            before = positions[g][-1]
+            positions[g].append(rec[g:g + 1].copy())
+            scores[g].append(float(score_h[g]))         # raw_score (chess_ai.py:161)
+            moves[g].append(_decode_move(best[g]))
+            fl = int(flags_h[g])
+            if fl & 0x10:                               # chess_ai.py:174-184
+                reward, done = -1.0, True
+            elif fl & 0x60:
+                reward, done = 0.0, True
+            else:
+                reward, done = 0.01 * math.tanh(float(score_h[g]) / 10.0), False
+            rewards[g].append(reward)
+            flags_of[g] = fl | (int(status[g]) << 24)
+            if agent is not None:
+                agent.store_transition(before, moves[g][-1], reward, rec[g:g + 1], done)
+                pending += 1
+                if len(agent.memory) >= agent.batch_size and pending >= train_every:
+                    losses[g].append(agent.train())
+                    pending = 0
+            if (fl & 0x70) or (status[g] & 6):          # is_game_over(): mate, stalemate, material, fivefold, 75 moves
+                active[g] = False
+        if on_ply is not None:
+            on_ply(ply, active)
+    return [{"positions": np.concatenate(positions[g]), "scores": scores[g], "moves": moves[g], "rewards": rewards[g],
+             "result_flags": flags_of[g], "losses": losses[g]} for g in range(n_games)]
 
 
 def self_play_game(neural_net, max_moves=200, iterations=50, samples_per_level=None, seed=42, start=None,
-                   training_progress=0.0):
-    """One self-play game in the manner of OptimizedChessAI.self_play_game (chess_ai.py:117-250) with
-    the batched search: returns the list of positions (records) and the per-ply handcrafted scores
-    that the reference uses for reward shaping (chess_ai.py:161,182)."""
-    from .evaluation import evaluate_batch
-    rng = _random.Random(seed)
-    ev = LeafEvaluator(neural_net)
-    if start is None:
-        start = _startpos()
-    positions, scores = [as_records(start)[:1].copy()], []
-    widths = samples_per_level or [21, 13, 8, 5, 3, 2, 1]
-    for ply in range(max_moves):
-        cur = positions[-1]
-        score, flags = evaluate_batch(cur)
-        scores.append(float(score[0].item()))
-        if int(flags[0].item()) & 0x70:          # checkmate / stalemate / insufficient material
-            break
-        tree = BatchedRussianDollMCTS(cur, iterations=iterations, samples_per_level=widths, rng=rng)
-        child, _ = tree.search(neural_net, current_move=ply, max_moves=max_moves, evaluator=ev,
-                               training_progress=training_progress)
-        if child is None:
-            break
-        positions.append(child)
-    return np.concatenate(positions), scores
+                   training_progress=0.0, **kw):
+    """One self-play game (chess_ai.py:117-250): -> (positions, per-ply handcrafted scores)."""
+    g = self_play_games(neural_net, 1, max_moves, iterations, samples_per_level, [seed], training_progress, start=start, **kw)[0]
+    return g["positions"], g["scores"]

@@ -276,6 +276,61 @@ int cdq_sample_children(const CdqBoard* d_children, const int32_t* d_counts, con
                         int32_t* d_sel_counts, void* stream);
 
 
+/* ---- device-resident Russian Doll MCTS (replaces ParallelRussianDollMCTS.search / _parallel_simulation / _expand_node,
+ * mcts.py:69-194, for any number of concurrent games) --------------------------------------------------
+ * A CdqForest holds, in device memory, `n_games` games (position, halfmove clock, ply, transposition keys since the last
+ * irreversible move) and one search tree per game.  cdq_forest_search runs `iterations` simulations per tree in waves of
+ * `workers` (the reference's thread count, mcts.py:20,77): per level one kernel (node expansion with categorize_moves /
+ * select_weighted_moves, evaluation.py:232-366; UCB selection with the annealed exploration weight, mcts.py:34-67;
+ * Board.push; is_game_over / is_repetition bookkeeping, mcts.py:151,209), per wave ONE cdq_leaf_eval over the leaves of
+ * all trees (net == NULL: the heuristic branch) and one backup kernel (mcts.py:158-164).  Nothing is read back: the host
+ * synchronises once per search.  Depth limit = len(samples_per_level), children per node = samples_per_level[0]
+ * (mcts.py:127,188).  cdq_forest_advance plays every tree's most visited root move in its game (chess_ai.py:151).
+ * All random draws are counter-based hashes of (game seed, ply, node key / wave, worker, depth): a tree's result does not
+ * depend on the other trees in the batch.  Limits: workers <= 32, depth <= 8, width <= 32, 256 history keys per game. */
+typedef struct CdqForest CdqForest;
+typedef struct CdqForestConfig {
+    int32_t n_games;         /* concurrent games = trees                                        */
+    int32_t workers;         /* simulations per wave (ParallelRussianDollMCTS.num_workers)       */
+    int32_t depth;           /* len(samples_per_level)                                           */
+    int32_t width;           /* samples_per_level[0]                                             */
+    int32_t max_iterations;  /* sizes the node pool: iterations * depth + 1 nodes per tree       */
+} CdqForestConfig;
+typedef struct CdqForestView {          /* device pointers into the forest (read-only for the caller) */
+    int32_t n_games, workers, depth, width, max_nodes;
+    const CdqBoard* game_boards;        /* [n_games] current positions (rep3 bit maintained)                  */
+    const int32_t* game_halfmove_clock; /* [n_games]                                                          */
+    const int32_t* game_ply;            /* [n_games]                                                          */
+    const int32_t* game_active;         /* [n_games]                                                          */
+    const uint32_t* game_status;        /* [n_games] after cdq_forest_advance: 1 moved, 2 fivefold, 4 75-move  */
+    const int32_t* game_history_len;    /* [n_games]                                                          */
+    const uint32_t* best_move;          /* [n_games] from | to << 6 | (promotion type) << 12 | special << 16; 0xffffffff none */
+    const int32_t* best_visits;         /* [n_games] visit count of that root child                            */
+    const int32_t* root_children;       /* [n_games] number of (sampled) root children                         */
+    const uint32_t* edge_move;          /* [n_games][max_nodes][width]; node 0 of a tree is its root           */
+    const int32_t* edge_visits;         /* N(state, action)                                                   */
+    const double* edge_value;           /* Q(state, action), running mean                                     */
+    const int32_t* node_children;       /* [n_games][max_nodes]                                               */
+    const int32_t* node_count;          /* [n_games] expanded nodes                                           */
+    const CdqBoard* leaf_boards;        /* [n_games][workers] leaves of the last wave                         */
+    const float* leaf_values;           /* [n_games][workers]                                                 */
+    const int32_t* leaf_depth;          /* [n_games][workers]                                                 */
+    const int64_t* positions_evaluated; /* [n_games] ParallelRussianDollMCTS.total_positions_evaluated        */
+} CdqForestView;
+int cdq_forest_create(const CdqForestConfig* cfg, CdqForest** out);
+void cdq_forest_destroy(CdqForest* forest);
+/* Install the games: d_boards [n_games]; optional halfmove clocks, plies (ply = the reference's current_move), history
+ * (d_history [n_games][history_stride] records of the positions BEFORE the current one since the last irreversible move,
+ * oldest first, d_history_len [n_games]) and active flags; d_seeds [n_games] uint64. */
+int cdq_forest_set_games(CdqForest* forest, const CdqBoard* d_boards, const int32_t* d_halfmove_clock, const int32_t* d_ply,
+                         const CdqBoard* d_history, const int32_t* d_history_len, int history_stride, const uint64_t* d_seeds,
+                         const int32_t* d_active, void* stream);
+int cdq_forest_set_active(CdqForest* forest, const int32_t* d_active, void* stream);
+int cdq_forest_search(CdqForest* forest, const CdqNet* net, int iterations, float exploration_weight, float training_progress,
+                      int max_moves, void* stream);
+int cdq_forest_advance(CdqForest* forest, void* stream);
+int cdq_forest_view(const CdqForest* forest, CdqForestView* out);
+
 /* Kernel launch counter (all cdq_* kernels launched by this process), for bench gpu_launches. */
 uint64_t cdq_launch_count(void);
 

@@ -27,21 +27,35 @@ def _successors(oracle, rec):
     return {oracle.push(rec, m)[0].tobytes() for m in oracle.legal_moves(rec)}
 
 
+def _move_code(mv):
+    frm, to, promo = mv
+    return frm | (to << 6) | ((promo - 1 if promo else 0) << 12)      # the oracle's uint16 move encoding
+
+
 def test_search_returns_legal_move_and_exact_leaf_values(cdq, oracle):
-    import random
     net, p = _net(cdq, oracle)
     root = oracle.from_fen("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1")
-    tree = cdq.BatchedRussianDollMCTS(root, iterations=64, rng=random.Random(1))
+    tree = cdq.BatchedRussianDollMCTS(root, iterations=64, seed=1)
     child, move = tree.search(net)
     assert child[0].tobytes() in _successors(oracle, root)
-    assert int(tree.N[root[0].tobytes()].sum()) == 64                  # every simulation backed up through the root
-    # every expanded node's children are legal successors of that node (sampled, at most width 21)
-    for key, kids in list(tree.children.items())[:40]:
-        parent = np.frombuffer(key, dtype=oracle.BOARD_DTYPE)
-        succ = _successors(oracle, parent)
-        assert len(kids) <= 21 and all(k.tobytes() in succ for k in kids)
-    # the wave's leaves: values follow mcts.py:196-232 (oracle: exact on terminals, 1e-3 on the network)
-    leaves, values = tree.last_leaves
+    assert int(tree.root_visits.sum()) == 64 and tree.total_positions_evaluated == 64     # every simulation backed up through the root
+    # the root's children are legal moves (sampled, at most width 21), all different
+    legal = set(int(m) for m in oracle.legal_moves(root))
+    codes = [_move_code(cdq.mcts._decode_move(m)) for m in tree.root_moves]
+    assert len(codes) == 21 == len(set(codes)) and all(c in legal for c in codes)
+    # the reported move transforms the root into the chosen child and is the most visited one
+    assert _move_code(move) in legal
+    assert oracle.push(root, _move_code(move))[0].tobytes() == child[0].tobytes()
+    assert codes[int(np.argmax(tree.root_visits))] == _move_code(move)
+    frm, to, _ = move
+    assert cdq.move_uci(root[0], child[0])[:4] == "abcdefgh"[frm & 7] + str((frm >> 3) + 1) + "abcdefgh"[to & 7] + str((to >> 3) + 1)
+    # the last wave's leaves: values follow mcts.py:196-232 (oracle: exact on terminals, 1e-3 on the network)
+    forest = cdq.mcts.DeviceForest(1, 8, [21, 13, 8, 5, 3, 2, 1], 64)
+    forest.set_games(root, [1])
+    forest.search(net, 64)
+    leaves = forest.leaf_boards[0].cpu().numpy().view(np.uint64).reshape(-1).view(cdq.BOARD_DTYPE)
+    values = forest.leaf_values[0].cpu().numpy()
+    assert (forest.leaf_depth[0].cpu().numpy() >= 1).all()
     _, _, flags = oracle.evaluate(leaves)
     v = oracle.net_forward(p, oracle.encode_planes(leaves)).reshape(-1)
     ref = np.clip(v, -1, 1)
@@ -51,32 +65,24 @@ def test_search_returns_legal_move_and_exact_leaf_values(cdq, oracle):
     ref[(flags & 0xE0) != 0] = 0.0
     assert np.abs(values - ref).max() <= 1e-3
     assert np.array_equal(values[mate], ref[mate])
-    # the reported move transforms the root into the chosen child
-    frm, to, promo = move
-    legal = oracle.legal_moves(root)
-    enc = frm | (to << 6) | ((promo - 1 if promo else 0) << 12)
-    assert enc in set(int(m) for m in legal)
-    assert oracle.push(root, enc)[0].tobytes() == child[0].tobytes()
-    assert cdq.move_uci(root[0], child[0])[:4] == "abcdefgh"[frm & 7] + str((frm >> 3) + 1) + "abcdefgh"[to & 7] + str((to >> 3) + 1)
+    forest.close()
 
 
 def test_mate_in_one_backs_up_the_exact_terminal_value(cdq, oracle):
     """Ra8# for white: the mated leaf is worth exactly +1 (mcts.py:202-203, white-centric) and the
     running mean of that edge stays +1; with the reference's UCB (which divides the mean by N once
     more, mcts.py:61-62) that edge is visited at least as often as the average edge."""
-    import random
     net, _ = _net(cdq, oracle, scale=1.0)
     root = oracle.from_fen("6k1/5ppp/8/8/8/8/8/R5K1 w - - 0 1")
-    tree = cdq.BatchedRussianDollMCTS(root, iterations=200, rng=random.Random(3))
+    tree = cdq.BatchedRussianDollMCTS(root, iterations=200, seed=3)
     tree.search(net)
-    key = root[0].tobytes()
-    kids = tree.children[key]
-    mate = [i for i, k in enumerate(kids) if oracle.evaluate(np.array([k], dtype=oracle.BOARD_DTYPE))[2][0] & 0x10]
-    assert len(mate) == 1 and cdq.move_from_records(root[0], kids[mate[0]])[:2] == (0, 56)
-    assert tree.Q[key][mate[0]] == 1.0
-    assert tree.N[key][mate[0]] >= tree.N[key].mean()
-    # nodes are keyed by position, so a line that returns to the root position (Ra2 Kh8 Ra1 Kg8) adds a visit
-    assert 200 <= int(tree.N[key].sum()) <= 210
+    mate = [i for i, m in enumerate(tree.root_moves) if cdq.mcts._decode_move(m)[:2] == (0, 56)]
+    assert len(mate) == 1
+    assert tree.root_values[mate[0]] == 1.0
+    assert tree.root_visits[mate[0]] >= tree.root_visits.mean()
+    # nodes are keyed like FENs (position + halfmove clock + move number): a line that returns to the root position
+    # is another node, so the root sees exactly its 200 simulations
+    assert int(tree.root_visits.sum()) == 200
 
 
 def test_terminal_root(cdq, oracle):
@@ -87,30 +93,30 @@ def test_terminal_root(cdq, oracle):
 
 
 def test_self_play_game_with_batched_leaf_evaluation(cdq, oracle):
-    """BASELINE configs[2] as a parity case: Russian Doll widths 21/13/8/5/3/2/1, batched GPU leaves."""
+    """BASELINE configs[2] as a parity case: Russian Doll widths 21/13/8/5/3/2/1, device-resident search."""
     net, _ = _net(cdq, oracle)
     positions, scores = cdq.self_play_game(net, max_moves=24, iterations=50, seed=42)
-    assert len(positions) >= 2 and len(scores) >= len(positions) - 1
+    assert len(positions) >= 2 and len(scores) == len(positions) - 1
     assert positions[0].tobytes() == oracle.startpos()[0].tobytes()
     for a, b in zip(positions[:-1], positions[1:]):
         assert b.tobytes() in _successors(oracle, np.array([a], dtype=oracle.BOARD_DTYPE))
-    _, s_ref, _ = oracle.evaluate(positions[: len(scores)])
-    assert np.array_equal(np.array(scores), s_ref)                     # reward-shaping scores are the bit-exact eval
+    _, s_ref, _ = oracle.evaluate(positions[1:])
+    assert np.array_equal(np.array(scores), s_ref)                     # reward-shaping scores are the bit-exact eval (chess_ai.py:161)
     again, _ = cdq.self_play_game(net, max_moves=24, iterations=50, seed=42)
     assert np.array_equal(again, positions)                           # seeded -> reproducible
 
 
 def test_lockstep_games_equal_single_games(cdq, oracle):
-    """self_play_games batches the searches of all games (one expansion per level, one leaf
+    """self_play_games runs the searches of all games in one device forest (one kernel per level, one leaf
     evaluation per wave for all of them); every game must still be move for move the game that
     self_play_game plays alone with the same seed."""
     net, _ = _net(cdq, oracle)
     seeds = [42, 7, 1234]
     games = cdq.self_play_games(net, n_games=3, max_moves=10, iterations=24, seeds=seeds)
-    for seed, (positions, scores) in zip(seeds, games):
+    for seed, g in zip(seeds, games):
         alone, alone_scores = cdq.self_play_game(net, max_moves=10, iterations=24, seed=seed)
-        assert np.array_equal(positions, alone), seed
-        assert scores == alone_scores, seed
+        assert np.array_equal(g["positions"], alone), seed
+        assert g["scores"] == alone_scores, seed
 
 
 def test_expand_weights_match_categorize_moves(cdq, oracle, eval_golden):
@@ -185,19 +191,17 @@ def test_device_child_sampler_matches_host_restatement(cdq, oracle, eval_golden)
 def test_weighted_child_sampling_prefers_tactical_moves(cdq, oracle):
     """exd5 wins a queen with a pawn (weight 10, evaluation.py:253); with 5 weighted draws out of ~31
     moves it must be sampled far more often than the ~16 % a uniform sampler would give."""
-    import random
     net, _ = _net(cdq, oracle)
     root = oracle.from_fen("rnb1kbnr/ppp1pppp/8/3q4/4P3/8/PPPP1PPP/RNBQKBNR w KQkq - 0 1")
     mv, w = oracle.categorize(root)
     best = [int(m) for m, x in zip(mv, w) if x == 10]
     assert len(best) == 1
-    target = oracle.push(root, best[0])[0].tobytes()
     hits = 0
     for seed in range(40):
-        tree = cdq.BatchedRussianDollMCTS(root, iterations=1, samples_per_level=[5], rng=random.Random(seed))
+        tree = cdq.BatchedRussianDollMCTS(root, iterations=1, samples_per_level=[5], seed=seed)
         tree.search(net)
-        kids = tree.children[root[0].tobytes()]
-        assert len(kids) == 5 and len({k.tobytes() for k in kids}) == 5
-        hits += any(k.tobytes() == target for k in kids)
+        codes = [_move_code(cdq.mcts._decode_move(m)) for m in tree.root_moves]
+        assert len(codes) == 5 and len(set(codes)) == 5
+        hits += best[0] in codes
     expected = 1.0 - np.prod([1.0 - 10.0 / (w.sum() - 2.0 * i) for i in range(5)])    # rough lower estimate
     assert hits >= 0.6 * 40 * expected and hits > 40 * 5 / len(mv) * 1.8
