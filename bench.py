@@ -373,6 +373,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dqn", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE configs[4]: device-resident throughput for 4K..16M positions per GPU (one JSON line)")
     args = ap.parse_args()
@@ -601,6 +602,25 @@ def main():
                 "eval_kernel_hbm": {"achieved_GBps": n * args.steps * 84 / (kms[0] * 1e-3) / 1e9 if kms[0] else None,
                                     "peak_GBps": peaks["hbm"], "note": "84 B/position; integer-issue bound"}}
 
+    # ---- BASELINE configs[2] as a throughput line: Russian Doll MCTS self-play, device-resident search, 1 024 lockstep games
+    selfplay = None
+    if not args.no_selfplay and world == 1:
+        from chess_deep_q_b200.mcts import annealed_search_parameters
+        its, sew, widths = annealed_search_parameters(0.0)
+        rows = []
+        for games, plies in ((1, 16), (64, 16), (1024, 12)):
+            cdq.self_play_games(net, games, max_moves=2, iterations=its, samples_per_level=widths, exploration_weight=sew)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            played = cdq.self_play_games(net, games, max_moves=plies, iterations=its, samples_per_level=widths, exploration_weight=sew)
+            torch.cuda.synchronize()
+            sec = time.perf_counter() - t0
+            moves = sum(len(g["moves"]) for g in played)
+            rows.append({"games": games, "plies_per_game": plies, "leaf_evals_per_s": moves * its / sec, "plies_per_s": moves / sec})
+        selfplay = {"workload": "BASELINE configs[2]: Russian Doll MCTS self-play, widths %s, %d simulations per move in waves of 8, "
+                                "GPU leaf evaluation; search trees resident on the device, one host synchronisation per ply" % (widths, its),
+                    "unit": "leaf evaluations/s", "lockstep": rows}
+
     gpu_base = None
     if not args.no_gpu_baseline and world == 1 and n >= 16384:
         bsc, bfl = cdq.evaluate_batch(boards[1:4097])
@@ -626,7 +646,7 @@ def main():
             "config": workload_config(n),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * H2D_PER_POS, "d2h_bytes_per_step": n * D2H_PER_POS},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "cpu_baseline_python": cpu_py, "gpu_baseline": gpu_base, "dqn": dqn,
+            "cpu_baseline_python": cpu_py, "gpu_baseline": gpu_base, "dqn": dqn, "selfplay": selfplay,
             "profiled_pass": {"ms_per_step": ms_profiled / args.steps,
                               "note": "per-kernel event pairs are recorded in a second pass of the same K steps, not in the timed region"}}
     print(json.dumps(line))

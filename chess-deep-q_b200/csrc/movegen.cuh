@@ -94,7 +94,9 @@ __device__ __forceinline__ u64& type_board(Pos& p, int t) {
 }
 
 // Board.push for standard chess on the packed representation (keeps castling rights clean).
-__device__ __forceinline__ void apply_move(Pos& p, const SelectVisitor& m) {
+struct PlainMove { int from = 0, to = 0, promo = -1, special = MV_NORMAL; bool found = false; };
+template <class M>
+__device__ __forceinline__ void apply_move(Pos& p, const M& m) {
     const bool white = p.meta & CDQ_META_TURN_WHITE;
     const int us = white ? 1 : 0, them = us ^ 1;
     const u64 fb = 1ull << m.from, tb = 1ull << m.to;
@@ -178,6 +180,142 @@ __device__ __forceinline__ int move_category_weight(const Pos& p, const Pos& chi
     }
     if (p.P & fb) return 2;
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One generator instance for both colours.  The kernels that LIST moves (tree_kernel.cu, expand_kernel) do not
+// instantiate gen_side once per colour and visitor (six inlined copies, 220 KB of code, instruction-cache bound): black
+// to move is turned into white to move by a vertical flip (byte swap of every bitboard, colours and castling rights
+// swapped, ep square mirrored), the r-th move is picked in that view by ONE non-inlined function, and its squares are
+// mirrored back.  Legal move sets are invariant under that symmetry; the ORDER in which moves are enumerated (which
+// cdq_expand / cdq_sample_children / the forest expose as child indices) is the order of this function.
+__device__ __forceinline__ u64 vflip(u64 b) {
+    return ((u64)__byte_perm((unsigned)b, 0, 0x0123) << 32) | (u64)__byte_perm((unsigned)(b >> 32), 0, 0x0123);
+}
+__device__ __forceinline__ Pos white_view(const Pos& p) {      // identity when white is to move
+    if (p.meta & CDQ_META_TURN_WHITE) return p;
+    Pos f;
+    f.P = vflip(p.P); f.N = vflip(p.N); f.B = vflip(p.B); f.R = vflip(p.R); f.Q = vflip(p.Q); f.K = vflip(p.K);
+    f.co[1] = vflip(p.co[0]); f.co[0] = vflip(p.co[1]);
+    const u64 m = p.meta;
+    u64 meta = CDQ_META_TURN_WHITE | ((m & (CDQ_META_CASTLE_BK | CDQ_META_CASTLE_BQ)) >> 2) | ((m & (CDQ_META_CASTLE_WK | CDQ_META_CASTLE_WQ)) << 2);
+    const u64 ep = (m >> CDQ_META_EP_SHIFT) & CDQ_META_EP_MASK;
+    if (ep) meta |= (((ep - 1) ^ 56) + 1) << CDQ_META_EP_SHIFT;
+    f.meta = meta | (m & CDQ_META_REP3);
+    return f;
+}
+
+// The generator's output for a white view as a list of move CLASSES (target-square sets; classes are disjoint, each
+// target is one move, x4 on the last rank): generation is one straight-line pass, picking the r-th move is a short loop
+// over 27 sets, so a warp generates once and every lane picks its own moves from the same list.
+enum { MC_SLIDE = 0, MC_KNIGHT = 8, MC_KING = 16, MC_PUSH = 17, MC_PUSH_PROMO = 18, MC_DOUBLE = 19, MC_CAP_W = 20, MC_CAP_W_PROMO = 21,
+       MC_CAP_E = 22, MC_CAP_E_PROMO = 23, MC_CASTLE_K = 24, MC_CASTLE_Q = 25, MC_EP = 26, MC_COUNT = 27 };
+struct MoveList {
+    u64 t[MC_COUNT];
+    u64 occ, king_bb, att_opp;   // white view
+    int ep_sq, n;                // n = number of legal moves
+    bool ep_legal;               // Board.has_legal_en_passant()
+};
+struct ListVisitor {
+    MoveList& L;
+    __device__ ListVisitor(MoveList& l) : L(l) {}
+    template <int D> __device__ __forceinline__ void slide(u64 t) { L.t[MC_SLIDE + D] = t; }
+    template <int J> __device__ __forceinline__ void knight(u64 t) { L.t[MC_KNIGHT + J] = t; }
+    __device__ __forceinline__ void king(u64 t) { L.t[MC_KING] = t; }
+    __device__ __forceinline__ void pawn_push(u64 s, u64 d) { L.t[MC_PUSH] = s & ~RANK_8; L.t[MC_PUSH_PROMO] = s & RANK_8; L.t[MC_DOUBLE] = d; }
+    template <int D> __device__ __forceinline__ void pawn_cap(u64 t) {      // white: D = 6 (north-west) and 4 (north-east)
+        L.t[D == 6 ? MC_CAP_W : MC_CAP_E] = t & ~RANK_8;
+        L.t[D == 6 ? MC_CAP_W_PROMO : MC_CAP_E_PROMO] = t & RANK_8;
+    }
+    __device__ __forceinline__ void castle(bool k, bool q) { L.t[MC_CASTLE_K] = k ? 1ull : 0ull; L.t[MC_CASTLE_Q] = q ? 1ull : 0ull; }
+    __device__ __forceinline__ void ep(u64 caps, int epsq) { L.t[MC_EP] = caps; L.ep_sq = epsq; }
+};
+__device__ __forceinline__ int class_mult(int k) { return (k == MC_PUSH_PROMO || k == MC_CAP_W_PROMO || k == MC_CAP_E_PROMO) ? 4 : 1; }
+
+// `w` must be a white view (white_view(p)).  The only place the list kernels expand gen_side.
+static __device__ __noinline__ void list_moves(const Pos& w, MoveList& L) {
+    L.occ = w.co[0] | w.co[1];
+    L.king_bb = w.K & w.co[1];
+    const Props q = make_props(~L.occ);
+    L.att_opp = attack_map<0>(w, q);
+    L.ep_sq = 0;
+    ListVisitor v(L);
+    gen_side<1>(w, q, L.att_opp, v);
+    int n = 0;
+#pragma unroll 1
+    for (int k = 0; k < MC_COUNT; k++) n += popc(L.t[k]) * class_mult(k);
+    L.n = n;
+    L.ep_legal = L.t[MC_EP] != 0;
+}
+// the r-th move of the list (enumeration order = class order, targets ascending, promotions Q R B N), white-view coordinates
+static __device__ __noinline__ PlainMove pick_from_list(const MoveList& L, int r) {
+    PlainMove m;
+    if (r < 0 || r >= L.n) return m;
+    int k = 0, base = 0;
+#pragma unroll 1
+    for (; k < MC_COUNT; k++) {
+        const int c = popc(L.t[k]) * class_mult(k);
+        if (r < base + c) break;
+        base += c;
+    }
+    const int mult = class_mult(k), idx = r - base;
+    const int sq = nth_bit(L.t[k], idx / mult);
+    m.found = true;
+    m.to = sq;
+    if (mult == 4) m.promo = PT_Q - (idx % 4);
+    if (k < MC_KNIGHT) {                                  // slider: origin = first piece behind the target
+        const int d = k - MC_SLIDE;
+        const int step = (d >> 1) == 0 ? 8 : (d >> 1) == 1 ? 1 : (d >> 1) == 2 ? 9 : 7;
+        const int delta = (d & 1) ? -step : step;
+        int f = sq - delta;
+        while (!((L.occ >> f) & 1)) f -= delta;
+        m.from = f;
+    } else if (k < MC_KING) m.from = sq - knight_delta(k - MC_KNIGHT);
+    else if (k == MC_KING) m.from = lsb_sq(L.king_bb);
+    else if (k == MC_PUSH || k == MC_PUSH_PROMO) m.from = sq - 8;
+    else if (k == MC_DOUBLE) { m.from = sq - 16; m.special = MV_DOUBLE; }
+    else if (k == MC_CAP_W || k == MC_CAP_W_PROMO) m.from = sq - 7;
+    else if (k == MC_CAP_E || k == MC_CAP_E_PROMO) m.from = sq - 9;
+    else if (k == MC_CASTLE_K) { m.from = 4; m.to = 6; m.special = MV_CASTLE_K; }
+    else if (k == MC_CASTLE_Q) { m.from = 4; m.to = 2; m.special = MV_CASTLE_Q; }
+    else { m.from = sq; m.to = L.ep_sq; m.special = MV_EP; }
+    return m;
+}
+// gives-check test of categorize_moves for a white-view child (black to move there): is black's king attacked by white
+static __device__ __noinline__ bool white_view_child_in_check(const Pos& c) {
+    const Props cq = make_props(~(c.co[0] | c.co[1]));
+    return (attack_map<1>(c, cq) & c.K & c.co[0]) != 0;
+}
+// categorize_moves' weight of move m (white-view coordinates) in white view w, att_opp from pick_move
+__device__ __forceinline__ int white_view_move_weight(const Pos& w, const PlainMove& m, u64 att_opp) {
+    const u64 fb = 1ull << m.from, tb = 1ull << m.to;
+    const u64 occ = w.co[0] | w.co[1];
+    if (occ & tb) {
+        const int vt = piece_value_at(w, tb), vf = piece_value_at(w, fb);
+        return vt > vf ? 10 : (vt == vf ? 8 : 5);
+    }
+    Pos c = w;
+    apply_move(c, m);
+    if (white_view_child_in_check(c)) return 9;
+    if (att_opp & fb) return 7;
+    const int fr = m.from >> 3, ff = m.from & 7;
+    if (((w.N | w.B) & fb) && fr == 0 && (ff == 1 || ff == 2 || ff == 5 || ff == 6)) return 6;
+    if (tb & 0x0000001818000000ull) return 4;
+    if (w.K & fb) {
+        const int d = ff - (m.to & 7);
+        if (d > 1 || d < -1) return 3;
+        if (fr == 0) return 3;
+    }
+    if (w.P & fb) return 2;
+    return 1;
+}
+// the move in the coordinates of the real position
+__device__ __forceinline__ PlainMove real_move(const PlainMove& m, bool white_to_move) {
+    PlainMove o;
+    o.found = m.found; o.promo = m.promo; o.special = m.special;
+    o.from = white_to_move ? m.from : (m.from ^ 56);
+    o.to = white_to_move ? m.to : (m.to ^ 56);
+    return o;
 }
 
 } // namespace cdq

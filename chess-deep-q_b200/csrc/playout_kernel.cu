@@ -45,22 +45,18 @@ expand_kernel(const CdqBoard* __restrict__ boards, long long n, int max_children
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Pos p = load_pos(reinterpret_cast<const u64*>(boards) + i * 9);
-    const u64 occ = p.co[0] | p.co[1];
-    const Props q = make_props(~occ);
     const bool white = p.meta & CDQ_META_TURN_WHITE;
-    const u64 att_opp = white ? attack_map<0>(p, q) : attack_map<1>(p, q);
-    CountVisitor cv;
-    if (white) gen_side<1>(p, q, att_opp, cv); else gen_side<0>(p, q, att_opp, cv);
-    counts[i] = cv.n;
-    const int m = cv.n < max_children ? cv.n : max_children;
+    const Pos wv = white_view(p);            // one generator instance for both colours (movegen.cuh): its order is the child order
+    MoveList L;
+    list_moves(wv, L);
+    counts[i] = L.n;
+    const int m = L.n < max_children ? L.n : max_children;
     for (int r = 0; r < m; r++) {
-        SelectVisitor sv(r, occ, white);
-        sv.king_bb = p.K & p.co[white ? 1 : 0];
-        if (white) gen_side<1>(p, q, att_opp, sv); else gen_side<0>(p, q, att_opp, sv);
+        const PlainMove mv = pick_from_list(L, r);
         Pos c = p;
-        apply_move(c, sv);
+        apply_move(c, real_move(mv, white));
         store_pos(c, reinterpret_cast<u64*>(children) + (i * max_children + r) * 9);
-        if (weights) weights[i * max_children + r] = (unsigned char)move_category_weight(p, c, sv, att_opp, white);
+        if (weights) weights[i * max_children + r] = (unsigned char)white_view_move_weight(wv, mv, L.att_opp);
     }
 }
 

@@ -58,34 +58,23 @@ struct Forest {
 };
 
 // ---- move codes: from | to << 6 | (promotion piece type + 1) << 12 | special << 16
-__device__ __forceinline__ unsigned encode_move(const SelectVisitor& m) {
+template <class M>
+__device__ __forceinline__ unsigned encode_move(const M& m) {
     return (unsigned)m.from | ((unsigned)m.to << 6) | ((unsigned)(m.promo + 1) << 12) | ((unsigned)m.special << 16);
 }
-__device__ __forceinline__ SelectVisitor decode_move(unsigned code, u64 occ, bool white) {
-    SelectVisitor m(0, occ, white);
+__device__ __forceinline__ PlainMove decode_move(unsigned code) {
+    PlainMove m;
     m.found = true;
     m.from = code & 63; m.to = (code >> 6) & 63; m.promo = (int)((code >> 12) & 15) - 1; m.special = (code >> 16) & 7;
     return m;
 }
 
-// ---- Board.has_legal_en_passant(): the generator's en-passant tail, everything else discarded
-struct EpVisitor {
-    u64 caps = 0;
-    template <int D> __device__ __forceinline__ void slide(u64) {}
-    template <int J> __device__ __forceinline__ void knight(u64) {}
-    __device__ __forceinline__ void king(u64) {}
-    __device__ __forceinline__ void pawn_push(u64, u64) {}
-    template <int D> __device__ __forceinline__ void pawn_cap(u64) {}
-    __device__ __forceinline__ void castle(bool, bool) {}
-    __device__ __forceinline__ void ep(u64 c, int) { caps = c; }
-};
-__device__ __noinline__ bool has_legal_ep(const Pos& p) {
+// ---- Board.has_legal_en_passant(): the shared generator instance, nothing picked
+__device__ __forceinline__ bool has_legal_ep(const Pos& p) {
     if (((p.meta >> CDQ_META_EP_SHIFT) & CDQ_META_EP_MASK) <= 1) return false;
-    const Props q = make_props(~(p.co[0] | p.co[1]));
-    const bool white = p.meta & CDQ_META_TURN_WHITE;
-    EpVisitor v;
-    if (white) gen_side<1>(p, q, attack_map<0>(p, q), v); else gen_side<0>(p, q, attack_map<1>(p, q), v);
-    return v.caps != 0;
+    MoveList L;
+    list_moves(white_view(p), L);
+    return L.ep_legal;
 }
 
 // Board._transposition_key() as a 64-bit hash: the eight bitboards, turn, clean castling rights, ep square if capturable
@@ -133,34 +122,77 @@ __device__ __forceinline__ int count_repeats(const u64* hist, int hist_len, cons
     return __reduce_add_sync(0xffffffffu, c);
 }
 
+// select_weighted_moves (evaluation.py:342-366): `width` successive draws without replacement, each proportional to the weight
+// of the remaining moves; draw k takes the first move in index order (index = lane + 32 block) whose running weight sum exceeds
+// r = (mix64(seed + (k+1) GOLD) * total) >> 64 -- the arithmetic of sample_children_kernel and of the host restatement.  Every
+// lane keeps the INCLUSIVE running sum of its moves; a draw is one ballot, and removing the drawn move is one predicated
+// subtraction per block (no prefix scan and no reduction per draw: they were 40 % of the kernel's instructions).
+template <int NB>
+__device__ __forceinline__ void sample_children(const unsigned (&mv)[MOVE_BLOCKS], const unsigned (&wt)[MOVE_BLOCKS], u64 seed, int width,
+                                                unsigned* e_move, int* e_n, double* e_q, int lane) {
+    unsigned w[NB], incl[NB], cum[NB];      // w: remaining weights; incl[j]: running sum up to and including move (lane, j); cum[j]: total of blocks <= j
+    unsigned base = 0;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        w[j] = wt[j];
+        unsigned x = w[j];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += up;
+        }
+        incl[j] = base + x;
+        base += __shfl_sync(0xffffffffu, x, 31);
+        cum[j] = base;
+    }
+    unsigned total = base;
+    for (int k = 0; k < width; k++) {
+        const u64 z = mix64(seed + (u64)(k + 1) * GOLD);
+        const unsigned r = (unsigned)__umul64hi(z, (u64)total);
+        int j = 0;
+#pragma unroll
+        for (int jj = 0; jj < NB - 1; jj++) j += (r >= cum[jj]);
+        unsigned mine = 0, w_here = 0, m_here = NO_MOVE;
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++) if (jj == j) { mine = incl[jj]; w_here = w[jj]; m_here = mv[jj]; }
+        // the first move of block j whose running sum exceeds r.  A move already drawn (or beyond n) has weight 0, i.e. the
+        // running sum of its predecessor, which comes first in the ballot if it exceeds r.
+        const int pick_lane = __ffs(__ballot_sync(0xffffffffu, mine > r)) - 1;
+        const unsigned drawn = __shfl_sync(0xffffffffu, w_here, pick_lane);
+        total -= drawn;
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++) {
+            if (jj > j || (jj == j && lane >= pick_lane)) incl[jj] -= drawn;
+            if (jj >= j) cum[jj] -= drawn;
+            if (jj == j && lane == pick_lane) w[jj] = 0;
+        }
+        if (lane == pick_lane) { e_move[k] = m_here; e_n[k] = 0; e_q[k] = 0.0; }
+    }
+}
+
 // _expand_node (mcts.py:166-194) by one warp: all legal moves of `p` with their tactical weights, lane l owning moves
 // l + 32 j, then select_weighted_moves' draw of `width` children without replacement (same integer arithmetic as
 // sample_children_kernel).  Returns the number of children stored (0 for a finished game).
 __device__ __noinline__ int expand_node(const Forest& f, const Pos& p, int hmc, u64 seed, unsigned* e_move, int* e_n, double* e_q,
                                         int lane) {
-    const u64 occ = p.co[0] | p.co[1];
-    const Props q = make_props(~occ);
     const bool white = p.meta & CDQ_META_TURN_WHITE;
-    const u64 att_opp = white ? attack_map<0>(p, q) : attack_map<1>(p, q);
-    CountVisitor cv;
-    if (white) gen_side<1>(p, q, att_opp, cv); else gen_side<0>(p, q, att_opp, cv);
+    const Pos wv = white_view(p);
+    MoveList L;
+    list_moves(wv, L);                       // every lane holds the same list; lane l picks moves l, l + 32, ...
     // Board(fen).is_game_over(): no legal move (checkmate / stalemate), insufficient material, 75-move rule; a board built
     // from a FEN has no history, so no repetition rule here (mcts.py:172-177)
-    if (cv.n == 0 || insufficient_material(p) || hmc >= 150) return 0;
-    const int n = min(cv.n, 32 * MOVE_BLOCKS);
+    if (L.n == 0 || insufficient_material(p) || hmc >= 150) return 0;
+    const int n = min(L.n, 32 * MOVE_BLOCKS);
     unsigned mv[MOVE_BLOCKS], wt[MOVE_BLOCKS];
-#pragma unroll 1
-    for (int j = 0; j < MOVE_BLOCKS; j++) {
-        const int r = lane + 32 * j;
-        mv[j] = NO_MOVE; wt[j] = 0;
-        if (r < n) {
-            SelectVisitor sv(r, occ, white);
-            sv.king_bb = p.K & p.co[white ? 1 : 0];
-            if (white) gen_side<1>(p, q, att_opp, sv); else gen_side<0>(p, q, att_opp, sv);
-            Pos c = p;
-            apply_move(c, sv);
-            mv[j] = encode_move(sv);
-            wt[j] = (unsigned)move_category_weight(p, c, sv, att_opp, white);
+#pragma unroll
+    for (int j = 0; j < MOVE_BLOCKS; j++) { mv[j] = NO_MOVE; wt[j] = 0; }
+    for (int j = 0; 32 * j < n; j++) {       // warp-uniform trip count
+        const PlainMove m = pick_from_list(L, lane + 32 * j);
+        if (m.found) {
+            const unsigned code = encode_move(real_move(m, white));
+            const unsigned weight = (unsigned)white_view_move_weight(wv, m, L.att_opp);
+#pragma unroll
+            for (int jj = 0; jj < MOVE_BLOCKS; jj++) if (jj == j) { mv[jj] = code; wt[jj] = weight; }
         }
     }
     const int width = f.width;
@@ -168,31 +200,9 @@ __device__ __noinline__ int expand_node(const Forest& f, const Pos& p, int hmc, 
         if (lane < n) { e_move[lane] = mv[0]; e_n[lane] = 0; e_q[lane] = 0.0; }
         return n;
     }
-    for (int k = 0; k < width; k++) {
-        unsigned blk[MOVE_BLOCKS], total = 0;
-#pragma unroll
-        for (int j = 0; j < MOVE_BLOCKS; j++) { blk[j] = __reduce_add_sync(0xffffffffu, wt[j]); total += blk[j]; }
-        const u64 z = mix64(seed + (u64)(k + 1) * GOLD);
-        unsigned r = (unsigned)__umul64hi(z, (u64)total);
-        int j = 0;
-        while (j < MOVE_BLOCKS - 1 && r >= blk[j]) { r -= blk[j]; j++; }
-        unsigned mine = 0, mymove = NO_MOVE;
-#pragma unroll
-        for (int jj = 0; jj < MOVE_BLOCKS; jj++) if (jj == j) { mine = wt[jj]; mymove = mv[jj]; }
-        unsigned incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
-        }
-        const unsigned hit = __ballot_sync(0xffffffffu, incl > r);
-        const int pick_lane = __ffs(hit) - 1;
-        if (lane == pick_lane) {
-#pragma unroll
-            for (int jj = 0; jj < MOVE_BLOCKS; jj++) if (jj == j) wt[jj] = 0;
-            e_move[k] = mymove; e_n[k] = 0; e_q[k] = 0.0;
-        }
-    }
+    if (n <= 32) sample_children<1>(mv, wt, seed, width, e_move, e_n, e_q, lane);
+    else if (n <= 64) sample_children<2>(mv, wt, seed, width, e_move, e_n, e_q, lane);
+    else sample_children<MOVE_BLOCKS>(mv, wt, seed, width, e_move, e_n, e_q, lane);
     return width;
 }
 
@@ -205,7 +215,7 @@ __device__ __forceinline__ Pushed push_move(const Pos& p, unsigned code, int hmc
     Pushed o;
     const u64 occ = p.co[0] | p.co[1];
     const bool white = p.meta & CDQ_META_TURN_WHITE;
-    const SelectVisitor m = decode_move(code, occ, white);
+    const PlainMove m = decode_move(code);
     o.c = p;
     apply_move(o.c, m);
     const u64 fb = 1ull << m.from, tb = 1ull << m.to;
@@ -226,7 +236,7 @@ __device__ __forceinline__ Pushed push_move(const Pos& p, unsigned code, int hmc
 }
 
 template <int MAXW>
-__global__ void __launch_bounds__(MAXW * 32)
+__global__ void __launch_bounds__(MAXW * 32, MAXW <= 8 ? 2 : 1)
 tree_level_kernel(const Forest f, int level, int wave, int wave_size, double ew, double alpha, int max_moves) {
     __shared__ u64 sh_key[MAXW];
     __shared__ int sh_need[MAXW], sh_node[MAXW], sh_new[MAXW];
@@ -307,55 +317,73 @@ tree_level_kernel(const Forest f, int level, int wave, int wave_size, double ew,
     if (dup_of >= 0) node = sh_node[dup_of];
     if (alive && node < 0) alive = false;
 
-    // ---- phase 2: action selection, simulations of the wave in worker order (claims of never-taken children are what
-    //      makes the order matter; mcts.py:34-67)
+    // ---- phase 2: action selection (mcts.py:34-67).  The reference's semantics are sequential -- simulations take their
+    //      action in worker order, and a simulation that finds never-taken children claims a random one of them -- but the only
+    //      state one simulation changes for another is that mask of never-taken children of THEIR COMMON node (N and Q move at
+    //      the back-up, after the wave).  So every simulation replays the claims of the lower-numbered simulations standing on
+    //      its node (their draws are counter-based hashes it can recompute) and then takes its own action: all in parallel, no
+    //      turn-taking; the highest-numbered simulation on a node stores the mask it leaves behind.
+    if (lane == 0) sh_node[w] = alive ? node : -1;
+    __syncthreads();
     unsigned move = NO_MOVE;
-    for (int turn = 0; turn < wave_size; turn++) {
-        if (turn == w && alive) {
-            const long long nb = (long long)t * f.max_nodes + node, eb = nb * f.width;
-            const int nchild = f.n_nchild[nb];
-            if (nchild == 0) alive = false;              // terminal node: `if not action ... break` (mcts.py:139)
-            else {
-                const u64 z = mix64(search_seed ^ mix64(((u64)(unsigned)wave << 32) | ((u64)(unsigned)w << 8) | (u64)(unsigned)depth |
-                                                        0x5E1EC70000000000ull));
-                const unsigned fresh = f.n_unexp[nb];
-                int child;
-                if (fresh) {                             // random.choice(unexplored)
-                    const int k = (int)__umul64hi(z, (u64)__popc(fresh));
-                    unsigned m = fresh;
-                    for (int i = 0; i < k; i++) m &= m - 1;
-                    child = __ffs(m) - 1;
-                    if (lane == 0) f.n_unexp[nb] = fresh & ~(1u << child);
-                } else {
-                    const int nc = lane < nchild ? f.e_n[eb + lane] : 0;
-                    const int total = __reduce_add_sync(0xffffffffu, nc);
-                    if (total == 0) child = (int)__umul64hi(z, (u64)nchild);      // random.choice(actions)
-                    else {
-                        // explicit IEEE operations in the reference's order (no FMA contraction), so that the argmax is the
-                        // one Python floats give
-                        const double beta = max_moves > 0 ? __ddiv_rn((double)(root_ply + depth), (double)max_moves) : 0.5;
-                        const double eff = __dmul_rn(ew, __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.5, alpha), beta)));
-                        const double nk = __dadd_rn((double)nc, 1e-10);
-                        // as written in the reference: the running mean Q is divided by N once more (mcts.py:61-62)
-                        double ucb = lane < nchild ? __dadd_rn(__ddiv_rn(f.e_q[eb + lane], nk),
-                                                               __dmul_rn(eff, sqrt(__ddiv_rn(log(__dadd_rn((double)total, 1e-10)), nk))))
-                                                   : -INFINITY;
-                        int arg = lane;
-#pragma unroll
-                        for (int d = 16; d >= 1; d >>= 1) {       // np.argmax: the first of equal maxima
-                            const double ou = __shfl_xor_sync(0xffffffffu, ucb, d);
-                            const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
-                            if (ou > ucb || (ou == ucb && oa < arg)) { ucb = ou; arg = oa; }
-                        }
-                        child = arg;
-                    }
-                }
-                move = f.e_move[eb + child];
-                if (lane == 0) { f.s_path_node[s * MAX_DEPTH + depth] = node; f.s_path_child[s * MAX_DEPTH + depth] = child; }
+    unsigned fresh_after = 0;
+    bool store_mask = false;
+    if (alive) {
+        const long long nb = (long long)t * f.max_nodes + node, eb = nb * f.width;
+        const int nchild = f.n_nchild[nb];
+        if (nchild == 0) alive = false;                  // terminal node: `if not action ... break` (mcts.py:139)
+        else {
+            auto draw = [&](int worker) {
+                return mix64(search_seed ^ mix64(((u64)(unsigned)wave << 32) | ((u64)(unsigned)worker << 8) | (u64)(unsigned)depth |
+                                                 0x5E1EC70000000000ull));
+            };
+            auto kth_bit = [](unsigned m, int k) {
+                for (int i = 0; i < k; i++) m &= m - 1;
+                return __ffs(m) - 1;
+            };
+            unsigned fresh = f.n_unexp[nb];
+            store_mask = true;
+            for (int a = 0; a < W; a++) {
+                if (a == w || sh_node[a] != node) continue;
+                if (a > w) { store_mask = false; continue; }
+                if (fresh) fresh &= ~(1u << kth_bit(fresh, (int)__umul64hi(draw(a), (u64)__popc(fresh))));
             }
+            const u64 z = draw(w);
+            int child;
+            if (fresh) {                                 // random.choice(unexplored)
+                child = kth_bit(fresh, (int)__umul64hi(z, (u64)__popc(fresh)));
+                fresh &= ~(1u << child);
+            } else {
+                const int nc = lane < nchild ? f.e_n[eb + lane] : 0;
+                const int total = __reduce_add_sync(0xffffffffu, nc);
+                if (total == 0) child = (int)__umul64hi(z, (u64)nchild);      // random.choice(actions)
+                else {
+                    // explicit IEEE operations in the reference's order (no FMA contraction), so that the argmax is the
+                    // one Python floats give
+                    const double beta = max_moves > 0 ? __ddiv_rn((double)(root_ply + depth), (double)max_moves) : 0.5;
+                    const double eff = __dmul_rn(ew, __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.5, alpha), beta)));
+                    const double nk = __dadd_rn((double)nc, 1e-10);
+                    // as written in the reference: the running mean Q is divided by N once more (mcts.py:61-62)
+                    double ucb = lane < nchild ? __dadd_rn(__ddiv_rn(f.e_q[eb + lane], nk),
+                                                           __dmul_rn(eff, sqrt(__ddiv_rn(log(__dadd_rn((double)total, 1e-10)), nk))))
+                                               : -INFINITY;
+                    int arg = lane;
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) {       // np.argmax: the first of equal maxima
+                        const double ou = __shfl_xor_sync(0xffffffffu, ucb, d);
+                        const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+                        if (ou > ucb || (ou == ucb && oa < arg)) { ucb = ou; arg = oa; }
+                    }
+                    child = arg;
+                }
+            }
+            fresh_after = fresh;
+            move = f.e_move[eb + child];
+            if (lane == 0) { f.s_path_node[s * MAX_DEPTH + depth] = node; f.s_path_child[s * MAX_DEPTH + depth] = child; }
         }
-        __syncthreads();
     }
+    __syncthreads();                                     // every simulation has read its node's mask
+    if (alive && store_mask && lane == 0) f.n_unexp[(long long)t * f.max_nodes + node] = fresh_after;
 
     // ---- phase 3: Board.push, halfmove clock, repetition (all simulations in parallel)
     if (move != NO_MOVE) {
@@ -573,6 +601,7 @@ int cdq_forest_search(CdqForest* F, const CdqNet* net, int iterations, float exp
     for (int first = 0, wave = 0; first < iterations; first += f.workers, wave++) {
         const int wave_size = iterations - first < f.workers ? iterations - first : f.workers;
         for (int level = 0; level < f.depth; level++) {
+            ProfileScope ps(KK_PLAYOUT, st);
             if (f.workers <= 8) launch_level<8>(f, level, wave, wave_size, ew, alpha, max_moves, st);
             else if (f.workers <= 16) launch_level<16>(f, level, wave, wave_size, ew, alpha, max_moves, st);
             else launch_level<32>(f, level, wave, wave_size, ew, alpha, max_moves, st);

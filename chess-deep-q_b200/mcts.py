@@ -346,13 +346,19 @@ def self_play_games(neural_net, n_games, max_moves=200, iterations=50, samples_p
     forest = _cached_forest(n_games, num_workers, widths, iterations)
     begin = np.concatenate([_startpos()] * n_games) if start is None else as_records(start)
     forest.set_games(begin, seeds)
-    positions = [[begin[g:g + 1].copy()] for g in range(n_games)]
-    scores, moves, rewards, losses = ([[] for _ in range(n_games)] for _ in range(4))
-    flags_of = [0] * n_games
-    active = np.ones(n_games, bool)
-    score0, flags0 = evaluate_batch(begin)
-    active &= (flags0.cpu().numpy() & 0x70) == 0          # `while not self.board.is_game_over()` (chess_ai.py:141)
+    # per-game logs as arrays (the per-ply bookkeeping below is vectorised over the games)
+    positions = np.zeros((n_games, max_moves + 1), BOARD_DTYPE)
+    positions[:, 0] = begin
+    scores = np.zeros((n_games, max_moves), np.float64)
+    rewards = np.zeros((n_games, max_moves), np.float64)
+    codes = np.zeros((n_games, max_moves), np.uint32)
+    length = np.zeros(n_games, np.int64)
+    flags_of = np.zeros(n_games, np.int64)
+    losses = [[] for _ in range(n_games)]
+    _, flags0 = evaluate_batch(begin)
+    active = (flags0.cpu().numpy() & 0x70) == 0          # `while not self.board.is_game_over()` (chess_ai.py:141)
     pending = 0
+    rows = np.arange(n_games)
     for ply in range(max_moves):
         if not active.any():
             break
@@ -363,36 +369,31 @@ def self_play_games(neural_net, n_games, max_moves=200, iterations=50, samples_p
         rec = forest.game_boards.cpu().numpy().view(np.uint64).reshape(-1).view(BOARD_DTYPE)     # the ply's one synchronisation
         status = forest.game_status.cpu().numpy()
         best = forest.best_move.cpu().numpy().view(np.uint32)
-        score_h, flags_h = score.cpu().numpy(), flags.cpu().numpy()
-        for g in np.nonzero(active)[0]:
-            if not status[g] & 1:                       # `if move is None: break` (chess_ai.py:148-149)
-                active[g] = False
-                continue
-            before = positions[g][-1]
-            positions[g].append(rec[g:g + 1].copy())
-            scores[g].append(float(score_h[g]))         # raw_score (chess_ai.py:161)
-            moves[g].append(_decode_move(best[g]))
-            fl = int(flags_h[g])
-            if fl & 0x10:                               # chess_ai.py:174-184
-                reward, done = -1.0, True
-            elif fl & 0x60:
-                reward, done = 0.0, True
-            else:
-                reward, done = 0.01 * math.tanh(float(score_h[g]) / 10.0), False
-            rewards[g].append(reward)
-            flags_of[g] = fl | (int(status[g]) << 24)
-            if agent is not None:
-                agent.store_transition(before, moves[g][-1], reward, rec[g:g + 1], done)
+        score_h, fl = score.cpu().numpy(), flags.cpu().numpy().astype(np.int64)
+        moved = active & ((status & 1) != 0)               # `if move is None: break` (chess_ai.py:148-149)
+        g = rows[moved]
+        k = length[g]
+        positions[g, k + 1] = rec[g]
+        scores[g, k] = score_h[g]                           # raw_score (chess_ai.py:161)
+        codes[g, k] = best[g]
+        mate, draw = (fl[g] & 0x10) != 0, (fl[g] & 0x60) != 0                # chess_ai.py:174-184
+        rewards[g, k] = np.where(mate, -1.0, np.where(draw, 0.0, 0.01 * np.tanh(score_h[g] / 10.0)))
+        flags_of[g] = fl[g] | (status[g].astype(np.int64) << 24)
+        length[g] = k + 1
+        if agent is not None:
+            for gi, ki, done in zip(g, k, mate | draw):
+                agent.store_transition(positions[gi, ki:ki + 1], _decode_move(codes[gi, ki]), float(rewards[gi, ki]), positions[gi, ki + 1:ki + 2], bool(done))
                 pending += 1
                 if len(agent.memory) >= agent.batch_size and pending >= train_every:
-                    losses[g].append(agent.train())
+                    losses[gi].append(agent.train())
                     pending = 0
-            if (fl & 0x70) or (status[g] & 6):          # is_game_over(): mate, stalemate, material, fivefold, 75 moves
-                active[g] = False
+        over = ((fl & 0x70) != 0) | ((status & 6) != 0)     # is_game_over(): mate, stalemate, material, fivefold, 75 moves
+        active = moved & ~over
         if on_ply is not None:
             on_ply(ply, active)
-    return [{"positions": np.concatenate(positions[g]), "scores": scores[g], "moves": moves[g], "rewards": rewards[g],
-             "result_flags": flags_of[g], "losses": losses[g]} for g in range(n_games)]
+    return [{"positions": positions[i, :length[i] + 1].copy(), "scores": scores[i, :length[i]].tolist(),
+             "moves": [_decode_move(c) for c in codes[i, :length[i]]], "rewards": rewards[i, :length[i]].tolist(),
+             "result_flags": int(flags_of[i]), "losses": losses[i]} for i in range(n_games)]
 
 
 def self_play_game(neural_net, max_moves=200, iterations=50, samples_per_level=None, seed=42, start=None,

@@ -59,3 +59,19 @@ for n_games in (64, 1024):
     steps = sum(len(g["losses"]) for g in games)
     print(json.dumps({"games": n_games, "with_training": True, "moves_played": moves, "train_steps": steps, "seconds": sec,
                       "leaf_evals_per_s": moves * iterations / sec, "plies_per_s": moves / sec}), flush=True)
+# per-kernel-kind device time of one 1024-game ply (event pairs): tree level kernels vs the leaf evaluation
+import ctypes
+forest = cdq.mcts.DeviceForest(1024, 8, widths, iterations)
+forest.set_games(np.concatenate([cdq.mcts._startpos()] * 1024), list(range(1024)))
+for _ in range(2):
+    forest.search(net, iterations, ew)
+    forest.advance()
+torch.cuda.synchronize()
+L.cdq_profile_enable(1)
+forest.search(net, iterations, ew)
+torch.cuda.synchronize()
+L.cdq_profile_enable(0)
+kms, kcnt = (ctypes.c_double * 8)(), (ctypes.c_uint64 * 8)()
+cdq._lib.check(L.cdq_profile_collect(kms, kcnt))
+print(json.dumps({"one_search_1024_games_ms": {"eval_terms": kms[0], "conv": kms[1], "fc": kms[2], "tree_level": kms[4]},
+                  "launches": {"eval_terms": kcnt[0], "conv": kcnt[1], "fc": kcnt[2], "tree_level": kcnt[4]}}))

@@ -23,7 +23,7 @@ def mix64(z):
 
 
 def mulhi(z, n):
-    return (z * n) >> 64
+    return (int(z) * int(n)) >> 64
 
 
 class Restatement:
@@ -49,7 +49,7 @@ class Restatement:
             cdq._lib.check(L.cdq_eval_terms(d.data_ptr(), 1, 0, None, None, flags.data_ptr(), st))
             c = int(counts.item())
             recs = kids[0, :c].cpu().numpy().view(np.uint64).reshape(-1).view(cdq.BOARD_DTYPE).copy()
-            self._kids[key] = (recs, wts[0, :c].cpu().numpy().astype(int), int(flags.item()))
+            self._kids[key] = (recs, [int(x) for x in wts[0, :c].cpu().numpy()], int(flags.item()))
         return self._kids[key]
 
     # ------------------------------------------------------------------ restated bookkeeping
