@@ -282,6 +282,22 @@ def dqn_cpu_reference(steps=2, B=4096):
             "torch_threads": torch.get_num_threads(), "kind": "reference maths on torch-CPU fp32, batch %d, %d steps" % (B, steps)}
 
 
+def eval_kernel_alu(positions_per_s):
+    """K1's honest roof: the integer (alu) pipe.  The pipe utilisation is a hardware counter, so it comes from the committed
+    ncu capture of one 1M-position launch (profiles/r2_eval_kernel.json); this run's own K1 rate is put next to the rate of
+    that capture so the fraction can be scaled."""
+    path = os.path.join(ROOT, "profiles", "r2_eval_kernel.json")
+    if not os.path.exists(path):
+        return None
+    j = json.load(open(path))
+    captured_rate = j["captured_positions"] / (j["time_us"] * 1e-6)
+    return {"bound": "alu pipe (LOP3/SHF/IADD3 at one warp instruction per 2 cycles per SMSP)",
+            "frac_in_capture": j["alu_pipe_pct_of_peak"] / 100.0, "issue_slots_in_capture": j["issue_slots_pct_of_peak"] / 100.0,
+            "capture_positions_per_s": captured_rate, "this_run_positions_per_s": positions_per_s,
+            "frac_scaled_to_this_run": (j["alu_pipe_pct_of_peak"] / 100.0) * positions_per_s / captured_rate if positions_per_s else None,
+            "source": "profiles/r2_eval_kernel.json (ncu --set full, sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active)"}
+
+
 def workload_config(n):
     """The workload both arms are quoted on (BASELINE configs[1] at the default size)."""
     return {"workload": "BASELINE configs[1]: %d random-playout positions per GPU per step, "
@@ -600,7 +616,8 @@ def main():
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kind::f16 shares the bf16 rate)",
                 "kernel_ms_per_step": {kinds[k][0]: kms[k] / args.steps for k in kinds if kms[k] > 0},
                 "eval_kernel_hbm": {"achieved_GBps": n * args.steps * 84 / (kms[0] * 1e-3) / 1e9 if kms[0] else None,
-                                    "peak_GBps": peaks["hbm"], "note": "84 B/position; integer-issue bound"}}
+                                    "peak_GBps": peaks["hbm"], "note": "84 B/position; integer-issue bound"},
+                "eval_kernel_alu": eval_kernel_alu(n * args.steps / (kms[0] * 1e-3) if kms[0] else None)}
 
     # ---- BASELINE configs[2] as a throughput line: Russian Doll MCTS self-play, device-resident search, 1 024 lockstep games
     selfplay = None

@@ -33,6 +33,8 @@ SIGNATURES = {
     "cdq_train_workspace_bytes": (c_size_t, [c_int64]),
     "cdq_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   ctypes.c_double, ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdq_train_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                               ctypes.c_double, ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdq_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.c_float, ctypes.c_float,
                               ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
     "cdq_dp_adam_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_float,
@@ -83,6 +85,12 @@ MAX_RANKS = 8
 
 class CdqDpPeers(ctypes.Structure):
     _fields_ = [("params", c_void_p * MAX_RANKS), ("grads", c_void_p * MAX_RANKS), ("flags", c_void_p * MAX_RANKS)]
+
+
+class CdqOptimizer(ctypes.Structure):
+    _fields_ = [("peers", CdqDpPeers), ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("d_m", c_void_p), ("d_v", c_void_p),
+                ("n_params_padded", c_int64), ("d_step", c_void_p), ("d_grid_bar", c_void_p), ("lr", ctypes.c_float),
+                ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float)]
 
 
 class CdqError(RuntimeError):

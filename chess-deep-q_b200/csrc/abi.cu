@@ -44,9 +44,9 @@ constexpr long long PIPE_MIN_POSITIONS = 512 * 1024;   // measured break-even is
 // ---- run-time switches: read from the environment once, changed afterwards only through cdq_set_option
 static std::atomic<int> g_opt[OPT_COUNT];
 static std::once_flag g_opt_once;
-static const char* const OPT_NAME[OPT_COUNT] = {"pipe", "fc_split", "host_ramp", "dp_timeout_s"};
-static const char* const OPT_ENV[OPT_COUNT] = {"CDQ_PIPE", "CDQ_FC_SPLIT", "CDQ_HOST_RAMP", "CDQ_DP_TIMEOUT_S"};
-static const int OPT_DEFAULT[OPT_COUNT] = {0, 1, 1, 600};
+static const char* const OPT_NAME[OPT_COUNT] = {"pipe", "fc_split", "host_ramp", "dp_timeout_s", "train_split_optimizer"};
+static const char* const OPT_ENV[OPT_COUNT] = {"CDQ_PIPE", "CDQ_FC_SPLIT", "CDQ_HOST_RAMP", "CDQ_DP_TIMEOUT_S", "CDQ_TRAIN_SPLIT_OPT"};
+static const int OPT_DEFAULT[OPT_COUNT] = {0, 1, 1, 600, 0};
 static void init_options() {
     std::call_once(g_opt_once, [] {
         for (int k = 0; k < OPT_COUNT; k++) {
@@ -347,6 +347,30 @@ int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeig
     return train_fwd_bwd(net, target_net, *d_weights, d_states, d_next_states, d_reward, d_done, n,
                          mean_over > 0.0 ? mean_over : (double)n, gamma, loss_kind,
                          *d_grads, d_loss, d_workspace, (cudaStream_t)stream);
+}
+
+int cdq_train_step(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights, const CdqBoard* d_states,
+                   const CdqBoard* d_next_states, const float* d_reward, const float* d_done, int64_t n, double mean_over, float gamma,
+                   int loss_kind, const CdqWeights* d_grads, float* d_loss, void* d_workspace, size_t workspace_bytes,
+                   const CdqOptimizer* opt, void* stream) {
+    if (!net || !target_net || !net->loaded || !target_net->loaded || !d_weights || !d_grads || !d_loss || n <= 0 || !d_states ||
+        !d_next_states || !d_reward || !d_done || !d_workspace || !opt || (loss_kind & 0xff) > CDQ_LOSS_HUBER ||
+        (loss_kind & ~(0xff | CDQ_TRAIN_WS_PERSISTENT | CDQ_TRAIN_REPACK | CDQ_TRAIN_ZERO_LOSS)))
+        return CDQ_E_BADARG;
+    if (opt->world < 1 || opt->world > CDQ_MAX_RANKS || opt->rank < 0 || opt->rank >= opt->world || !opt->d_m || !opt->d_v || !opt->d_step ||
+        !opt->d_grid_bar || opt->n_params_padded != ((CDQ_NPARAMS + 3) / 4) * 4)
+        return CDQ_E_BADARG;
+    for (int p = 0; p < opt->world; p++)
+        if (!opt->peers.params[p] || !opt->peers.grads[p] || !opt->peers.flags[p]) return CDQ_E_BADARG;
+    // the two-launch optimizer addresses fc1.weight by its offset in the flat vector: the views must be that vector's
+    if (d_weights->conv1_w != opt->peers.params[opt->rank] || d_weights->fc1_w != opt->peers.params[opt->rank] + 21984 ||
+        d_grads->conv1_w != opt->peers.grads[opt->rank] || d_grads->fc1_w != opt->peers.grads[opt->rank] + 21984)
+        return CDQ_E_BADARG;
+    if (workspace_bytes < train_workspace_bytes(n)) return CDQ_E_WORKSPACE;
+    if (int e = check_device()) return e;
+    release_persisting_l2();
+    return train_fwd_bwd(net, target_net, *d_weights, d_states, d_next_states, d_reward, d_done, n,
+                         mean_over > 0.0 ? mean_over : (double)n, gamma, loss_kind, *d_grads, d_loss, d_workspace, (cudaStream_t)stream, opt);
 }
 
 int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n_params, int step, float lr,

@@ -20,7 +20,9 @@ struct PackedNet {
     const float* fc2_b;
 };
 
-int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me = nullptr);   // fp32 parameters -> all of p
+int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me = nullptr, int part = 0);   // fp32 parameters -> p
+int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float* v, long long n_padded, int* d_step,
+                   unsigned* grid_bar, float lr, float b1, float b2, float eps, cudaStream_t st, int part);
 int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream_t st);   // 1 bit per ReLU(conv2) output, dgrad's order
 int launch_fc1_dgrad(const __half* dz1h, const unsigned* relu_mask, const __half* fc1tp, long long n, __half* dz2_boards,
                      cudaStream_t st);
@@ -40,8 +42,15 @@ int launch_fc_head(const __half* act2, long long n, const PackedNet& net, float*
 // routes batches of at most FC_SPLIT_MAX_TILES tiles of 128 positions there unless CDQ_FC_SPLIT=0
 constexpr long long FC_SPLIT_MAX_TILES = 64;
 bool fc_split_enabled();
+// the backward head fused into the online network's fc kernel of the replay step (fc_split_kernel.cu, TRAIN)
+struct TrainHead {
+    const float* qn; const float* reward; const float* done;     // target values, rewards, done flags [n] (qn / done unused in upstream mode)
+    float gamma, inv_n, scale; int loss_kind;
+    __half* dz1h;                                                // fc1 pre-activation gradient, fp16 tiles scaled by `scale`
+    float* g_fc2_w; float* g_fc2_b; float* g_fc1_b; float* loss;  // accumulated
+};
 int launch_fc_head_split(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
-                         float* leaf, float* hidden, cudaStream_t st);
+                         float* leaf, float* hidden, cudaStream_t st, const TrainHead* train_head = nullptr);
 
 size_t train_workspace_bytes(long long n);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2,
@@ -53,7 +62,8 @@ struct CdqNet;
 namespace cdq {
 int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
                   const CdqBoard* next_states, const float* reward, const float* done, long long n, double mean_over,
-                  float gamma, int loss_kind, const CdqWeights& g, float* loss, void* ws_base, cudaStream_t st);
+                  float gamma, int loss_kind, const CdqWeights& g, float* loss, void* ws_base, cudaStream_t st,
+                  const CdqOptimizer* opt = nullptr);
 }
 
 // what the opaque C handle points to

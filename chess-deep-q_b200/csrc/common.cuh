@@ -28,7 +28,7 @@ inline void once_per_device(int slot, F&& f) {      // e.g. raising a kernel's d
 
 // ---- run-time switches (cdq_set_option / cdq_get_option).  Each is initialised ONCE from its environment variable
 // when the library is first used; no call path reads the environment afterwards.
-enum Option { OPT_PIPE, OPT_FC_SPLIT, OPT_HOST_RAMP, OPT_DP_TIMEOUT_S, OPT_COUNT };
+enum Option { OPT_PIPE, OPT_FC_SPLIT, OPT_HOST_RAMP, OPT_DP_TIMEOUT_S, OPT_TRAIN_SPLIT_OPT, OPT_COUNT };
 int option(int which);
 
 // every kernel launch made by the library bumps this (bench.py reports it as gpu_launches)

@@ -60,8 +60,14 @@ __device__ __forceinline__ bool wait_peers(const unsigned* my_flags, int world, 
 
 __global__ void __launch_bounds__(DP_THREADS)
 dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ m, float* __restrict__ v,
-               long long n_chunks, int* __restrict__ d_step, unsigned* __restrict__ grid_bar, float lr, float b1, float b2,
-               float eps, unsigned long long timeout_ns) {
+               long long chunk_lo, long long chunk_hi, long long chunk_lo2, long long chunk_hi2, int phase, int bump,
+               int* __restrict__ d_step, unsigned* __restrict__ grid_bar_base, float lr, float b1, float b2, float eps,
+               unsigned long long timeout_ns) {
+    // phase: a step may be applied in two launches (fc1.weight early, the rest at the end of the backward pass); each
+    // launch of a step uses its own arrival counters (grid_bar + 4 phase) and its own flag row (flags + CDQ_MAX_RANKS phase);
+    // only the launch with bump = 1 advances Adam's step counter, both use t = *d_step + 1
+    unsigned* __restrict__ grid_bar = grid_bar_base + 4 * phase;
+    const int flag_off = CDQ_MAX_RANKS * phase;
     __shared__ float s_bc[2];
     const unsigned long long deadline = globaltimer_ns() + timeout_ns;
     // both counters are read by every thread before block 0 bumps them at the very end
@@ -73,13 +79,16 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
         s_bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
     }
     // ---- A: this rank's gradients are complete (stream order); tell every peer, wait for all of them
-    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch - 1);
-    const bool late = wait_peers(peers.flags[rank], world, epoch - 1, deadline, grid_bar + 2);
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + flag_off + rank, epoch - 1);
+    const bool late = wait_peers(peers.flags[rank] + flag_off, world, epoch - 1, deadline, grid_bar_base + 2);
     const float bc1 = s_bc[0], bc2_sqrt = s_bc[1], inv_world = 1.f / (float)world;
 
     // ---- reduce-scatter + Adam + all-gather on this rank's slice (skipped when a peer's gradients never arrived)
+    // the chunks [chunk_lo, chunk_hi) followed by [chunk_lo2, chunk_hi2) form one virtual range that is sliced over the ranks
+    const long long n1 = chunk_hi - chunk_lo, n_chunks = n1 + (chunk_hi2 - chunk_lo2);
     const long long lo = n_chunks * rank / world, hi = late ? 0 : n_chunks * (rank + 1) / world;
-    for (long long c = lo + (long long)blockIdx.x * DP_THREADS + threadIdx.x; c < hi; c += (long long)gridDim.x * DP_THREADS) {
+    for (long long ci = lo + (long long)blockIdx.x * DP_THREADS + threadIdx.x; ci < hi; ci += (long long)gridDim.x * DP_THREADS) {
+        const long long c = ci < n1 ? chunk_lo + ci : chunk_lo2 + (ci - n1);
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int p = 0; p < world; p++) {
             const float4 x = reinterpret_cast<const float4*>(peers.grads[p])[c];
@@ -109,18 +118,18 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned target = gen * gridDim.x;                 // grid_bar[0] is never reset
-        atomicAdd(grid_bar, 1u);
+        // arrival counter that wraps to 0 with the last CTA of THIS launch (launches of different sizes share it); the last
+        // arriver publishes the generation, block 0 waits for it (co-resident cooperative grid: always arrives)
+        if (atomicInc(grid_bar, gridDim.x - 1) == gridDim.x - 1) { __threadfence(); atomicExch(grid_bar + 3, gen); }
         if (blockIdx.x == 0) {
-            // co-resident CTAs of THIS launch (cooperative grid): always arrive, no time limit needed
-            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) { }
+            while (*reinterpret_cast<volatile unsigned*>(grid_bar + 3) != gen) { }
             __threadfence_system();
         }
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
-    wait_peers(peers.flags[rank], world, epoch, deadline, grid_bar + 2);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *d_step = step; grid_bar[1] = gen; }
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + flag_off + rank, epoch);
+    wait_peers(peers.flags[rank] + flag_off, world, epoch, deadline, grid_bar_base + 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { if (bump) *d_step = step; grid_bar[1] = gen; }
 }
 
 // world = 1: no peers, so no flags and no system-scope fences.  One 16-byte chunk per thread (the grid is
@@ -129,9 +138,13 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
 // bumped by block 0 after every CTA has read it, through the same never-reset arrival counter.
 __global__ void __launch_bounds__(DP_THREADS)
 adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v,
-                   long long n_chunks, int* __restrict__ d_step, unsigned* __restrict__ grid_bar, float lr, float b1, float b2,
-                   float eps) {
+                   long long chunk_lo, long long chunk_hi, long long chunk_lo2, long long chunk_hi2, int phase, int bump,
+                   int* __restrict__ d_step, unsigned* __restrict__ grid_bar_base, float lr, float b1, float b2, float eps) {
+    // the chunks [chunk_lo, chunk_hi) followed by [chunk_lo2, chunk_hi2) (the parameters before and after fc1.weight when a
+    // step is applied in two launches); phase / bump as in dp_adam_kernel
     __shared__ float s_bc[2];
+    unsigned* __restrict__ grid_bar = grid_bar_base + 4 * phase;
+    const long long n1 = chunk_hi - chunk_lo, n_chunks = n1 + (chunk_hi2 - chunk_lo2);
     const int step = *d_step + 1;
     const unsigned gen = grid_bar[1] + 1u;
     if (threadIdx.x == 0) {
@@ -139,8 +152,9 @@ adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float*
         s_bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)step));
     }
     for (long long c0 = (long long)blockIdx.x * DP_THREADS; c0 < n_chunks; c0 += (long long)gridDim.x * DP_THREADS) {
-        const long long c = c0 + threadIdx.x;
-        const bool live = c < n_chunks;
+        const long long ci = c0 + threadIdx.x;
+        const bool live = ci < n_chunks;
+        const long long c = ci < n1 ? chunk_lo + ci : chunk_lo2 + (ci - n1);
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f), mi = g, vi = g, pi = g;
         if (live) {
             g = reinterpret_cast<const float4*>(grads)[c];
@@ -168,23 +182,29 @@ adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float*
     }
     __syncthreads();                                     // every thread of this CTA has read d_step / grid_bar[1]
     if (threadIdx.x == 0) {
-        const unsigned target = gen * gridDim.x;
-        atomicAdd(grid_bar, 1u);
+        if (atomicInc(grid_bar, gridDim.x - 1) == gridDim.x - 1) atomicExch(grid_bar + 3, gen);
         if (blockIdx.x == 0) {
-            while ((int)(*reinterpret_cast<volatile unsigned*>(grid_bar) - target) < 0) { }   // co-resident CTAs of this cooperative launch
-            *d_step = step;
+            while (*reinterpret_cast<volatile unsigned*>(grid_bar + 3) != gen) { }   // co-resident CTAs of this cooperative launch
+            if (bump) *d_step = step;
             grid_bar[1] = gen;
         }
     }
 }
 
+// part: 0 = the whole vector in one launch; 1 = fc1.weight only (phase 0, no step bump); 2 = everything else (phase 1, bumps).
+// The flat vector is laid out in the reference's parameter order, so fc1.weight is chunks [FC1_LO, FC1_HI).
+constexpr long long FC1_LO = (32 * 12 * 9 + 32 + 64 * 32 * 9 + 64) / 4, FC1_HI = FC1_LO + 256 * 4096 / 4;
 int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float* v, long long n_padded, int* d_step,
-                   unsigned* grid_bar, float lr, float b1, float b2, float eps, cudaStream_t st) {
-    const long long n_chunks = n_padded / 4;
-    const long long slice = (n_chunks + world - 1) / world;
-    int grid = (int)((slice + DP_THREADS - 1) / DP_THREADS);
+                   unsigned* grid_bar, float lr, float b1, float b2, float eps, cudaStream_t st, int part) {
+    const long long all_chunks = n_padded / 4;
+    const int phase = part == 2 ? 1 : 0, bump = part == 1 ? 0 : 1;
     const int sms = device_sm_count();
     if (world == 1) {
+        long long lo = 0, hi = all_chunks, lo2 = 0, hi2 = 0;
+        if (part == 1) { lo = FC1_LO; hi = FC1_HI; }
+        else if (part == 2) { hi = FC1_LO; lo2 = FC1_HI; hi2 = all_chunks; }
+        const long long n_chunks = (hi - lo) + (hi2 - lo2);
+        int grid = (int)((n_chunks + DP_THREADS - 1) / DP_THREADS);
         // block 0 waits for the arrival of all others, so the grid must be co-resident: cooperative launch,
         // at most what the occupancy calculator says fits (4 CTAs of 512 threads per SM at 32 registers)
         static std::atomic<int> per_sm_cached{0};      // a property of the kernel and the architecture (sm_100 only)
@@ -195,20 +215,29 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
             per_sm_cached.store(per_sm, std::memory_order_relaxed);
         }
         if (grid > sms * per_sm) grid = sms * per_sm;
+        // fc1.weight's launch runs UNDER conv2's backward (cdq_train_step): one CTA per SM is co-resident with that kernel's
+        // CTAs, a grid that needs four per SM would wait for it to drain (a cooperative launch starts only when it fits)
+        if (part == 1 && grid > sms) grid = sms;
         if (grid < 1) grid = 1;
         float* params = peers.params[0];
         float* grads = peers.grads[0];
         ProfileScope ps(KK_ADAM, st);
-        void* args[] = {&params, &grads, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
+        void* args[] = {&params, &grads, &m, &v, &lo, &hi, &lo2, &hi2, (void*)&phase, (void*)&bump, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
         cudaError_t e = cudaLaunchCooperativeKernel((const void*)adam_single_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
         count_launch();
         return (int)e;
     }
+    unsigned long long timeout_ns = (unsigned long long)(option(OPT_DP_TIMEOUT_S) > 0 ? option(OPT_DP_TIMEOUT_S) : 1) * 1000000000ull;
+    long long lo = 0, hi = all_chunks, lo2 = 0, hi2 = 0;
+    if (part == 1) { lo = FC1_LO; hi = FC1_HI; }
+    else if (part == 2) { hi = FC1_LO; lo2 = FC1_HI; hi2 = all_chunks; }
+    const long long slice = ((hi - lo) + (hi2 - lo2) + world - 1) / world;
+    int grid = (int)((slice + DP_THREADS - 1) / DP_THREADS);
     if (grid > sms) grid = sms;          // all CTAs must be co-resident: block 0 waits for the others
     if (grid < 1) grid = 1;
     ProfileScope ps(KK_ADAM, st);
-    unsigned long long timeout_ns = (unsigned long long)(option(OPT_DP_TIMEOUT_S) > 0 ? option(OPT_DP_TIMEOUT_S) : 1) * 1000000000ull;
-    void* args[] = {(void*)&peers, &rank, &world, &m, &v, (void*)&n_chunks, &d_step, &grid_bar, &lr, &b1, &b2, &eps, &timeout_ns};
+    void* args[] = {(void*)&peers, &rank, &world, &m, &v, &lo, &hi, &lo2, &hi2, (void*)&phase, (void*)&bump, &d_step, &grid_bar, &lr, &b1, &b2,
+                    &eps, &timeout_ns};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)dp_adam_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
     count_launch();
     return (int)e;
@@ -250,7 +279,7 @@ int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, f
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (major != 10) return CDQ_E_NODEVICE;
     return launch_dp_adam(*peers, rank, world, d_m, d_v, n_params_padded, d_step, d_grid_bar, lr, beta1, beta2, eps,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, 0);
 }
 
 

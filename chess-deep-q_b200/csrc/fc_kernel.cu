@@ -184,8 +184,9 @@ constexpr long long PK_N1 = 9 * 32 * 16, PK_N2 = 9 * 64 * 32, PK_V3 = 64ll * 256
 constexpr long long PK_SMALL = 2 * PK_N1 + 3 * PK_N2 + 577;
 constexpr long long PK_SMALL_PAD = (PK_SMALL + 255) / 256 * 256;     // the vector parts start on a CTA boundary
 __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __half* fc1p, __half* fc1tp, __half* w2tp,
-                                    __half* wss, float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b, float* zero_me) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                    __half* wss, float* conv2_b, float* fc1_b, float* fc2_w, float* fc2_b, float* zero_me,
+                                    long long first) {
+    const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;   // first: PK_SMALL_PAD when only fc1's tiles are packed
     if (i == 0 && zero_me) *zero_me = 0.f;       // the training step's loss accumulator (saves a fill launch in the graph)
     constexpr long long N1 = PK_N1, N2 = PK_N2;
     if (i >= PK_SMALL_PAD) {
@@ -259,12 +260,14 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
     }
 }
 
-int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me) {
-    const long long total = PK_SMALL_PAD + 2 * PK_V3;
+// part: 0 = everything; 1 = the two fc1 tile sets only (2 x 2 MB, almost all of the work); 2 = everything else (conv tiles, fp32 vectors)
+int launch_pack_weights(const CdqWeights& w, const PackedNet& p, cudaStream_t st, float* zero_me, int part) {
+    const long long first = part == 1 ? PK_SMALL_PAD : 0;
+    const long long total = (part == 2 ? PK_SMALL_PAD : PK_SMALL_PAD + 2 * PK_V3) - first;
     ProfileScope ps(KK_PACK, st);
     pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         w, (__half*)p.w1p, (__half*)p.w2p, (__half*)p.fc1p, (__half*)p.fc1tp, (__half*)p.w2tp, (__half*)p.wss, (float*)p.conv2_b,
-        (float*)p.fc1_b, (float*)p.fc2_w, (float*)p.fc2_b, zero_me);
+        (float*)p.fc1_b, (float*)p.fc2_w, (float*)p.fc2_b, zero_me, first);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -65,9 +65,30 @@ __device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// sums v[0..31] over the 32 lanes of a warp: afterwards lane l holds the total of element l (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float keep = up ? v[i + s] : v[i], send = up ? v[i] : v[i + s];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+// TRAIN: the online network's forward of the replay step.  The loss, tanh' and fc2's backward need nothing but q (known in
+// CTA 0 right after the forward), q' of the target network (complete before this launch) and ReLU(fc1), which every CTA still
+// holds in registers -- so the head of the backward pass (head_bwd_kernel: 9 us of the step's critical chain plus a 4 MB round
+// trip of ReLU(fc1)) is this kernel's epilogue: CTA 0 broadcasts d loss / d z2 per position through distributed shared memory,
+// every CTA writes its 64 columns of fc1's pre-activation gradient as the fp16 tiles fc1's backward kernels read and reduces
+// its slice of the fc2-weight and fc1-bias gradients.
+template <bool TRAIN>
 __global__ void __cluster_dims__(FS_SPLIT, 1, 1) __launch_bounds__(FC_THREADS, 1)
 fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedNet net, float* __restrict__ value,
-                     const unsigned* __restrict__ flags, float* __restrict__ leaf, float* __restrict__ hidden) {
+                     const unsigned* __restrict__ flags, float* __restrict__ leaf, float* __restrict__ hidden, const TrainHead th) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* sb1 = reinterpret_cast<float*>(smem + FS_OFF_VEC);
     float* sw2 = sb1 + 256;
@@ -147,6 +168,7 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
     }
     cluster_sync_all();                     // every CTA's partial sums are visible cluster-wide
 
+    float hk[TRAIN ? 64 : 1];               // TRAIN: ReLU(fc1) of this CTA's 64 columns stays in registers for the backward head
     if (warp >= 2) {
         // ---------------- phase 2: fc1 outputs 64 rank .. 64 rank + 63 of all 128 positions
         const int q = warp & 3, row = q * 32 + lane;
@@ -155,7 +177,7 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
 #pragma unroll
         for (int k = 0; k < FS_SPLIT; k++) pbase[k] = dsmem_addr(smem_u32(part), (uint32_t)k) + (uint32_t)row * 16u;
         float dot = 0.f;
-#pragma unroll 1
+#pragma unroll (TRAIN ? 8 : 1)
         for (int c0 = 0; c0 < 64; c0 += 8) {
             float p[FS_SPLIT][8];
 #pragma unroll
@@ -172,6 +194,7 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
                 const float z = ((p[0][j] + p[1][j]) + p[2][j]) + p[3][j];       // rank order, whoever adds
                 h[j] = fmaxf(z + sb1[c], 0.f);
                 dot = fmaf(h[j], sw2[c], dot);
+                if (TRAIN) hk[TRAIN ? c0 + j : 0] = h[j];
             }
             if (hidden && pos < n) {
                 float4* hp = reinterpret_cast<float4*>(hidden + pos * 256 + (int)rank * 64 + c0);
@@ -186,6 +209,7 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
     if (rank == 0 && warp >= 2) {
         const int q = warp & 3, row = q * 32 + lane;
         const long long pos = (tile << 7) + row;
+        float dz2 = 0.f, ls = 0.f;
         if (pos < n) {
             const float v = tanhf((((sdot[row] + sdot[128 + row]) + sdot[256 + row]) + sdot[384 + row]) + sb2[0]);
             if (value) value[pos] = v;
@@ -197,6 +221,64 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
                 else if (f & (CDQ_F_STALEMATE | CDQ_F_INSUFFICIENT | CDQ_F_REP3)) lv = 0.f;
                 leaf[pos] = lv;
             }
+            if (TRAIN) {
+                float dl;                                                          // d loss / d q
+                if (th.loss_kind == CDQ_LOSS_UPSTREAM) { dl = th.reward[pos]; ls = dl * v; }
+                else {
+                    const float y = th.reward[pos] + (1.f - th.done[pos]) * th.gamma * th.qn[pos];     // neural_network.py:238
+                    const float d = v - y;
+                    if (th.loss_kind == 0) { ls = d * d; dl = 2.f * d; }           // F.mse_loss (neural_network.py:241)
+                    else { const float ad = fabsf(d); ls = ad < 1.f ? 0.5f * d * d : ad - 0.5f; dl = fminf(1.f, fmaxf(-1.f, d)); }
+                }
+                dz2 = dl * th.inv_n * (1.f - v * v);                               // through tanh
+            }
+        }
+        if (TRAIN) {
+            // this thread has read its four partial dots: their slots carry d loss / d z2 to the four CTAs
+#pragma unroll
+            for (int k = 0; k < FS_SPLIT; k++) dsmem_st(dsmem_addr(smem_u32(sdot), (uint32_t)k) + (uint32_t)(row * 4), dz2);
+            float gb = dz2;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) { gb += __shfl_xor_sync(0xffffffffu, gb, d); ls += __shfl_xor_sync(0xffffffffu, ls, d); }
+            if (lane == 0) { atomicAdd(th.g_fc2_b, gb); atomicAdd(th.loss, ls * th.inv_n); }
+        }
+    }
+    if (TRAIN) {
+        cluster_sync_all();                 // d loss / d z2 of the tile's 128 positions is in every CTA's shared memory
+        float* red = reinterpret_cast<float*>(smem);          // [4 warps][128]: the partial-sum area is dead after the second barrier
+        if (warp >= 2) {
+            const int q = warp & 3, row = q * 32 + lane;
+            const float dz2 = sdot[row];    // 0 for rows beyond n
+            uint8_t* out = reinterpret_cast<uint8_t*>(th.dz1h) + (tile << 16) + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                float gw[32], gb1[32];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float dz[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int cl = half * 32 + g * 8 + i, c = (int)rank * 64 + cl;
+                        const float h = hk[TRAIN ? cl : 0];
+                        dz[i] = h > 0.f ? dz2 * sw2[c] : 0.f;                      // through fc2 and ReLU
+                        gw[g * 8 + i] = dz2 * h;
+                        gb1[g * 8 + i] = dz[i];
+                    }
+                    __half2 p0 = __floats2half2_rn(dz[0] * th.scale, dz[1] * th.scale), p1 = __floats2half2_rn(dz[2] * th.scale, dz[3] * th.scale);
+                    __half2 p2 = __floats2half2_rn(dz[4] * th.scale, dz[5] * th.scale), p3 = __floats2half2_rn(dz[6] * th.scale, dz[7] * th.scale);
+                    // dz1h tile: [32 column groups of 8][16 row groups][8 rows][8 halfs]
+                    *reinterpret_cast<uint4*>(out + ((int)rank * 8 + half * 4 + g) * 2048) =
+                        make_uint4(*reinterpret_cast<unsigned*>(&p0), *reinterpret_cast<unsigned*>(&p1), *reinterpret_cast<unsigned*>(&p2),
+                                   *reinterpret_cast<unsigned*>(&p3));
+                }
+                const float sw = warp_transpose_sum(gw, lane), sb = warp_transpose_sum(gb1, lane);   // lane l: column half * 32 + l
+                red[q * 128 + half * 32 + lane] = sw;
+                red[q * 128 + 64 + half * 32 + lane] = sb;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps
+            const int t = q * 32 + lane;                     // 0..63: fc2.weight gradient, 64..127: fc1.bias gradient
+            const float tot = (red[t] + red[128 + t]) + (red[256 + t] + red[384 + t]);
+            atomicAdd((t < 64 ? th.g_fc2_w : th.g_fc1_b) + (int)rank * 64 + (t & 63), tot);
         }
     }
     tc_fence_before();
@@ -207,11 +289,15 @@ fc_head_split_kernel(const __half* __restrict__ act2, long long n, const PackedN
 bool fc_split_enabled() { return option(OPT_FC_SPLIT) != 0; }     // cdq_set_option("fc_split", 0): A/B against the persistent kernel
 
 int launch_fc_head_split(const __half* act2, long long n, const PackedNet& net, float* value, const unsigned* flags,
-                         float* leaf, float* hidden, cudaStream_t st) {
-    once_per_device(ONCE_FC_SPLIT, [] { cudaFuncSetAttribute(fc_head_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM); });
+                         float* leaf, float* hidden, cudaStream_t st, const TrainHead* th) {
+    once_per_device(ONCE_FC_SPLIT, [] {
+        cudaFuncSetAttribute(fc_head_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
+        cudaFuncSetAttribute(fc_head_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
+    });
     const long long tiles = (n + 127) / 128;
     ProfileScope ps(KK_FC, st);
-    fc_head_split_kernel<<<(unsigned)(tiles * FS_SPLIT), FC_THREADS, FS_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden);
+    if (th) fc_head_split_kernel<true><<<(unsigned)(tiles * FS_SPLIT), FC_THREADS, FS_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden, *th);
+    else fc_head_split_kernel<false><<<(unsigned)(tiles * FS_SPLIT), FC_THREADS, FS_SMEM, st>>>(act2, n, net, value, flags, leaf, hidden, TrainHead{});
     count_launch();
     return (int)cudaGetLastError();
 }

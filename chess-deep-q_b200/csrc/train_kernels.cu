@@ -324,7 +324,7 @@ size_t train_workspace_bytes(long long n) { return n > 0 ? carve(nullptr, n).tot
 namespace {
 struct SideStream {
     cudaStream_t st = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, join2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, join2 = nullptr, dgrad_done = nullptr, target_done = nullptr;
     int init() {
         if (st) return 0;
         CDQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -332,6 +332,8 @@ struct SideStream {
         CDQ_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         CDQ_CUDA(cudaEventCreateWithFlags(&mid, cudaEventDisableTiming));
         CDQ_CUDA(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
+        CDQ_CUDA(cudaEventCreateWithFlags(&dgrad_done, cudaEventDisableTiming));
+        CDQ_CUDA(cudaEventCreateWithFlags(&target_done, cudaEventDisableTiming));
         return 0;
     }
 };
@@ -342,7 +344,7 @@ std::mutex g_side_mu[MAX_DEVICES];    // serialises the ENQUEUE of concurrent tr
 int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, const CdqBoard* states,
                   const CdqBoard* next_states, const float* reward, const float* done, long long n, double mean_over,
                   float gamma, int loss_kind_flags, const CdqWeights& g /* gradient outputs, pre-zeroed */, float* loss,
-                  void* ws_base, cudaStream_t st) {
+                  void* ws_base, cudaStream_t st, const CdqOptimizer* opt) {
     TrainWs ws = carve(ws_base, n);
     const int loss_kind = loss_kind_flags & 0xff;
     int e;
@@ -362,13 +364,29 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     // on the whole machine they would run one after the other, each with its own prologue and a half-empty
     // last round, so each gets half of the SMs and they run side by side.
     // The online launch also writes the ReLU(conv1) boards and sits on the longer chain (repack -> conv -> fc),
-    // so it gets the larger share (CDQ_TRAIN_CONV_SPLIT = percent of the SMs for the online network, default 50: measured flat between 50 and 61, profiles/conv_split_sweep.sh).
+    // so it gets the larger share (CDQ_TRAIN_CONV_SPLIT = percent of the SMs for the online network, default 50: measured flat between 50 and 61, profiles/conv_split_sweep.sh; with the backward head fused into the online fc kernel 36 / 42 / 50 % give 165.7 / 162.8 / 161.7 us, profiles/README.md round 2).
     static const int online_pct = [] { const char* e = getenv("CDQ_TRAIN_CONV_SPLIT"); const int v = e ? atoi(e) : 0; return v >= 20 && v <= 80 ? v : 50; }();
     const int online_sms = device_sm_count() * online_pct / 100, target_sms = device_sm_count() - online_sms;
     const bool upstream = loss_kind == CDQ_LOSS_UPSTREAM;     // no target network: d loss / d q comes from the caller
+    // cdq_train_step (opt != NULL): `net` is already packed from the current parameters (the previous step's tail did it), so the
+    // online forward starts at once; the loss accumulator is cleared on the side stream in front of the target forward
+    // Two schedules for the optimizer (option "train_split_optimizer"):
+    //   0  the parameters are repacked at the head of the step and ONE optimizer launch closes it;
+    //   1  fc1.weight's optimizer launch and repack follow its weight gradient on the side stream, the rest closes the step and
+    //      the next step starts with the convolution at once.  On one GPU the backward kernels already fill the machine from the
+    //      head to conv1's gradient, so 1 only moves work around (163 against 160 us, profiles/README.md); it is for peer groups,
+    //      where the optimizer kernel waits on NVLink round trips that the convolution backward can cover.
+    const bool split_opt = opt && option(OPT_TRAIN_SPLIT_OPT) != 0;
+    if (opt && !split_opt) loss_kind_flags |= CDQ_TRAIN_REPACK;
+    if (split_opt) {
+        loss_kind_flags &= ~CDQ_TRAIN_REPACK;
+        if (loss_kind_flags & CDQ_TRAIN_ZERO_LOSS) CDQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), side));
+        loss_kind_flags &= ~CDQ_TRAIN_ZERO_LOSS;
+    }
     if (!upstream) {
         if ((e = launch_conv_stack(next_states, n, target->p, ws.act2_target, nullptr, side, nullptr, target_sms))) return e;
         if ((e = launch_fc_head(ws.act2_target, n, target->p, ws.qn, nullptr, nullptr, nullptr, side))) return e;
+        CDQ_CUDA(cudaEventRecord(g_side.target_done, side));
     }
     // the online network's fp16 tiles are rebuilt from the fp32 parameters next to the target forward
     const bool zero_in_pack = (loss_kind_flags & CDQ_TRAIN_REPACK) && (loss_kind_flags & CDQ_TRAIN_ZERO_LOSS);
@@ -387,12 +405,21 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
         count_launch();
     }
     CDQ_CUDA(cudaEventRecord(g_side.join2, side));
-    if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
-    CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
-    // ---- loss, tanh, fc2, fc1 bias
     // lift into fp16's normal range; undone in the fp32 epilogues (upstream mode: the caller normalises max|dl| to 1)
     const float scale = upstream ? 64.f : 64.f * (float)mean_over;
-    {
+    // ---- loss, tanh, fc2, fc1 bias: for batches the cluster split-K fc kernel handles (<= 8 192 positions) this head of the
+    //      backward pass is that kernel's epilogue (it needs q' of the target network, so it starts after the target forward);
+    //      larger batches keep the persistent fc kernel + head_bwd_kernel
+    const bool fused_head = ((n + 127) >> 7) <= FC_SPLIT_MAX_TILES && fc_split_enabled();
+    if (fused_head) {
+        if (!upstream) CDQ_CUDA(cudaStreamWaitEvent(st, g_side.target_done, 0));
+        TrainHead th{ws.qn, reward, done, gamma, upstream ? 1.f : (float)(1.0 / mean_over), scale, loss_kind, ws.dz1h,
+                     (float*)g.fc2_w, (float*)g.fc2_b, (float*)g.fc1_b, loss};
+        if ((e = launch_fc_head_split(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, nullptr, st, &th))) return e;
+        CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
+    } else {
+        if ((e = launch_fc_head(ws.act2_tiles, n, net->p, ws.q, nullptr, nullptr, ws.hidden, st))) return e;
+        CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
         ProfileScope ps(KK_HEAD_BWD, st);
         const long long n_pad = ((n + 127) >> 7) << 7;
         const unsigned blocks = (unsigned)(n_pad / 8 < 1184 ? n_pad / 8 : 1184);
@@ -405,8 +432,18 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     CDQ_CUDA(cudaEventRecord(g_side.fork, st));
     CDQ_CUDA(cudaStreamWaitEvent(side, g_side.fork, 0));
     if ((e = launch_fc1_wgrad(ws.dz1h, ws.act2_tiles, n, 1.f / scale, (float*)g.fc1_w, side))) return e;
-    CDQ_CUDA(cudaEventRecord(g_side.join, side));
     if ((e = launch_fc1_dgrad(ws.dz1h, ws.relu_mask, net->p.fc1tp, n, ws.dz2_boards, st))) return e;
+    if (split_opt) {
+        // fc1.weight (98 % of the parameters): optimizer -- with its reduce-scatter / all-gather under a peer group -- and the
+        // repack of fc1's two tile sets follow the weight gradient on the side stream, under conv2's and conv1's backward.
+        // The repack overwrites the tiles fc1's data gradient reads, so it waits for that kernel.
+        CDQ_CUDA(cudaEventRecord(g_side.dgrad_done, st));
+        if ((e = launch_dp_adam(opt->peers, opt->rank, opt->world, opt->d_m, opt->d_v, opt->n_params_padded, opt->d_step, opt->d_grid_bar,
+                                opt->lr, opt->beta1, opt->beta2, opt->eps, side, 1))) return e;
+        CDQ_CUDA(cudaStreamWaitEvent(side, g_side.dgrad_done, 0));
+        if ((e = launch_pack_weights(w, net->p, side, nullptr, 1))) return e;
+    }
+    CDQ_CUDA(cudaEventRecord(g_side.join, side));
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join2, 0));
     if ((e = launch_conv2_bwd(ws.dz2_boards, ws.a1_boards, net->p.w2tp, n, 1.f / scale, (float*)g.conv2_w, (float*)g.conv2_b,
                               ws.dz1c, ws.sched, st))) return e;
@@ -419,7 +456,17 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
         conv1_wgrad_kernel<<<blocks, C1W_THREADS, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
         count_launch();
     }
+    if (split_opt) {
+        // the remaining 22 497 parameters (conv1, conv2, biases, fc2) and their tiles
+        if ((e = launch_dp_adam(opt->peers, opt->rank, opt->world, opt->d_m, opt->d_v, opt->n_params_padded, opt->d_step, opt->d_grid_bar,
+                                opt->lr, opt->beta1, opt->beta2, opt->eps, st, 2))) return e;
+        if ((e = launch_pack_weights(w, net->p, st, nullptr, 2))) return e;
+    }
     CDQ_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
+    if (opt && !split_opt) {
+        if ((e = launch_dp_adam(opt->peers, opt->rank, opt->world, opt->d_m, opt->d_v, opt->n_params_padded, opt->d_step, opt->d_grid_bar,
+                                opt->lr, opt->beta1, opt->beta2, opt->eps, st, 0))) return e;
+    }
     return (int)cudaGetLastError();
 }
 

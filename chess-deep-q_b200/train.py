@@ -145,7 +145,7 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
         self._d_step = torch.zeros(1, dtype=torch.int32, device=dev)       # device copy of step_count (step_fused)
-        self._grid_bar = torch.zeros(4, dtype=torch.int32, device=dev)   # arrivals, generation, time-out flag, reserved
+        self._grid_bar = torch.zeros(8, dtype=torch.int32, device=dev)   # per optimizer launch of a step: arrivals, generation, time-out flag, last complete generation
         self._flags = torch.zeros(64, dtype=torch.int32, device=dev)        # flag row of the world = 1 case
         self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": 0, "amsgrad": False,
                               "params": list(range(len(PARAM_ORDER)))}]
@@ -182,6 +182,13 @@ class FusedAdam:
         peers.params[0], peers.grads[0], peers.flags[0] = self.flat.data_ptr(), self.grad.data_ptr(), self._flags.data_ptr()
         return peers, 0, 1
 
+    def optimizer_struct(self):
+        """CdqOptimizer for cdq_train_step (the whole replay step as one call, optimizer launches inside the backward pass)."""
+        g = self.param_groups[0]
+        peers, rank, world = self._peers()
+        return _lib.CdqOptimizer(peers, rank, world, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), NPARAMS_PAD,
+                                 self._d_step.data_ptr(), self._grid_bar.data_ptr(), g["lr"], g["betas"][0], g["betas"][1], g["eps"])
+
     def step_fused(self):
         """cdq_dp_adam_step: gradient reduction over the peer group (if any), Adam with the step
         counter on the device, parameter broadcast and gradient zeroing in one kernel.  Safe to
@@ -194,6 +201,7 @@ class FusedAdam:
                                                self._grid_bar.data_ptr(), g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                                                _lib.stream_ptr()))
         self.network.invalidate_packed()
+        self.network._cdq_param_epoch = getattr(self.network, "_cdq_param_epoch", 0) + 1
 
     def step(self, grad_scale=1.0):
         g = self.param_groups[0]
@@ -205,6 +213,7 @@ class FusedAdam:
                                             self.exp_avg_sq.data_ptr(), NPARAMS, self.step_count, g["lr"],
                                             g["betas"][0], g["betas"][1], g["eps"], grad_scale, _lib.stream_ptr()))
         self.network.invalidate_packed()   # parameters changed behind autograd's back: repack before next forward
+        self.network._cdq_param_epoch = getattr(self.network, "_cdq_param_epoch", 0) + 1
 
     def _gathered_state(self):
         """exp_avg / exp_avg_sq of all parameters.  Under a peer group each rank only maintains its
@@ -337,6 +346,7 @@ class GraphedDQNStep:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)        # mean over THIS rank's shard
         self.ws = torch.zeros(_lib.lib().cdq_train_workspace_bytes(self.batch), dtype=torch.uint8, device=dev)
         self.graph = None
+        self._param_versions = None
         optimizer.zero_grad()
         target_network.net_handle()       # packed once here; update_target_network() repacks in place
 
@@ -345,12 +355,14 @@ class GraphedDQNStep:
         weights = _weights_struct([params[k] for k in PARAM_ORDER])
         gv = self.optimizer.grad_views()
         grads = _weights_struct([gv[k] for k in PARAM_ORDER])
-        _lib.check(_lib.lib().cdq_train_fwd_bwd(
+        opt = self.optimizer.optimizer_struct()
+        _lib.check(_lib.lib().cdq_train_step(
             self.q_network.raw_handle(), self.target_network.net_handle(), ctypes.byref(weights),
             self.states.data_ptr(), self.next_states.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
-            self.batch, self.mean_over, self.gamma, self.loss_kind | WS_PERSISTENT | REPACK | ZERO_LOSS, ctypes.byref(grads), self.loss.data_ptr(), self.ws.data_ptr(),
-            self.ws.numel(), _lib.stream_ptr()))
-        self.optimizer.step_fused()
+            self.batch, self.mean_over, self.gamma, self.loss_kind | WS_PERSISTENT | ZERO_LOSS, ctypes.byref(grads), self.loss.data_ptr(),
+            self.ws.data_ptr(), self.ws.numel(), ctypes.byref(opt), _lib.stream_ptr()))
+        self.optimizer.step_count += 1
+        self.q_network.invalidate_packed()
 
     INPUT_BYTES_PER_SAMPLE = 72 + 72 + 4 + 4     # state record, next-state record, reward, done
 
@@ -369,6 +381,13 @@ class GraphedDQNStep:
         """One step on the current contents of the static buffers; returns the local loss tensor."""
         if getattr(self.q_network, "_cdq_grads_dirty", False):
             self.optimizer.zero_grad()         # an eager backward / step() in between left gradients behind; the step accumulates
+        # cdq_train_step expects the online network's tiles to be packed from the current parameters and leaves them packed
+        # from the updated ones; parameters changed from outside since the last step (load_state_dict bumps the tensors'
+        # version counters, FusedAdam.step / step_fused bump the network's _cdq_param_epoch) are repacked here
+        versions = tuple(p._version for p in self.q_network.parameters()) + (getattr(self.q_network, "_cdq_param_epoch", 0),)
+        if versions != self._param_versions:
+            self.q_network.net_handle()
+            self._param_versions = versions
         if self.graph is None:
             self._body()                       # eager once: function attributes, lazy tables
             torch.cuda.synchronize()

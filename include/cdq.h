@@ -126,6 +126,7 @@ const char* cdq_error_string(int code);
  *   "fc_split"     [CDQ_FC_SPLIT, 1]      0: small batches use the persistent fc kernel instead of the cluster split-K one
  *   "host_ramp"    [CDQ_HOST_RAMP, 1]     0: cdq_leaf_eval_host starts with full chunks
  *   "dp_timeout_s" [CDQ_DP_TIMEOUT_S, 600] wall-clock limit of cdq_dp_adam_step's wait for its peers
+ *   "train_split_optimizer" [CDQ_TRAIN_SPLIT_OPT, 0] 1: cdq_train_step applies fc1.weight's optimizer launch under the convolution backward
  * Unknown names return CDQ_E_BADARG. */
 int cdq_set_option(const char* name, int value);
 int cdq_get_option(const char* name, int* value);
@@ -226,7 +227,8 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
  * parameters into every rank's parameter buffer and zeroes the consumed gradients on every rank.
  * *d_step (device int32, Adam's t) is incremented by the call; d_grid_bar = 4 zero-initialised
  * device uint32 that belong to this group and are never reset ([0] arrivals, [1] launch generation,
- * [2] sticky time-out flag, [3] reserved).  n_params_padded = parameter count
+ * [2] sticky time-out flag, [3] generation of the last complete arrival; cdq_train_step uses words 4..7 the same way for
+ * its second optimizer launch, so allocate 8).  n_params_padded = parameter count
  * rounded up to a multiple of 4 (padding elements stay zero).  world = 1 is the single-GPU fused
  * Adam step with a device-side step counter (CUDA-graph friendly).  All ranks must call it once
  * per step and reach it within option "dp_timeout_s" of wall clock (default 600 s) of each other: a rank
@@ -242,6 +244,30 @@ typedef struct CdqDpPeers {
 int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, float* d_v, int64_t n_params_padded,
                      int32_t* d_step, uint32_t* d_grid_bar, float lr, float beta1, float beta2, float eps, void* stream);
 int cdq_dp_adam_status(const uint32_t* d_grid_bar, void* stream);
+
+/* The whole replay step as ONE call: cdq_train_fwd_bwd + cdq_dp_adam_step + the repack of `net` for the next step, scheduled
+ * as one dependency graph so that the optimizer and repack of fc1.weight (98 % of the parameters) run under the convolution
+ * backward instead of after it: fc1's weight gradient -> [reduce-scatter +] Adam on fc1.weight [+ all-gather] -> fc1 tiles of
+ * `net` on the library's side stream, the remaining 22 497 parameters after conv1's gradient.  Requirements: d_weights and
+ * d_grads are the eight views, in the reference's parameter order, of the flat buffers opt->peers.params[rank] / .grads[rank]
+ * (fc1.weight at floats [21 984, 1 070 560)); `net` is packed from the current parameters on entry (cdq_net_load once; every
+ * call leaves it packed from the updated ones; CDQ_TRAIN_REPACK is implied and ignored).  d_grid_bar is 8 words here.
+ * That schedule is option "train_split_optimizer" = 1; with 0 (default) the call is cdq_train_fwd_bwd (repack at its head) followed
+ * by one cdq_dp_adam_step.  Either way `net` must not be used between the call and the completion of `stream`. */
+typedef struct CdqOptimizer {
+    CdqDpPeers peers;
+    int32_t rank, world;
+    float* d_m;
+    float* d_v;
+    int64_t n_params_padded;
+    int32_t* d_step;
+    uint32_t* d_grid_bar;
+    float lr, beta1, beta2, eps;
+} CdqOptimizer;
+int cdq_train_step(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights, const CdqBoard* d_states,
+                   const CdqBoard* d_next_states, const float* d_reward, const float* d_done, int64_t n, double mean_over,
+                   float gamma, int loss_kind, const CdqWeights* d_grads, float* d_loss, void* d_workspace,
+                   size_t workspace_bytes, const CdqOptimizer* opt, void* stream);
 /* CUDA IPC plumbing for the above: allocate a zeroed device region and export its 64-byte handle;
  * map a peer's handle; unmap; free. */
 int cdq_ipc_alloc(size_t bytes, void** d_ptr, void* handle64);
