@@ -70,7 +70,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         res = subprocess.run(cmd, capture_output=True, text=True, env=env)
         log += " ".join(cmd) + "\n" + res.stdout + res.stderr
         failed = res.returncode != 0
-    with open(os.path.join(HERE, "build.log"), "a" if not force and os.path.exists(os.path.join(HERE, "build.log")) else "w") as f:
+    with open(os.path.join(HERE, "build.log"), "w") as f:
         f.write(log)
     if failed:
         sys.stderr.write(log)

@@ -217,7 +217,7 @@ int cdq_expand_weighted(const CdqBoard* d_boards, int64_t n, int max_children, C
 int cdq_sample_children(const CdqBoard* d_children, const int32_t* d_counts, const uint8_t* d_weights, int64_t n,
                         int max_children, int width, const uint64_t* d_seeds, CdqBoard* d_selected, int32_t* d_sel_counts,
                         void* stream) {
-    if (n < 0 || max_children < 1 || max_children > 128 || width < 1 || width > max_children ||
+    if (n < 0 || max_children < 1 || max_children > 224 || width < 1 || width > max_children ||
         (n > 0 && (!d_children || !d_counts || !d_weights || !d_seeds || !d_selected || !d_sel_counts)))
         return CDQ_E_BADARG;
     if (int e = check_device()) return e;

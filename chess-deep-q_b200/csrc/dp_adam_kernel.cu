@@ -11,8 +11,8 @@
 //     scales by 1/W, updates ITS slice of exp_avg / exp_avg_sq (optimizer state is sharded,
 //     28 -> 28/W bytes of state traffic per parameter) and stores the new parameters into every
 //     rank's parameter buffer;
-//   * the gradient slice it has just consumed is zeroed on every rank, so the next step needs no
-//     zero_grad pass;
+//   * once every peer has signalled that it is done reading, each rank zeroes its own gradient buffer (locally), so the
+//     next step needs no zero_grad pass;
 //   * cross-GPU ordering uses two epoch flags per (rank, peer) written with system-scope release
 //     stores: "my gradients are complete" before the reduction, "my stores have landed" after it.
 // With W = 1 the same kernel is the plain fused Adam step with a device-side step counter, which
@@ -81,6 +81,10 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
     // ---- A: this rank's gradients are complete (stream order); tell every peer, wait for all of them
     if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + flag_off + rank, epoch - 1);
     const bool late = wait_peers(peers.flags[rank] + flag_off, world, epoch - 1, deadline, grid_bar_base + 2);
+#ifdef CDQ_DP_TRACE
+    unsigned long long* trace = reinterpret_cast<unsigned long long*>(grid_bar_base + 16);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { trace[0] = deadline - timeout_ns; trace[1] = globaltimer_ns(); }
+#endif
     const float bc1 = s_bc[0], bc2_sqrt = s_bc[1], inv_world = 1.f / (float)world;
 
     // ---- reduce-scatter + Adam + all-gather on this rank's slice (skipped when a peer's gradients never arrived)
@@ -108,15 +112,18 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
 #undef CDQ_ADAM1
         reinterpret_cast<float4*>(m)[c] = mi;
         reinterpret_cast<float4*>(v)[c] = vi;
-        for (int p = 0; p < world; p++) {
-            reinterpret_cast<float4*>(peers.params[p])[c] = pi;
-            reinterpret_cast<float4*>(peers.grads[p])[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int p = 0; p < world; p++) reinterpret_cast<float4*>(peers.params[p])[c] = pi;
     }
 
     // ---- B: all CTAs of this rank have stored; publish, then wait until every peer's stores have landed here
+#ifdef CDQ_DP_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace[2] = globaltimer_ns();
+#endif
     __threadfence_system();
     __syncthreads();
+#ifdef CDQ_DP_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace[3] = globaltimer_ns();
+#endif
     if (threadIdx.x == 0) {
         // arrival counter that wraps to 0 with the last CTA of THIS launch (launches of different sizes share it); the last
         // arriver publishes the generation, block 0 waits for it (co-resident cooperative grid: always arrives)
@@ -127,8 +134,22 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
         }
     }
     __syncthreads();
+#ifdef CDQ_DP_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace[4] = globaltimer_ns();
+#endif
     if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + flag_off + rank, epoch);
     wait_peers(peers.flags[rank] + flag_off, world, epoch, deadline, grid_bar_base + 2);
+#ifdef CDQ_DP_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace[5] = globaltimer_ns();
+#endif
+    // every peer has published epoch, i.e. finished its loop: nobody reads this rank's gradients any more.  They are zeroed
+    // HERE, locally (zeroing the consumed slice on every peer from the owner's loop doubled the NVLink store traffic that
+    // the system fence above has to drain: profiles/README.md, round 2)
+    if (!late) {
+        float4* mine = reinterpret_cast<float4*>(peers.grads[rank]);
+        for (long long ci = (long long)blockIdx.x * DP_THREADS + threadIdx.x; ci < n_chunks; ci += (long long)gridDim.x * DP_THREADS)
+            mine[ci < n1 ? chunk_lo + ci : chunk_lo2 + (ci - n1)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) { if (bump) *d_step = step; grid_bar[1] = gen; }
 }
 
@@ -136,7 +157,7 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
 // sized so that the whole parameter vector is in flight at once; the looped, 148-CTA peer version spends
 // 28 us on 30 MB), loads issued before the bias-correction constants are needed.  The step counter is still
 // bumped by block 0 after every CTA has read it, through the same never-reset arrival counter.
-__global__ void __launch_bounds__(DP_THREADS)
+__global__ void __launch_bounds__(DP_THREADS, 4)      // 4 x 512 threads per SM (32 registers): the whole vector in flight in one round
 adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v,
                    long long chunk_lo, long long chunk_hi, long long chunk_lo2, long long chunk_hi2, int phase, int bump,
                    int* __restrict__ d_step, unsigned* __restrict__ grid_bar_base, float lr, float b1, float b2, float eps) {

@@ -62,7 +62,7 @@ expand_kernel(const CdqBoard* __restrict__ boards, long long n, int max_children
 
 // select_weighted_moves (evaluation.py:342-366) on the device: `width` successive draws without
 // replacement, each with probability proportional to the tactical weight of the remaining moves.
-// One warp per node; lane l holds the weights of children l, l+32, l+64, l+96.  Integer arithmetic
+// One warp per node; lane l holds the weights of children l, l+32, ... l+192.  Integer arithmetic
 // only -- draw k uses z = mix64(seed + (k+1) * 0x9E3779B97F4A7C15), r = (z * W) >> 64 with W the sum
 // of the remaining weights, and takes the first child (in index order) whose running weight sum
 // exceeds r -- so a host restatement reproduces the selection exactly (tests/test_gpu_mcts.py).
@@ -74,7 +74,8 @@ sample_children_kernel(const CdqBoard* __restrict__ children, const int* __restr
     const int lane = threadIdx.x & 31;
     const long long node = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (node >= n) return;
-    const int c = min(counts[node], min(max_children, 128));
+    constexpr int NB = 7;                           // 224 >= the 218 legal moves a chess position can have
+    const int c = min(counts[node], min(max_children, 32 * NB));
     const u64* src = reinterpret_cast<const u64*>(children + node * max_children);
     u64* dst = reinterpret_cast<u64*>(selected + node * width);
     const int keep = min(c, width);
@@ -83,25 +84,28 @@ sample_children_kernel(const CdqBoard* __restrict__ children, const int* __restr
         for (int w = lane; w < c * 9; w += 32) dst[w] = src[w];
         return;
     }
-    unsigned wt[4];
+    unsigned wt[NB];
     unsigned total = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < NB; j++) {
         const int idx = lane + 32 * j;
         wt[j] = idx < c ? weights[node * max_children + idx] : 0u;
     }
     const u64 seed = seeds[node];
     for (int k = 0; k < width; k++) {
         // remaining weight per 32-child block j (children are ordered j-major: idx = lane + 32 j)
-        unsigned blk[4];
+        unsigned blk[NB];
         total = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) { blk[j] = __reduce_add_sync(0xffffffffu, wt[j]); total += blk[j]; }
+        for (int j = 0; j < NB; j++) { blk[j] = __reduce_add_sync(0xffffffffu, wt[j]); total += blk[j]; }
         const u64 z = mix64(seed + (u64)(k + 1) * 0x9E3779B97F4A7C15ull);
         unsigned r = (unsigned)__umul64hi(z, (u64)total);
         int j = 0;                                  // block that contains the r-th unit of weight
-        while (j < 3 && r >= blk[j]) { r -= blk[j]; j++; }
-        const unsigned mine = j == 0 ? wt[0] : j == 1 ? wt[1] : j == 2 ? wt[2] : wt[3];
+#pragma unroll
+        for (int jj = 0; jj < NB - 1; jj++) if (j == jj && r >= blk[jj]) { r -= blk[jj]; j++; }
+        unsigned mine = 0;
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++) if (jj == j) mine = wt[jj];
         unsigned incl = mine;                       // inclusive prefix sum over lanes
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -110,7 +114,8 @@ sample_children_kernel(const CdqBoard* __restrict__ children, const int* __restr
         }
         const unsigned hit = __ballot_sync(0xffffffffu, incl > r);
         const int pick_lane = __ffs(hit) - 1, pick = pick_lane + 32 * j;
-        if (lane == pick_lane) { if (j == 0) wt[0] = 0; else if (j == 1) wt[1] = 0; else if (j == 2) wt[2] = 0; else wt[3] = 0; }
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++) if (jj == j && lane == pick_lane) wt[jj] = 0;
         if (lane < 9) dst[k * 9 + lane] = src[pick * 9 + lane];
     }
 }

@@ -145,7 +145,7 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
         self._d_step = torch.zeros(1, dtype=torch.int32, device=dev)       # device copy of step_count (step_fused)
-        self._grid_bar = torch.zeros(8, dtype=torch.int32, device=dev)   # per optimizer launch of a step: arrivals, generation, time-out flag, last complete generation
+        self._grid_bar = torch.zeros(32, dtype=torch.int32, device=dev)   # per optimizer launch of a step: arrivals, generation, time-out flag, last complete generation
         self._flags = torch.zeros(64, dtype=torch.int32, device=dev)        # flag row of the world = 1 case
         self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": 0, "amsgrad": False,
                               "params": list(range(len(PARAM_ORDER)))}]

@@ -224,7 +224,7 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
  * passes the mapped pointers in rank order.  Rank r sums ITS slice of all gradient buffers (rank
  * order, so all replicas get identical bits), scales by 1/world, updates its slice of d_m / d_v
  * (optimizer state is sharded: only the owned slice of those arrays is meaningful), writes the new
- * parameters into every rank's parameter buffer and zeroes the consumed gradients on every rank.
+ * parameters into every rank's parameter buffer; after the closing handshake every rank zeroes its own gradient buffer.
  * *d_step (device int32, Adam's t) is incremented by the call; d_grid_bar = 4 zero-initialised
  * device uint32 that belong to this group and are never reset ([0] arrivals, [1] launch generation,
  * [2] sticky time-out flag, [3] generation of the last complete arrival; cdq_train_step uses words 4..7 the same way for
@@ -296,7 +296,8 @@ int cdq_expand_weighted(const CdqBoard* d_boards, int64_t n, int max_children, C
  * z = mix64(d_seeds[i] + (k+1) * 0x9E3779B97F4A7C15) (splitmix64 finalizer), r = (z * W) >> 64 with
  * W = sum of the remaining weights, and takes the first remaining child in index order whose
  * running weight sum exceeds r: integer arithmetic only, reproducible on the host.
- * d_selected is [n][width] records, d_sel_counts[i] = min(count_i, width).  max_children <= 128. */
+ * d_selected is [n][width] records, d_sel_counts[i] = min(count_i, width).  max_children <= 224 (a chess position has at most
+ * 218 legal moves). */
 int cdq_sample_children(const CdqBoard* d_children, const int32_t* d_counts, const uint8_t* d_weights, int64_t n,
                         int max_children, int width, const uint64_t* d_seeds, CdqBoard* d_selected,
                         int32_t* d_sel_counts, void* stream);

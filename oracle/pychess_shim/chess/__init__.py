@@ -1,14 +1,24 @@
-"""Minimal pure-Python stand-in for the `chess` package (python-chess) -- TEST INFRASTRUCTURE.
+"""Minimal pure-Python stand-in for the `chess` package (python-chess) -- TEST INFRASTRUCTURE, never shipped.
 
-python-chess is the un-vendored, unpinned dependency (`chess>=1.9.0`, requirements.txt:4) that
-holds all bitboard arithmetic of the reference's evaluation path and it is not installable in
-this image (no network).  This shim restates, from its published behaviour, just
-the API surface that the reference's board_utils.py / evaluation.py / mcts.py touch, so that the
-reference's OWN unmodified evaluation.py can be imported and run here to generate golden vectors
-(tests/golden/make_golden.py).  It is written independently of oracle/cdq_oracle.c (Python,
-table-free ray walks) so the two restatements cross-check each other; perft pins both.
+What it is.  python-chess is the un-vendored, unpinned dependency (`chess>=1.9.0`, requirements.txt:4) that
+holds all bitboard arithmetic of the reference's evaluation path; it is not installable in this image (no
+network).  This module is a FAITHFUL RESTATEMENT of the part of its API that the reference's board_utils.py /
+evaluation.py / mcts.py touch: it follows the library's published algorithm step by step -- `_attackers_mask`,
+slider blockers and `pin_mask`, `_generate_evasions`, `_is_safe`, `_ep_skewered`, `generate_castling_moves`
+through `clean_castling_rights`, `is_insufficient_material`, `_transposition_key` -- and keeps its method names
+where the reference calls them, because the quirks that leak into the reference's scores (captures of the enemy
+king when the turn is forced, the raw ep square, promotions counted four times) ARE that algorithm.  It is
+therefore not an independent derivation and not a clean-room work: python-chess is GPL-3.0, and this file stays
+in oracle/ as a checker -- the product (chess-deep-q_b200/) neither imports nor links it
+(tests/test_host_abi.py::test_product_never_imports_the_oracle).
 
-If the real library is ever importable it must be preferred: make_golden.py tries it first.
+What it pins.  The reference's OWN unmodified evaluation.py is imported over this module to record the golden
+vectors (tests/golden/make_golden.py).  So "bit-exact against the reference" means: against the reference's code
+running on this restatement of its dependency, with both this module and oracle/cdq_oracle.c pinned to the six
+public perft suites.  The C oracle shares the algorithm (per-move generation + `_is_safe`), not the code; the
+CUDA kernels use a different, set-wise method.  If the real library is ever importable it is preferred:
+make_golden.py tries it first, and tests/test_oracle.py::test_goldens_against_real_python_chess re-derives a
+sample of the golden vectors with it.
 """
 WHITE, BLACK = True, False
 COLORS = [WHITE, BLACK]

@@ -149,3 +149,28 @@ def test_python_path_restatement_reproduces_the_reference_scores(oracle, eval_go
         assert np.array_equal(py_eval.board_to_planes(py_eval.unpack_board(g["boards"][i])), planes[i])
     v, sec, scores = py_eval.python_path_throughput(g["boards"][100:132], processes=2)
     assert np.array_equal(scores, g["score"][100:132]) and v > 0
+
+
+def test_goldens_against_real_python_chess(oracle, eval_golden):
+    """Optional: where the REAL python-chess is installed (it is not in this image) and the reference checkout is
+    reachable, a sample of the golden vectors is re-derived with the real library under the reference's unmodified
+    evaluation.py -- the pin the shim-based goldens cannot give."""
+    import importlib.util
+    import os
+    import sys
+    spec = importlib.util.find_spec("chess")
+    if spec is None or "pychess_shim" in (spec.origin or "") or not os.path.exists("/root/reference/evaluation.py"):
+        pytest.skip("real python-chess (or the reference checkout) is not available")
+    import chess
+    if not hasattr(chess, "__version__"):
+        pytest.skip("`chess` on the path is the restated shim")
+    sys.path.insert(0, "/root/reference")
+    import evaluation as ref_eval
+    import py_eval
+    g = eval_golden
+    for i in range(0, len(g["boards"]), 7):
+        if g["boards"][i]["meta"] & (1 << 16):
+            continue
+        b = py_eval.unpack_board(g["boards"][i])
+        ref_eval.EVAL_CACHE.clear()
+        assert ref_eval.fast_evaluate_position(b) == g["score"][i], i
