@@ -603,7 +603,7 @@ def main():
     avg_ms = kms[dom] / max(1, kcnt[dom])
     achieved = per_launch_pos * kinds[dom][1] / (avg_ms * 1e-3) / 1e12
     traffic = None        # DRAM bytes per launch of that kernel from the committed ncu capture, scaled to this launch size
-    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         ent = tj.get(kinds[dom][0])
@@ -611,7 +611,7 @@ def main():
             traffic = ent["traffic_bytes"] * per_launch_pos / ent.get("captured_positions", tj["captured_positions"])
     roofline = {"kernel": kinds[dom][0], "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                "traffic_note": "DRAM read+write bytes per launch: ncu capture of a 151 552-position launch (profiles/r1c_traffic.json) scaled to "
+                "traffic_note": "DRAM read+write bytes per launch: ncu capture of a 151 552-position launch (profiles/r2_traffic.json) scaled to "
                                 "this run's average launch of %d positions; algorithmic %.3f GB" % (per_launch_pos, per_launch_pos * 8264 / 1e9),
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kind::f16 shares the bf16 rate)",
                 "kernel_ms_per_step": {kinds[k][0]: kms[k] / args.steps for k in kinds if kms[k] > 0},
