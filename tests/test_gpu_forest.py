@@ -138,3 +138,24 @@ def test_self_play_on_the_device_is_legal_reproducible_and_trains(cdq, oracle):
     assert n_losses == stored - 15 and all(np.isfinite(x) for g in out for x in g["losses"])
     mv = agent.select_move(cdq.mcts._startpos(), training_progress=0.0, current_move=0)
     assert mv is not None and len(mv.uci()) in (4, 5)
+
+
+def test_optimized_chess_ai_trains_through_self_play(cdq, oracle, tmp_path):
+    """chess_ai.OptimizedChessAI: games of self-play in lockstep on the device forest with the reference's annealing
+    (neural_network.py:150-163), transitions stored, one training step per ply once the memory holds a batch, the
+    target network synchronised every five games (chess_ai.py:117-250, 346-413), then a checkpoint."""
+    from chess_deep_q_b200.chess_ai import OptimizedChessAI
+    torch.manual_seed(1)
+    ai = OptimizedChessAI(training_games=6)
+    ai.dqn_agent.batch_size = 8
+    ai.train(parallel_games=3, max_moves=7)
+    assert len(ai.game_history) == 6 and all(g["move_count"] == len(g["moves"]) <= 7 for g in ai.game_history)
+    assert all(len(m) in (4, 5) for g in ai.game_history for m in g["moves"])
+    plies = sum(g["move_count"] for g in ai.game_history)
+    assert len(ai.dqn_agent.memory) == plies and len(ai.loss_history) == plies - 7
+    assert all(np.isfinite(x) for x in ai.loss_history) and len(ai.evaluation_history) == 6
+    assert ai.game_history[0]["result"] in ("*", "1-0", "0-1", "1/2-1/2")
+    # the target network was synchronised after the fifth game (and not after the sixth)
+    ai.save_model(str(tmp_path / "m.pth"))
+    ck = torch.load(str(tmp_path / "m.pth"), map_location="cpu", weights_only=False)
+    assert ck["total_games_trained"] == 6 and ck["training_games"] == 6 and len(ck["move_count_history"]) == 6
