@@ -1,7 +1,7 @@
 // tree_kernel.cu -- SURVEY.md 8(f1): the caller of the leaf evaluator, ParallelRussianDollMCTS (mcts.py:14-194), with
 // its trees RESIDENT IN HBM for thousands of concurrent searches (one per self-play game) and every phase a kernel:
 //
-//   tree_level_kernel   one tree level of one wave for all trees: node lookup / expansion (_expand_node, mcts.py:166-194:
+//   tree_level_kernel   the descent of one wave for all trees, level by level inside ONE launch: node lookup / expansion (_expand_node, mcts.py:166-194:
 //                       legal moves, categorize_moves weights, select_weighted_moves sampling), action selection
 //                       (_select_action, mcts.py:34-67: unexplored children first, else the annealed UCB argmax), Board.push,
 //                       halfmove clock and repetition bookkeeping (is_game_over / is_repetition, mcts.py:151,209)
@@ -9,8 +9,8 @@
 //   tree_backup_kernel  running-mean backup with the sign flip per ply (mcts.py:158-164)
 //   tree_best_kernel    most visited root child (mcts.py:100-116); game_advance_kernel plays it in the game
 //
-// The launch sequence of a search is static (waves x (depth levels + leaf evaluation + backup)), so the host enqueues it
-// without reading anything back: one synchronisation per SEARCH, not per level or per simulation.
+// The launch sequence of a search is static (waves x (descent + leaf evaluation + backup)), so the host enqueues it -- or
+// replays it as a CUDA graph -- without reading anything back: one synchronisation per SEARCH, not per level or simulation.
 //
 // Layout.  A block = one tree, a warp = one simulation of the current wave (the reference's worker thread), lanes = the
 // node's children (width <= 32) or the node's legal moves during expansion (lane l owns moves l, l+32, ... of <= 224).
@@ -237,7 +237,7 @@ __device__ __forceinline__ Pushed push_move(const Pos& p, unsigned code, int hmc
 
 template <int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, MAXW <= 8 ? 2 : 1)
-tree_level_kernel(const Forest f, int level, int wave, int wave_size, double ew, double alpha, int max_moves) {
+tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alpha, int max_moves) {
     __shared__ u64 sh_key[MAXW];
     __shared__ int sh_need[MAXW], sh_node[MAXW], sh_new[MAXW];
     const int t = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,26 +249,17 @@ tree_level_kernel(const Forest f, int level, int wave, int wave_size, double ew,
     const int root_ply = f.g_ply[t];
     const u64 search_seed = mix64(f.g_seed[t] + (u64)(unsigned)root_ply * GOLD);
 
-    // ---- phase 0: the simulation's state (level 0: a fresh copy of the game position, mcts.py:83,121)
-    bool alive;
-    Pos p;
-    int hmc, depth, valid_from;
-    bool ep_legal;
-    if (level == 0) {
-        alive = f.g_active[t] != 0 && w < wave_size;
-        p = load_pos(reinterpret_cast<const u64*>(f.g_rec + t));
-        hmc = f.g_hmc[t]; depth = 0; valid_from = 0; ep_legal = f.g_ep_legal[t] != 0;
-        if (lane == 0) {
-            store_pos(p, reinterpret_cast<u64*>(f.s_rec + s));
-            path_keys[0] = f.g_key[t];
-            f.s_depth[s] = 0; f.s_hmc[s] = hmc; f.s_valid_from[s] = 0; f.s_ep_legal[s] = ep_legal; f.s_alive[s] = alive;
-        }
-        __syncwarp();
-    } else {
-        alive = f.s_alive[s] != 0;
-        p = load_pos(reinterpret_cast<const u64*>(f.s_rec + s));
-        hmc = f.s_hmc[s]; depth = f.s_depth[s]; valid_from = f.s_valid_from[s]; ep_legal = f.s_ep_legal[s] != 0;
-    }
+    // ---- the simulation's state: a fresh copy of the game position (mcts.py:83,121), kept in registers over the levels.
+    //      A tree is one CTA and nothing crosses trees, so all levels of a wave run in ONE launch (the first version launched
+    //      one kernel per level and carried this state through global memory).
+    bool alive = f.g_active[t] != 0 && w < wave_size;
+    Pos p = load_pos(reinterpret_cast<const u64*>(f.g_rec + t));
+    int hmc = f.g_hmc[t], depth = 0, valid_from = 0;
+    bool ep_legal = f.g_ep_legal[t] != 0;
+    if (lane == 0) path_keys[0] = f.g_key[t];
+    __syncwarp();
+
+  for (int level = 0; level < D; level++) {
 
     // ---- phase 1: find the node of the current position, expanding it if this tree has not seen it (mcts.py:128-133)
     u64 key = 0;
@@ -388,16 +379,21 @@ tree_level_kernel(const Forest f, int level, int wave, int wave_size, double ew,
     // ---- phase 3: Board.push, halfmove clock, repetition (all simulations in parallel)
     if (move != NO_MOVE) {
         const Pushed o = push_move<true>(p, move, hmc, ep_legal, hist, hist_len, path_keys, valid_from, hist_len + depth + 1, lane);
-        if (lane == 0) {
-            store_pos(o.c, reinterpret_cast<u64*>(f.s_rec + s));
-            path_keys[depth + 1] = o.key;
-            f.s_depth[s] = depth + 1; f.s_hmc[s] = o.hmc; f.s_valid_from[s] = o.valid_from; f.s_ep_legal[s] = o.ep_legal;
-            // fivefold repetition ends the game (is_game_over, mcts.py:151); the 75-move rule and no-legal-move positions
-            // end the descent at the next level's expansion, which is the same leaf
-            f.s_alive[s] = (o.reps < 5 && depth + 1 < D) ? 1 : 0;
-        }
-    } else if (lane == 0) {
-        f.s_alive[s] = 0;                   // finished game, depth limit, or a slot beyond the (partial) wave
+        if (lane == 0) path_keys[depth + 1] = o.key;
+        __syncwarp();
+        p = o.c; hmc = o.hmc; valid_from = o.valid_from; ep_legal = o.ep_legal; depth += 1;
+        // fivefold repetition ends the game (is_game_over, mcts.py:151); the 75-move rule and no-legal-move positions
+        // end the descent at the next level's expansion, which is the same leaf
+        alive = o.reps < 5 && depth < D;
+    } else {
+        alive = false;                      // finished game, depth limit, or a slot beyond the (partial) wave
+    }
+    __syncthreads();                        // sh_* are reused by the next level
+  }
+    // the leaf: this array IS the batch cdq_leaf_eval evaluates next
+    if (lane == 0) {
+        store_pos(p, reinterpret_cast<u64*>(f.s_rec + s));
+        f.s_depth[s] = depth;
     }
 }
 
@@ -490,8 +486,8 @@ __global__ void __launch_bounds__(128) game_advance_kernel(const Forest f) {
 using namespace cdq;
 
 template <int MAXW>
-static void launch_level(const tree::Forest& f, int level, int wave, int wave_size, double ew, double alpha, int max_moves, cudaStream_t st) {
-    tree::tree_level_kernel<MAXW><<<f.T, f.workers * 32, 0, st>>>(f, level, wave, wave_size, ew, alpha, max_moves);
+static void launch_descent(const tree::Forest& f, int wave, int wave_size, double ew, double alpha, int max_moves, cudaStream_t st) {
+    tree::tree_level_kernel<MAXW><<<f.T, f.workers * 32, 0, st>>>(f, wave, wave_size, ew, alpha, max_moves);
 }
 
 struct CdqForest {
@@ -600,11 +596,11 @@ int cdq_forest_search(CdqForest* F, const CdqNet* net, int iterations, float exp
     const long long S = (long long)f.T * f.workers;
     for (int first = 0, wave = 0; first < iterations; first += f.workers, wave++) {
         const int wave_size = iterations - first < f.workers ? iterations - first : f.workers;
-        for (int level = 0; level < f.depth; level++) {
+        {   // the wave's descent, all levels (selection, expansion, push) in one launch
             ProfileScope ps(KK_PLAYOUT, st);
-            if (f.workers <= 8) launch_level<8>(f, level, wave, wave_size, ew, alpha, max_moves, st);
-            else if (f.workers <= 16) launch_level<16>(f, level, wave, wave_size, ew, alpha, max_moves, st);
-            else launch_level<32>(f, level, wave, wave_size, ew, alpha, max_moves, st);
+            if (f.workers <= 8) launch_descent<8>(f, wave, wave_size, ew, alpha, max_moves, st);
+            else if (f.workers <= 16) launch_descent<16>(f, wave, wave_size, ew, alpha, max_moves, st);
+            else launch_descent<32>(f, wave, wave_size, ew, alpha, max_moves, st);
             count_launch();
         }
         // the wave's leaves of all trees: ONE batched leaf evaluation (K1 + K2; without a network K1's heuristic leaf)

@@ -158,6 +158,7 @@ class DeviceForest:
         h = ctypes.c_void_p()
         _lib.check(_lib.lib().cdq_forest_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
+        self._graphs = {}
         v = _lib.CdqForestView()
         _lib.check(_lib.lib().cdq_forest_view(h, ctypes.byref(v)))
         self._view = v
@@ -190,6 +191,7 @@ class DeviceForest:
     def close(self):
         if self._h is not None:
             torch.cuda.synchronize()
+            self._graphs.clear()
             _lib.lib().cdq_forest_destroy(self._h)
             self._h = None
 
@@ -237,6 +239,31 @@ class DeviceForest:
 
     def advance(self):
         _lib.check(_lib.lib().cdq_forest_advance(self._h, _lib.stream_ptr()))
+
+    def search_and_advance(self, neural_net=None, iterations=None, exploration_weight=1.0, training_progress=0.0, max_moves=200):
+        """search() + advance() as ONE CUDA graph replay.  A search is a static sequence of launches (waves x (levels +
+        leaf evaluation + backup)) whose arguments do not depend on the positions, so it is captured once per
+        (network, iterations, exploration weight, progress, max_moves) and replayed every ply: for a handful of games
+        the ~80 launches of a search cost more host time than device time.  The network's tiles are referenced by
+        address, so weight updates (repacked in place by net_handle()) are picked up by the replay."""
+        it = self.max_iterations if iterations is None else int(iterations)
+        key = (id(neural_net), it, float(exploration_weight), float(training_progress), int(max_moves))
+        if neural_net is not None:
+            neural_net.net_handle()                  # repack (eagerly, in place) if the parameters changed
+        g = self._graphs.get(key)
+        if g is None:
+            self.search(neural_net, it, exploration_weight, training_progress, max_moves)     # eager once: lazy attributes
+            self.advance()
+            torch.cuda.synchronize()
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.search(neural_net, it, exploration_weight, training_progress, max_moves)
+                self.advance()
+            self._graphs[key] = g
+            return
+        g.replay()
 
 
 _forest_cache = {}
@@ -363,8 +390,7 @@ def self_play_games(neural_net, n_games, max_moves=200, iterations=50, samples_p
         if not active.any():
             break
         forest.set_active(active.astype(np.int32))
-        forest.search(neural_net, iterations, exploration_weight, training_progress, max_moves)
-        forest.advance()
+        forest.search_and_advance(neural_net, iterations, exploration_weight, training_progress, max_moves)
         score, flags = evaluate_batch(forest.game_boards)                    # same stream: after the moves were played
         rec = forest.game_boards.cpu().numpy().view(np.uint64).reshape(-1).view(BOARD_DTYPE)     # the ply's one synchronisation
         status = forest.game_status.cpu().numpy()

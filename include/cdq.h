@@ -307,9 +307,9 @@ int cdq_sample_children(const CdqBoard* d_children, const int32_t* d_counts, con
  * mcts.py:69-194, for any number of concurrent games) --------------------------------------------------
  * A CdqForest holds, in device memory, `n_games` games (position, halfmove clock, ply, transposition keys since the last
  * irreversible move) and one search tree per game.  cdq_forest_search runs `iterations` simulations per tree in waves of
- * `workers` (the reference's thread count, mcts.py:20,77): per level one kernel (node expansion with categorize_moves /
+ * `workers` (the reference's thread count, mcts.py:20,77): per wave one descent kernel (per level: node expansion with categorize_moves /
  * select_weighted_moves, evaluation.py:232-366; UCB selection with the annealed exploration weight, mcts.py:34-67;
- * Board.push; is_game_over / is_repetition bookkeeping, mcts.py:151,209), per wave ONE cdq_leaf_eval over the leaves of
+ * Board.push; is_game_over / is_repetition bookkeeping, mcts.py:151,209), ONE cdq_leaf_eval over the leaves of
  * all trees (net == NULL: the heuristic branch) and one backup kernel (mcts.py:158-164).  Nothing is read back: the host
  * synchronises once per search.  Depth limit = len(samples_per_level), children per node = samples_per_level[0]
  * (mcts.py:127,188).  cdq_forest_advance plays every tree's most visited root move in its game (chess_ai.py:151).
