@@ -216,6 +216,7 @@ class ReplayMemory:
         self.dones = np.zeros(self.maxlen, np.float32)
         self.moves = [None] * self.maxlen
         self._start, self._len = 0, 0
+        self.appended = 0          # total number of append() calls: lets a device mirror upload only what is new
 
     def __len__(self):
         return self._len
@@ -229,6 +230,7 @@ class ReplayMemory:
             self._len += 1
         self.states[slot], self.next_states[slot] = s, ns
         self.rewards[slot], self.dones[slot], self.moves[slot] = reward, done, move
+        self.appended += 1
         return slot
 
     def _slot(self, i):
@@ -280,8 +282,7 @@ class DQNAgent:
         import multiprocessing
         self.num_cpu_cores = max(1, multiprocessing.cpu_count() - 1)     # neural_network.py:69 (simulations per wave)
         self._graph_step = None
-        self._stage = None
-        self._np_rng = None
+        self._dmem = None
 
     def update_target_network(self):
         """neural_network.py:183-185"""
@@ -369,50 +370,75 @@ class DQNAgent:
         ns = as_records(next_state)[0] if next_state is not None and next_state is not False else np.zeros(1, BOARD_DTYPE)[0]
         self.memory.append((s, move, float(reward), ns, float(done)))
 
-    def _staging(self):
-        """One pinned buffer laid out like GraphedDQNStep.inputs, with numpy views for the gather."""
-        if self._stage is None or self._stage["batch"] != self.batch_size:
-            B = self.batch_size
-            flat = torch.empty(B * 152, dtype=torch.uint8).pin_memory()
-            raw = flat.numpy()
-            self._stage = {"batch": B, "flat": flat,
-                           "states": raw[:B * 72].view(np.uint64).reshape(B, 9),
-                           "next_states": raw[B * 72:B * 144].view(np.uint64).reshape(B, 9),
-                           "rewards": raw[B * 144:B * 148].view(np.float32),
-                           "dones": raw[B * 148:B * 152].view(np.float32),
-                           "loss": torch.empty(1, dtype=torch.float32).pin_memory()}
-        return self._stage
+    def _device_memory(self):
+        """Device mirror of the replay memory ([maxlen] records x 2, rewards, dones: 1.5 MB), brought up to date with ONE
+        host-to-device copy of the transitions appended since the last call (in self-play: one per training step,
+        chess_ai.py:187-192) through a pinned staging buffer.  The minibatch is then drawn and gathered on the device."""
+        mem = self.memory
+        if self._dmem is None or self._dmem["maxlen"] != mem.maxlen or self._dmem["memory"] is not mem:
+            dev, n = self.device, mem.maxlen
+            flat = torch.zeros(n * 152, dtype=torch.uint8, device=dev)
+            self._dmem = {"maxlen": n, "memory": mem, "synced": 0, "flat": flat,
+                          "states": flat[:n * 72].view(torch.int64).view(n, 9),
+                          "next_states": flat[n * 72:n * 144].view(torch.int64).view(n, 9),
+                          "rewards": flat[n * 144:n * 148].view(torch.float32),
+                          "dones": flat[n * 148:n * 152].view(torch.float32),
+                          "stage": torch.empty(n * 152, dtype=torch.uint8).pin_memory(),
+                          "loss": torch.empty(1, dtype=torch.float32).pin_memory()}
+        d = self._dmem
+        new = min(mem.appended - d["synced"], mem._len)
+        if new > 0:
+            n = mem.maxlen
+            first = (mem._start + mem._len - new) % n               # slots [first, first + new) modulo maxlen
+            stage, off = d["stage"].numpy(), 0
+            head = min(new, n - first)
+            for lo, cnt in ((first, head), (0, new - head)):
+                if cnt <= 0:
+                    continue
+                # one staging block per segment: [cnt records | cnt records | cnt rewards | cnt dones], one H2D copy, four device views.
+                # Every train() ends with a stream synchronisation, so the staging buffer is free again at the next call.
+                blk = stage[off:off + cnt * 152]
+                blk[:cnt * 72] = mem.states[lo:lo + cnt].view(np.uint8)
+                blk[cnt * 72:cnt * 144] = mem.next_states[lo:lo + cnt].view(np.uint8)
+                blk[cnt * 144:cnt * 148] = mem.rewards[lo:lo + cnt].view(np.uint8)
+                blk[cnt * 148:cnt * 152] = mem.dones[lo:lo + cnt].view(np.uint8)
+                up = d["stage"][off:off + cnt * 152].to(self.device, non_blocking=True)
+                d["states"][lo:lo + cnt].copy_(up[:cnt * 72].view(torch.int64).view(cnt, 9))
+                d["next_states"][lo:lo + cnt].copy_(up[cnt * 72:cnt * 144].view(torch.int64).view(cnt, 9))
+                d["rewards"][lo:lo + cnt].copy_(up[cnt * 144:cnt * 148].view(torch.float32))
+                d["dones"][lo:lo + cnt].copy_(up[cnt * 148:cnt * 152].view(torch.float32))
+                off += cnt * 152
+            d["synced"] = mem.appended
+        return d
 
-    def _sample_indices(self):
-        """Uniform minibatch without replacement, like random.sample(self.memory, batch_size)
-        (neural_network.py:224).  random.sample itself costs 1.3 ms for 4 096 of 10 000 in CPython -- eight
-        times the training step -- so the draw is numpy's, from a generator seeded ONCE from the `random`
-        module (random.seed() therefore still makes runs reproducible; the stream is not the reference's)."""
-        if self._np_rng is None:
-            self._np_rng = np.random.Generator(np.random.PCG64(random.getrandbits(128)))
-        return self._np_rng.choice(len(self.memory), self.batch_size, replace=False)
+    def _sample_slots(self):
+        """Uniform minibatch without replacement, like random.sample(self.memory, batch_size) (neural_network.py:224), drawn
+        ON THE DEVICE (torch's CUDA generator: torch.manual_seed makes runs reproducible; the stream is not the reference's
+        `random` stream).  random.sample itself costs 1.3 ms for 4 096 of 10 000 in CPython, eight times the training step."""
+        n = len(self.memory)
+        idx = torch.randperm(n, device=self.device)[:self.batch_size]
+        return (idx + self.memory._start) % self.memory.maxlen
 
     def train(self):
         """neural_network.py:218-252: sample, q=net(s), q'=target(s'), y=r+(1-done)*gamma*q',
-        MSE, Adam step, epsilon decay; returns the loss as a float.  The minibatch is gathered into
-        ONE pinned buffer, reaches the static inputs of the step's CUDA graph with one copy, and the
-        loss comes back with one 4-byte read."""
+        MSE, Adam step, epsilon decay; returns the loss as a float.  New transitions reach the device mirror of the replay
+        memory with one copy, the minibatch is drawn and gathered there straight into the static inputs of the step's
+        CUDA graph, and the loss comes back with one 4-byte read."""
         if len(self.memory) < self.batch_size:
             return 0
         from .train import GraphedDQNStep
-        idx = self.memory.slots(self._sample_indices())
-        st = self._staging()
-        mem = self.memory
-        np.take(mem.states.view(np.uint64).reshape(-1, 9), idx, axis=0, out=st["states"])
-        np.take(mem.next_states.view(np.uint64).reshape(-1, 9), idx, axis=0, out=st["next_states"])
-        np.take(mem.rewards, idx, out=st["rewards"])
-        np.take(mem.dones, idx, out=st["dones"])
+        d = self._device_memory()
         if self._graph_step is None or self._graph_step.batch != self.batch_size or self._graph_step.gamma != float(self.gamma):
             self._graph_step = GraphedDQNStep(self.q_network, self.target_q_network, self.optimizer,
                                               batch=self.batch_size, gamma=self.gamma)
         g = self._graph_step
-        g.load_packed(st["flat"])
+        slots = self._sample_slots()
+        torch.index_select(d["states"], 0, slots, out=g.states)
+        torch.index_select(d["next_states"], 0, slots, out=g.next_states)
+        torch.index_select(d["rewards"], 0, slots, out=g.rewards)
+        torch.index_select(d["dones"], 0, slots, out=g.dones)
         loss = g.run()
+        st = d
         st["loss"].copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         if self.epsilon > self.epsilon_min:

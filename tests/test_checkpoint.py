@@ -144,9 +144,9 @@ def test_agent_checkpoint_round_trip_continues_training_identically(tmp_path, or
     for k, v in a.dqn_agent.q_network.state_dict().items():
         assert torch.equal(b.dqn_agent.q_network.state_dict()[k], v), k
         assert torch.equal(b.dqn_agent.target_q_network.state_dict()[k], a.dqn_agent.target_q_network.state_dict()[k]), k
-    for ag in (a, b):                                  # same minibatches from here on
-        ag.dqn_agent._np_rng = np.random.Generator(np.random.PCG64(2))
+    torch.manual_seed(2)                               # same minibatches from here on (the draw is torch's CUDA generator)
     la = [a.dqn_agent.train() for _ in range(2)]
+    torch.manual_seed(2)
     lb = [b.dqn_agent.train() for _ in range(2)]
     # same kernels on the same bits; fp32 atomics (loss, weight gradients) make the last digits order dependent
     assert la == pytest.approx(lb, rel=1e-5)

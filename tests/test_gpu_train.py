@@ -369,16 +369,31 @@ def test_dqn_agent_train_is_the_graphed_step_and_matches_the_eager_one(cdq, orac
     a, b = agents
     assert len(a.memory) == 300 and a.memory[7][1] == 7 and len(list(a.memory)) == 300
     to_dev = cdq.board_utils.to_device
-    random.seed(100)
     for it in range(3):
+        torch.manual_seed(100 + it)
         la = a.train()
-        if it == 0:
-            random.seed(100)
-        idx = b.memory.slots(b._sample_indices())
+        torch.manual_seed(100 + it)
+        idx = b._sample_slots().cpu().numpy()
         lb = float(dqn_train_step(b.q_network, b.target_q_network, b.optimizer, to_dev(b.memory.states[idx]),
                                   to_dev(b.memory.next_states[idx]), torch.from_numpy(b.memory.rewards[idx]).cuda(),
                                   torch.from_numpy(b.memory.dones[idx]).cuda(), b.gamma).item())
         assert la == pytest.approx(lb, rel=1e-5), it
+    # transitions appended between steps reach the device mirror; a wrapped ring too
+    for i in range(12):
+        a.store_transition(boards[i:i + 1], 1000 + i, 0.5, boards[i + 1:i + 2], False)
+    a.train()
+    d = a._device_memory()
+    assert np.array_equal(d["states"].cpu().numpy().view(np.uint64), a.memory.states.view(np.uint64).reshape(-1, 9))
+    assert np.array_equal(d["rewards"].cpu().numpy(), a.memory.rewards)
+    small = cdq.DQNAgent(batch_size=4)
+    small.memory = cdq.neural_network.ReplayMemory(maxlen=10)
+    for i in range(27):
+        small.store_transition(boards[i:i + 1], i, float(i), boards[i + 1:i + 2], i % 5 == 0)
+        if i % 4 == 3:
+            assert np.isfinite(small.train())
+    d = small._device_memory()
+    assert np.array_equal(d["rewards"].cpu().numpy(), small.memory.rewards) and np.array_equal(d["dones"].cpu().numpy(), small.memory.dones)
+    assert np.array_equal(d["next_states"].cpu().numpy().view(np.uint64), small.memory.next_states.view(np.uint64).reshape(-1, 9))
     # deque(maxlen) semantics of the replay ring
     m = cdq.neural_network.ReplayMemory(maxlen=4)
     for i in range(6):
