@@ -588,10 +588,11 @@ def main():
                 eloss = agent.train()
             esec = time.perf_counter() - t0
             dqn["e2e"] = {"value": B * esteps / esec, "unit": "samples/s", "ms_per_step": esec / esteps * 1e3,
-                          "h2d_bytes_per_step": 152, "d2h_bytes_per_step": 4, "loss": eloss,
-                          "what": "DQNAgent.train() after one store_transition per step: the new transition (152 B) from pinned host memory "
-                                  "to the device mirror of the replay memory, minibatch drawn and gathered on the device, graphed step, "
-                                  "loss back as a float; the initial upload of the 10 000-transition memory (1.5 MB) is outside the timed region"}
+                          "h2d_bytes_per_step": 152 + 12, "d2h_bytes_per_step": 4, "loss": eloss,
+                          "what": "DQNAgent.train() after one store_transition per step: the new transition (152 B) and the ring geometry (12 B) from "
+                                  "host memory to the device mirror of the replay memory (cdq_replay_append), then ONE graph replay -- minibatch drawn "
+                                  "and gathered on the device (cdq_replay_sample), forward, backward, optimizer -- and the loss back as a float; "
+                                  "the initial upload of the 10 000-transition memory (1.5 MB) is outside the timed region"}
             del agent
 
     if rank != 0:

@@ -30,6 +30,11 @@ SIGNATURES = {
     "cdq_host_ctx_destroy": (None, [c_void_p]),
     "cdq_leaf_eval_host_ctx": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "cdq_host_release": (None, []),
+    "cdq_replay_append": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_void_p]),
+    "cdq_replay_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_int64, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "cdq_replay_permute": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32, c_uint64, ctypes.c_uint32]),
     "cdq_train_workspace_bytes": (c_size_t, [c_int64]),
     "cdq_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   ctypes.c_double, ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

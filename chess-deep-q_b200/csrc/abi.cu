@@ -373,6 +373,41 @@ int cdq_train_step(const CdqNet* net, const CdqNet* target_net, const CdqWeights
                          mean_over > 0.0 ? mean_over : (double)n, gamma, loss_kind, *d_grads, d_loss, d_workspace, (cudaStream_t)stream, opt);
 }
 
+int cdq_replay_append(CdqBoard* d_mem_states, CdqBoard* d_mem_next, float* d_mem_reward, float* d_mem_done, int32_t* d_ring,
+                      const CdqBoard* h_states, const CdqBoard* h_next, const float* h_reward, const float* h_done, int64_t first_slot,
+                      int64_t count, int32_t start, int32_t len, int32_t capacity, void* stream) {
+    if (!d_mem_states || !d_mem_next || !d_mem_reward || !d_mem_done || !d_ring || count < 0 || first_slot < 0 ||
+        first_slot + count > capacity || len < 0 || len > capacity || start < 0 || start >= (capacity > 0 ? capacity : 1) ||
+        (count > 0 && (!h_states || !h_next || !h_reward || !h_done)))
+        return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count > 0) {
+        CDQ_CUDA(cudaMemcpyAsync(d_mem_states + first_slot, h_states, count * sizeof(CdqBoard), cudaMemcpyHostToDevice, st));
+        CDQ_CUDA(cudaMemcpyAsync(d_mem_next + first_slot, h_next, count * sizeof(CdqBoard), cudaMemcpyHostToDevice, st));
+        CDQ_CUDA(cudaMemcpyAsync(d_mem_reward + first_slot, h_reward, count * 4, cudaMemcpyHostToDevice, st));
+        CDQ_CUDA(cudaMemcpyAsync(d_mem_done + first_slot, h_done, count * 4, cudaMemcpyHostToDevice, st));
+    }
+    const int32_t geo[3] = {start, len, capacity};      // pageable source: the runtime stages it before returning
+    CDQ_CUDA(cudaMemcpyAsync(d_ring, geo, sizeof(geo), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int cdq_replay_sample(const CdqBoard* d_mem_states, const CdqBoard* d_mem_next, const float* d_mem_reward, const float* d_mem_done,
+                      const int32_t* d_ring, uint64_t seed, uint32_t* d_counter, int64_t batch, CdqBoard* d_states,
+                      CdqBoard* d_next_states, float* d_reward, float* d_done, void* stream) {
+    if (!d_mem_states || !d_mem_next || !d_mem_reward || !d_mem_done || !d_ring || !d_counter || batch <= 0 || !d_states ||
+        !d_next_states || !d_reward || !d_done)
+        return CDQ_E_BADARG;
+    if (int e = check_device()) return e;
+    return launch_replay_sample(d_mem_states, d_mem_next, d_mem_reward, d_mem_done, d_ring, seed, d_counter, batch, d_states,
+                                d_next_states, d_reward, d_done, (cudaStream_t)stream);
+}
+
+uint32_t cdq_replay_permute(uint32_t k, uint32_t len, uint64_t seed, uint32_t counter) {
+    return len ? replay_permute_host(k, len, seed, counter) : 0u;
+}
+
 int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n_params, int step, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream) {
     if (!d_params || !d_grads || !d_m || !d_v || n_params < 0 || step < 1) return CDQ_E_BADARG;

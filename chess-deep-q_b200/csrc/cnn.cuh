@@ -53,6 +53,10 @@ int launch_fc_head_split(const __half* act2, long long n, const PackedNet& net, 
                          float* leaf, float* hidden, cudaStream_t st, const TrainHead* train_head = nullptr);
 
 size_t train_workspace_bytes(long long n);
+int launch_replay_sample(const CdqBoard* mem_states, const CdqBoard* mem_next, const float* mem_reward, const float* mem_done,
+                         const int* ring, unsigned long long seed, unsigned* counter, long long batch, CdqBoard* states, CdqBoard* next,
+                         float* reward, float* done, cudaStream_t st);
+unsigned replay_permute_host(unsigned k, unsigned len, unsigned long long seed, unsigned counter);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2,
                 float eps, float grad_scale, cudaStream_t st);
 

@@ -287,6 +287,71 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, int s
 }
 
 // ------------------------------------------------------------------------------------------
+// Replay minibatch on the device (random.sample + torch.stack of DQNAgent.train, neural_network.py:224-229).  The draw is a
+// pseudo-random PERMUTATION of the logical indices [0, len): a four-round Feistel network on b bits (2^b >= len) with
+// cycle walking, keyed by (seed, draw counter); its first `batch` images are `batch` distinct, uniformly drawn entries, every
+// thread computes its own, and a host restatement reproduces them (tests/test_gpu_train.py).
+__host__ __device__ inline unsigned long long replay_mix(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline unsigned replay_permute(unsigned k, unsigned len, unsigned long long key) {
+    unsigned half = 1;                                   // bits per Feistel half
+    while ((1u << (2 * half)) < len) half++;
+    const unsigned mask = (1u << half) - 1u;
+    unsigned x = k;
+    do {
+        unsigned l = x >> half, r = x & mask;
+        for (int round = 0; round < 4; round++) {
+            const unsigned f = (unsigned)replay_mix(key + ((unsigned long long)round << 32) + r) & mask;
+            const unsigned t = l ^ f;
+            l = r; r = t;
+        }
+        x = (l << half) | r;
+    } while (x >= len);                                  // cycle walking keeps it a permutation of [0, len)
+    return x;
+}
+__global__ void __launch_bounds__(256)
+replay_sample_kernel(const unsigned long long* __restrict__ mem_states, const unsigned long long* __restrict__ mem_next,
+                     const float* __restrict__ mem_reward, const float* __restrict__ mem_done, const int* __restrict__ ring,
+                     unsigned long long seed, unsigned* __restrict__ counter, long long batch, unsigned long long* __restrict__ states,
+                     unsigned long long* __restrict__ next, float* __restrict__ reward, float* __restrict__ done) {
+    const int start = ring[0], len = ring[1], cap = ring[2];
+    const unsigned long long key = replay_mix(seed ^ replay_mix((unsigned long long)*counter));
+    // one thread per (sample, word): 9 words of the state record, 9 of the next state, reward + done ride with word 0
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long k = t / 9;
+    const int word = (int)(t - k * 9);
+    if (k < batch && len > 0) {
+        const int slot = (int)(((long long)start + replay_permute((unsigned)k, (unsigned)len, key)) % cap);
+        states[k * 9 + word] = mem_states[(long long)slot * 9 + word];
+        next[k * 9 + word] = mem_next[(long long)slot * 9 + word];
+        if (word == 0) { reward[k] = mem_reward[slot]; done[k] = mem_done[slot]; }
+    }
+    // the draw counter advances once per launch, after every CTA has read it: last block out (ring[3] counts arrivals)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* arrivals = const_cast<int*>(ring) + 3;
+        if (atomicAdd(arrivals, 1) == (int)gridDim.x - 1) { *arrivals = 0; *counter += 1u; }
+    }
+}
+int launch_replay_sample(const CdqBoard* mem_states, const CdqBoard* mem_next, const float* mem_reward, const float* mem_done,
+                         const int* ring, unsigned long long seed, unsigned* counter, long long batch, CdqBoard* states, CdqBoard* next,
+                         float* reward, float* done, cudaStream_t st) {
+    ProfileScope ps(KK_TRAIN, st);
+    replay_sample_kernel<<<(unsigned)((batch * 9 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const unsigned long long*>(mem_states), reinterpret_cast<const unsigned long long*>(mem_next), mem_reward, mem_done,
+        ring, seed, counter, batch, reinterpret_cast<unsigned long long*>(states), reinterpret_cast<unsigned long long*>(next), reward, done);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+unsigned replay_permute_host(unsigned k, unsigned len, unsigned long long seed, unsigned counter) {
+    return replay_permute(k, len, replay_mix(seed ^ replay_mix((unsigned long long)counter)));
+}
+
+// ------------------------------------------------------------------------------------------
 // workspace carve-up (bytes per position; everything 256-byte aligned per section)
 struct TrainWs {
     __half* act2_tiles; __half* act2_target; __half* dz1h; __half* a1_dump; __half* a1_boards; __half* dz2_boards; unsigned* sched; unsigned* relu_mask; float* hidden; float* q; float* qn; float* dz1c;

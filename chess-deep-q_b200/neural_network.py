@@ -371,73 +371,58 @@ class DQNAgent:
         self.memory.append((s, move, float(reward), ns, float(done)))
 
     def _device_memory(self):
-        """Device mirror of the replay memory ([maxlen] records x 2, rewards, dones: 1.5 MB), brought up to date with ONE
-        host-to-device copy of the transitions appended since the last call (in self-play: one per training step,
-        chess_ai.py:187-192) through a pinned staging buffer.  The minibatch is then drawn and gathered on the device."""
+        """Device mirror of the replay memory (four arrays of maxlen entries: 1.5 MB; ring geometry and draw counter next to
+        them), brought up to date by cdq_replay_append with the transitions stored since the last call (in self-play: one per
+        training step, chess_ai.py:187-192).  The minibatch is drawn and gathered from it by cdq_replay_sample inside the
+        training step's CUDA graph."""
         mem = self.memory
         if self._dmem is None or self._dmem["maxlen"] != mem.maxlen or self._dmem["memory"] is not mem:
             dev, n = self.device, mem.maxlen
-            flat = torch.zeros(n * 152, dtype=torch.uint8, device=dev)
-            self._dmem = {"maxlen": n, "memory": mem, "synced": 0, "flat": flat,
-                          "states": flat[:n * 72].view(torch.int64).view(n, 9),
-                          "next_states": flat[n * 72:n * 144].view(torch.int64).view(n, 9),
-                          "rewards": flat[n * 144:n * 148].view(torch.float32),
-                          "dones": flat[n * 148:n * 152].view(torch.float32),
-                          "stage": torch.empty(n * 152, dtype=torch.uint8).pin_memory(),
+            self._dmem = {"maxlen": n, "memory": mem, "synced": 0,
+                          "states": torch.zeros((n, 9), dtype=torch.int64, device=dev),
+                          "next_states": torch.zeros((n, 9), dtype=torch.int64, device=dev),
+                          "rewards": torch.zeros(n, dtype=torch.float32, device=dev),
+                          "dones": torch.zeros(n, dtype=torch.float32, device=dev),
+                          "ring": torch.zeros(4, dtype=torch.int32, device=dev),
+                          "counter": torch.zeros(1, dtype=torch.int32, device=dev),
+                          "seed": random.getrandbits(63),          # random.seed() makes the draws reproducible
                           "loss": torch.empty(1, dtype=torch.float32).pin_memory()}
+            self._graph_step = None                               # the graph holds the old mirror's addresses
         d = self._dmem
         new = min(mem.appended - d["synced"], mem._len)
-        if new > 0:
-            n = mem.maxlen
-            first = (mem._start + mem._len - new) % n               # slots [first, first + new) modulo maxlen
-            stage, off = d["stage"].numpy(), 0
-            head = min(new, n - first)
-            for lo, cnt in ((first, head), (0, new - head)):
-                if cnt <= 0:
-                    continue
-                # one staging block per segment: [cnt records | cnt records | cnt rewards | cnt dones], one H2D copy, four device views.
-                # Every train() ends with a stream synchronisation, so the staging buffer is free again at the next call.
-                blk = stage[off:off + cnt * 152]
-                blk[:cnt * 72] = mem.states[lo:lo + cnt].view(np.uint8)
-                blk[cnt * 72:cnt * 144] = mem.next_states[lo:lo + cnt].view(np.uint8)
-                blk[cnt * 144:cnt * 148] = mem.rewards[lo:lo + cnt].view(np.uint8)
-                blk[cnt * 148:cnt * 152] = mem.dones[lo:lo + cnt].view(np.uint8)
-                up = d["stage"][off:off + cnt * 152].to(self.device, non_blocking=True)
-                d["states"][lo:lo + cnt].copy_(up[:cnt * 72].view(torch.int64).view(cnt, 9))
-                d["next_states"][lo:lo + cnt].copy_(up[cnt * 72:cnt * 144].view(torch.int64).view(cnt, 9))
-                d["rewards"][lo:lo + cnt].copy_(up[cnt * 144:cnt * 148].view(torch.float32))
-                d["dones"][lo:lo + cnt].copy_(up[cnt * 148:cnt * 152].view(torch.float32))
-                off += cnt * 152
-            d["synced"] = mem.appended
+        n = mem.maxlen
+        first = (mem._start + mem._len - new) % n                   # slots [first, first + new) modulo maxlen
+        head = min(new, n - first)
+        L, st = _lib.lib(), _lib.stream_ptr()
+        segments = [(lo, cnt) for lo, cnt in ((first, head), (0, new - head)) if cnt > 0] or [(0, 0)]   # (0, 0): geometry only
+        for lo, cnt in segments:
+            _lib.check(L.cdq_replay_append(d["states"].data_ptr(), d["next_states"].data_ptr(), d["rewards"].data_ptr(),
+                                           d["dones"].data_ptr(), d["ring"].data_ptr(), mem.states[lo:].ctypes.data,
+                                           mem.next_states[lo:].ctypes.data, mem.rewards[lo:].ctypes.data, mem.dones[lo:].ctypes.data,
+                                           lo, cnt, mem._start, mem._len, n, st))
+        d["synced"] = mem.appended
         return d
 
-    def _sample_slots(self):
-        """Uniform minibatch without replacement, like random.sample(self.memory, batch_size) (neural_network.py:224), drawn
-        ON THE DEVICE (torch's CUDA generator: torch.manual_seed makes runs reproducible; the stream is not the reference's
-        `random` stream).  random.sample itself costs 1.3 ms for 4 096 of 10 000 in CPython, eight times the training step."""
-        n = len(self.memory)
-        idx = torch.randperm(n, device=self.device)[:self.batch_size]
-        return (idx + self.memory._start) % self.memory.maxlen
+    def sampled_indices(self, draw):
+        """Logical indices (0 = oldest entry) of the minibatch of draw number `draw` (0 = this agent's first train() call),
+        as cdq_replay_sample computes them on the device: for tests and reproducibility."""
+        L, d = _lib.lib(), self._dmem
+        return [int(L.cdq_replay_permute(k, len(self.memory), d["seed"], draw)) for k in range(self.batch_size)]
 
     def train(self):
         """neural_network.py:218-252: sample, q=net(s), q'=target(s'), y=r+(1-done)*gamma*q',
-        MSE, Adam step, epsilon decay; returns the loss as a float.  New transitions reach the device mirror of the replay
-        memory with one copy, the minibatch is drawn and gathered there straight into the static inputs of the step's
-        CUDA graph, and the loss comes back with one 4-byte read."""
+        MSE, Adam step, epsilon decay; returns the loss as a float.  Transitions stored since the last call reach the device
+        mirror of the replay memory with one small copy each; drawing the minibatch (uniform, without replacement, like
+        random.sample: neural_network.py:224), gathering it, the whole step and the optimizer are ONE CUDA graph replay, and
+        the loss comes back with one 4-byte read."""
         if len(self.memory) < self.batch_size:
             return 0
         from .train import GraphedDQNStep
         d = self._device_memory()
         if self._graph_step is None or self._graph_step.batch != self.batch_size or self._graph_step.gamma != float(self.gamma):
             self._graph_step = GraphedDQNStep(self.q_network, self.target_q_network, self.optimizer,
-                                              batch=self.batch_size, gamma=self.gamma)
-        g = self._graph_step
-        slots = self._sample_slots()
-        torch.index_select(d["states"], 0, slots, out=g.states)
-        torch.index_select(d["next_states"], 0, slots, out=g.next_states)
-        torch.index_select(d["rewards"], 0, slots, out=g.rewards)
-        torch.index_select(d["dones"], 0, slots, out=g.dones)
-        loss = g.run()
+                                              batch=self.batch_size, gamma=self.gamma, replay=d)
+        loss = self._graph_step.run()
         st = d
         st["loss"].copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()

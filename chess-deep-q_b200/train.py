@@ -331,8 +331,13 @@ class GraphedDQNStep:
     global_batch when the shards are not all the same size, so that the step is the mean over the
     global batch (neural_network.py:241) and not the mean of the shard means."""
 
-    def __init__(self, q_network, target_network, optimizer, batch, gamma=0.99, loss_kind=LOSS_MSE, global_batch=None):
+    def __init__(self, q_network, target_network, optimizer, batch, gamma=0.99, loss_kind=LOSS_MSE, global_batch=None,
+                 replay=None):
+        """replay: a device-resident replay memory (dict of tensors states / next_states / rewards / dones / ring / counter
+        and an int seed, see DQNAgent._device_memory): the minibatch is then drawn and gathered by cdq_replay_sample as the
+        first node of the graph, so a step needs no input from the host at all."""
         dev = _lib.require_cuda()
+        self.replay = replay
         self.q_network, self.target_network, self.optimizer = q_network, target_network, optimizer
         self.batch, self.gamma, self.loss_kind = int(batch), float(gamma), int(loss_kind)
         self.mean_over = _mean_over(self.batch, global_batch, optimizer.world)
@@ -355,6 +360,12 @@ class GraphedDQNStep:
         weights = _weights_struct([params[k] for k in PARAM_ORDER])
         gv = self.optimizer.grad_views()
         grads = _weights_struct([gv[k] for k in PARAM_ORDER])
+        if self.replay is not None:
+            r = self.replay
+            _lib.check(_lib.lib().cdq_replay_sample(r["states"].data_ptr(), r["next_states"].data_ptr(), r["rewards"].data_ptr(),
+                                                    r["dones"].data_ptr(), r["ring"].data_ptr(), r["seed"], r["counter"].data_ptr(),
+                                                    self.batch, self.states.data_ptr(), self.next_states.data_ptr(),
+                                                    self.rewards.data_ptr(), self.dones.data_ptr(), _lib.stream_ptr()))
         opt = self.optimizer.optimizer_struct()
         _lib.check(_lib.lib().cdq_train_step(
             self.q_network.raw_handle(), self.target_network.net_handle(), ctypes.byref(weights),

@@ -209,6 +209,23 @@ void cdq_host_release(void);
 #define CDQ_TRAIN_WS_PERSISTENT 0x100
 #define CDQ_TRAIN_REPACK 0x200 /* re-pack `net` from d_weights inside the call (next to the target forward) */
 #define CDQ_TRAIN_ZERO_LOSS 0x400 /* *d_loss is zeroed inside the call (no separate fill launch in a captured step) */
+/* Replay memory on the device (replaces `random.sample(self.memory, batch_size)` + `torch.stack(...).to(device)` of
+ * DQNAgent.train, neural_network.py:224-229).  The ring lives in device memory as four arrays of `capacity` entries (state
+ * records, next-state records, rewards, done flags) plus d_ring = 4 x int32 {start slot, length, capacity, scratch (zero it once)}.
+ * cdq_replay_append copies `count` new transitions from HOST memory into slots [first_slot, first_slot + count) (a wrapped
+ * range is two calls) and publishes the ring's new geometry.  cdq_replay_sample draws `batch` DISTINCT entries uniformly
+ * among the `len` logical entries and copies them into the step's input buffers: entry k of the minibatch is logical index
+ * cdq_replay_permute(k, len, seed, *d_counter) -- a keyed pseudo-random permutation (four-round Feistel network with cycle
+ * walking), so every thread computes its own index and the host can reproduce the draw -- and *d_counter advances by one per
+ * call (both read on the device: the call is CUDA-graph friendly).  batch <= len is the caller's business: with batch > len
+ * only the first len entries of the minibatch are written. */
+int cdq_replay_append(CdqBoard* d_mem_states, CdqBoard* d_mem_next, float* d_mem_reward, float* d_mem_done, int32_t* d_ring,
+                      const CdqBoard* h_states, const CdqBoard* h_next, const float* h_reward, const float* h_done, int64_t first_slot,
+                      int64_t count, int32_t start, int32_t len, int32_t capacity, void* stream);
+int cdq_replay_sample(const CdqBoard* d_mem_states, const CdqBoard* d_mem_next, const float* d_mem_reward, const float* d_mem_done,
+                      const int32_t* d_ring, uint64_t seed, uint32_t* d_counter, int64_t batch, CdqBoard* d_states,
+                      CdqBoard* d_next_states, float* d_reward, float* d_done, void* stream);
+uint32_t cdq_replay_permute(uint32_t k, uint32_t len, uint64_t seed, uint32_t counter);
 size_t cdq_train_workspace_bytes(int64_t n);
 int cdq_train_fwd_bwd(const CdqNet* net, const CdqNet* target_net, const CdqWeights* d_weights,
                       const CdqBoard* d_states, const CdqBoard* d_next_states, const float* d_reward,

@@ -144,9 +144,12 @@ def test_agent_checkpoint_round_trip_continues_training_identically(tmp_path, or
     for k, v in a.dqn_agent.q_network.state_dict().items():
         assert torch.equal(b.dqn_agent.q_network.state_dict()[k], v), k
         assert torch.equal(b.dqn_agent.target_q_network.state_dict()[k], a.dqn_agent.target_q_network.state_dict()[k]), k
-    torch.manual_seed(2)                               # same minibatches from here on (the draw is torch's CUDA generator)
+    for ag in (a.dqn_agent, b.dqn_agent):              # same minibatches from here on: same seed and draw counter
+        ag._device_memory()
+        ag._dmem["seed"] = 1234
+        ag._dmem["counter"].zero_()
+        ag._graph_step = None                          # the graph holds the seed as a kernel argument
     la = [a.dqn_agent.train() for _ in range(2)]
-    torch.manual_seed(2)
     lb = [b.dqn_agent.train() for _ in range(2)]
     # same kernels on the same bits; fp32 atomics (loss, weight gradients) make the last digits order dependent
     assert la == pytest.approx(lb, rel=1e-5)

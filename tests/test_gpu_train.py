@@ -370,14 +370,22 @@ def test_dqn_agent_train_is_the_graphed_step_and_matches_the_eager_one(cdq, orac
     assert len(a.memory) == 300 and a.memory[7][1] == 7 and len(list(a.memory)) == 300
     to_dev = cdq.board_utils.to_device
     for it in range(3):
-        torch.manual_seed(100 + it)
         la = a.train()
-        torch.manual_seed(100 + it)
-        idx = b._sample_slots().cpu().numpy()
+        logical = a.sampled_indices(it)                 # what cdq_replay_sample drew on the device, recomputed on the host
+        assert len(set(logical)) == a.batch_size and max(logical) < len(a.memory)
+        idx = b.memory.slots(logical)
         lb = float(dqn_train_step(b.q_network, b.target_q_network, b.optimizer, to_dev(b.memory.states[idx]),
                                   to_dev(b.memory.next_states[idx]), torch.from_numpy(b.memory.rewards[idx]).cuda(),
                                   torch.from_numpy(b.memory.dones[idx]).cuda(), b.gamma).item())
         assert la == pytest.approx(lb, rel=1e-5), it
+    # the draw is a permutation: uniform over the memory (chi-square-free sanity: every eighth of the memory gets its share)
+    L = cdq._lib.lib()
+    hist = np.zeros(8)
+    for draw in range(40):
+        for k in range(128):
+            hist[int(L.cdq_replay_permute(k, 300, 99, draw)) * 8 // 300] += 1
+    assert hist.min() > 0.8 * hist.mean() and hist.max() < 1.2 * hist.mean()
+    assert sorted(int(L.cdq_replay_permute(k, 300, 7, 3)) for k in range(300)) == list(range(300))
     # transitions appended between steps reach the device mirror; a wrapped ring too
     for i in range(12):
         a.store_transition(boards[i:i + 1], 1000 + i, 0.5, boards[i + 1:i + 2], False)
