@@ -159,3 +159,43 @@ def test_optimized_chess_ai_trains_through_self_play(cdq, oracle, tmp_path):
     ai.save_model(str(tmp_path / "m.pth"))
     ck = torch.load(str(tmp_path / "m.pth"), map_location="cpu", weights_only=False)
     assert ck["total_games_trained"] == 6 and ck["training_games"] == 6 and len(ck["move_count_history"]) == 6
+
+
+def test_maximum_move_count_and_widest_configuration(cdq, oracle):
+    """Edge cases of the expansion: the position with the most legal moves known (218) through cdq_expand_weighted
+    (all of them, with categorize_moves' weights), cdq_sample_children and a forest search at the limits the ABI
+    states (width 32, depth 8, 32 workers), against the oracle and the host restatement."""
+    from forest_restatement import Restatement
+    L = cdq._lib.lib()
+    root = oracle.from_fen("R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - - 0 1")
+    assert len(oracle.legal_moves(root)) == 218
+    d = cdq.board_utils.to_device(root)
+    kids = torch.empty((1, 224, 9), dtype=torch.int64, device="cuda")
+    counts = torch.empty(1, dtype=torch.int32, device="cuda")
+    wts = torch.empty((1, 224), dtype=torch.uint8, device="cuda")
+    st = cdq._lib.stream_ptr()
+    cdq._lib.check(L.cdq_expand_weighted(d.data_ptr(), 1, 224, kids.data_ptr(), counts.data_ptr(), wts.data_ptr(), st))
+    assert int(counts.item()) == 218
+    got = {k.tobytes(): int(w) for k, w in zip(_recs(kids[0, :218]), wts[0, :218].cpu().numpy())}
+    mv, w = oracle.categorize(root)
+    want = {oracle.push(root, m)[0].tobytes(): int(x) for m, x in zip(mv, w)}
+    assert got == want
+    # weighted sampling over all 218 children: 32 distinct ones, and exactly the host restatement's choice
+    seeds = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    sel = torch.empty((1, 32, 9), dtype=torch.int64, device="cuda")
+    selc = torch.empty(1, dtype=torch.int32, device="cuda")
+    cdq._lib.check(L.cdq_sample_children(kids.data_ptr(), counts.data_ptr(), wts.data_ptr(), 1, 224, 32, seeds.data_ptr(),
+                                         sel.data_ptr(), selc.data_ptr(), st))
+    assert int(selc.item()) == 32 and len({k.tobytes() for k in _recs(sel[0])}) == 32
+    net = _net(cdq, oracle)
+    widths, workers, iterations = [32] * 8, 32, 40
+    forest = cdq.mcts.DeviceForest(2, workers, widths, iterations)
+    roots = np.concatenate([root, cdq.mcts._startpos()])
+    forest.set_games(roots, [3, 4], ply=[60, 0])
+    forest.search(net, iterations)
+    torch.cuda.synchronize()
+    rs = Restatement(cdq, net, workers, widths)
+    for i in range(2):
+        _compare(cdq, forest, i, rs.search(roots[i], [3, 4][i], iterations, ply=[60, 0][i]), roots[i])
+    assert int(forest.root_children[0].item()) == 32
+    forest.close()
