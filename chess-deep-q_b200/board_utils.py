@@ -103,3 +103,36 @@ def planes_to_packed(planes, turn_white=True):
     out[:, 7] = black
     out[:, 8] = 1 if turn_white else 0
     return out
+
+
+class Move:
+    """Stand-in for chess.Move where python-chess is not installed: from_square, to_square,
+    promotion (piece type 2..5 or None), uci(); compares equal to anything with the same uci()."""
+    __slots__ = ("from_square", "to_square", "promotion")
+
+    def __init__(self, from_square, to_square, promotion=None):
+        self.from_square, self.to_square, self.promotion = int(from_square), int(to_square), promotion
+
+    def uci(self):
+        name = lambda s: "abcdefgh"[s & 7] + str((s >> 3) + 1)  # noqa: E731
+        return name(self.from_square) + name(self.to_square) + ("" if self.promotion is None else " nbrq"[self.promotion])
+
+    def __eq__(self, other):
+        return hasattr(other, "uci") and other.uci() == self.uci()
+
+    def __hash__(self):
+        return hash(self.uci())
+
+    def __repr__(self):
+        return "Move.from_uci(%r)" % self.uci()
+
+
+def _make_move(board, frm, to, promo):
+    """chess.Move when the caller handed us a python-chess board (so `board.push(move)` works), else Move."""
+    if hasattr(board, "legal_moves"):
+        try:
+            import chess
+            return chess.Move(frm, to, promotion=promo)
+        except ImportError:
+            pass
+    return Move(frm, to, promo)

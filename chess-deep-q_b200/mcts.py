@@ -304,6 +304,21 @@ class BatchedRussianDollMCTS:
         return search_many([self], net, training_progress, [current_move], max_moves)[0]
 
 
+class ParallelRussianDollMCTS(BatchedRussianDollMCTS):
+    """The reference's class name, constructor and return type (mcts.py:14-116), so that
+    `from chess_deep_q_b200.mcts import ParallelRussianDollMCTS` is the import swap for neural_network.py:166-181:
+    search() returns the move -- a chess.Move when the board is a python-chess board, else board_utils.Move -- or None."""
+
+    def __init__(self, board, iterations=20, exploration_weight=1.0, samples_per_level=None, num_workers=None):
+        super().__init__(board, iterations, exploration_weight, samples_per_level, num_workers)
+        self.board = board
+
+    def search(self, neural_net=None, device=None, training_progress=0.0, current_move=0, max_moves=200):
+        from .board_utils import _make_move
+        child, mv = super().search(neural_net, device, training_progress, current_move, max_moves)
+        return None if child is None else _make_move(self.board, *mv)
+
+
 def search_many(trees, neural_net, training_progress=0.0, current_moves=None, max_moves=200):
     """The searches of several trees (e.g. one per concurrent self-play game) as ONE device forest: every level of a
     wave is one kernel for all trees, every wave one cdq_leaf_eval.  A tree's result depends only on its own seed and

@@ -199,3 +199,28 @@ def test_maximum_move_count_and_widest_configuration(cdq, oracle):
         _compare(cdq, forest, i, rs.search(roots[i], [3, 4][i], iterations, ply=[60, 0][i]), roots[i])
     assert int(forest.root_children[0].item()) == 32
     forest.close()
+
+
+def test_reference_call_surface_with_a_chess_board(cdq, oracle):
+    """The import swap of INTEGRATION.md with a python-chess style Board (here the restated `chess` API of oracle/): the
+    reference's own calls -- ParallelRussianDollMCTS(board, ...).search(neural_net=, device=, ...) (neural_network.py:166-181)
+    and DQNAgent.select_move(board, progress, is_training, current_move, max_moves) (chess_ai.py:51-58) -- return a
+    chess.Move that is legal on that board and can be pushed."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "pychess_shim"))
+    import chess
+    board = chess.Board()
+    for uci in ("e2e4", "e7e5", "g1f3", "b8c6"):
+        board.push([m for m in board.legal_moves if m.uci() == uci][0])
+    net = _net(cdq, oracle)
+    tree = cdq.ParallelRussianDollMCTS(board, iterations=24, exploration_weight=1.6, samples_per_level=[25, 15, 10, 7, 5, 3, 2], num_workers=7)
+    move = tree.search(neural_net=net, device=torch.device("cuda"), training_progress=0.0, current_move=4, max_moves=200)
+    assert isinstance(move, chess.Move) and move.uci() in {m.uci() for m in board.legal_moves}
+    board.push(move)
+    agent = cdq.DQNAgent()
+    mv = agent.select_move(board, 0.0, True, 5, 200)
+    assert isinstance(mv, chess.Move) and mv.uci() in {m.uci() for m in board.legal_moves}
+    board.push(mv)
+    assert agent.get_q_value(board) == pytest.approx(float(agent.q_network.forward_packed(cdq.pack_board(board)).item()))
+    assert isinstance(cdq.fast_evaluate_position(board), float)
