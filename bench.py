@@ -538,7 +538,9 @@ def main():
                "ms_per_step": dms / dsteps, "scaling": "strong", "loss": float(dloss.item()),
                "tensor_bound_frac": (19154944.0 * B / world) / (dms / dsteps * 1e-3) / 1e12 / measured_peaks()["tflops"],
                "parallelism": ("dp%d: one CUDA graph per rank; gradients reduce-scattered, Adam and parameter all-gather "
-                               "in one kernel over NVLink peer memory" % world) if world > 1 else
+                               "in one kernel over NVLink peer memory%s" % (world, " (NVLS: multimem.ld_reduce / multimem.st through the switch's "
+                                                                             "multicast mapping)" if opt.region is not None and opt.region.multicast
+                                                                      else " (unicast peer loads / stores)")) if world > 1 else
                               "single GPU, whole step as one CUDA graph"}
         if opt.region is not None:
             if dist:

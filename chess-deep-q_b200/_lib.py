@@ -89,7 +89,8 @@ MAX_RANKS = 8
 
 
 class CdqDpPeers(ctypes.Structure):
-    _fields_ = [("params", c_void_p * MAX_RANKS), ("grads", c_void_p * MAX_RANKS), ("flags", c_void_p * MAX_RANKS)]
+    _fields_ = [("params", c_void_p * MAX_RANKS), ("grads", c_void_p * MAX_RANKS), ("flags", c_void_p * MAX_RANKS),
+                ("mc_params", c_void_p), ("mc_grads", c_void_p)]
 
 
 class CdqOptimizer(ctypes.Structure):

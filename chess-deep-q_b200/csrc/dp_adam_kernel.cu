@@ -45,6 +45,16 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// NVLS: one load that returns the sum over every rank's copy (added inside the NVSwitch), one store that lands in every copy
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // every CTA waits until all W ranks have published `epoch` in this rank's flag row; true = the wait ran out
 __device__ __forceinline__ bool wait_peers(const unsigned* my_flags, int world, unsigned epoch, unsigned long long deadline,
                                            unsigned* err) {
@@ -86,6 +96,7 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0) { trace[0] = deadline - timeout_ns; trace[1] = globaltimer_ns(); }
 #endif
     const float bc1 = s_bc[0], bc2_sqrt = s_bc[1], inv_world = 1.f / (float)world;
+    const bool multicast = peers.mc_params != nullptr && peers.mc_grads != nullptr;
 
     // ---- reduce-scatter + Adam + all-gather on this rank's slice (skipped when a peer's gradients never arrived)
     // the chunks [chunk_lo, chunk_hi) followed by [chunk_lo2, chunk_hi2) form one virtual range that is sliced over the ranks
@@ -94,10 +105,12 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
     for (long long ci = lo + (long long)blockIdx.x * DP_THREADS + threadIdx.x; ci < hi; ci += (long long)gridDim.x * DP_THREADS) {
         const long long c = ci < n1 ? chunk_lo + ci : chunk_lo2 + (ci - n1);
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = 0; p < world; p++) {
-            const float4 x = reinterpret_cast<const float4*>(peers.grads[p])[c];
-            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
-        }
+        if (multicast) g = multimem_ld_reduce_add(peers.mc_grads + 4 * c);
+        else
+            for (int p = 0; p < world; p++) {
+                const float4 x = reinterpret_cast<const float4*>(peers.grads[p])[c];
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            }
         float4 mi = reinterpret_cast<float4*>(m)[c], vi = reinterpret_cast<float4*>(v)[c];
         float4 pi = reinterpret_cast<const float4*>(peers.params[rank])[c];
 #define CDQ_ADAM1(F)                                                                    \
@@ -112,7 +125,9 @@ dp_adam_kernel(const CdqDpPeers peers, int rank, int world, float* __restrict__ 
 #undef CDQ_ADAM1
         reinterpret_cast<float4*>(m)[c] = mi;
         reinterpret_cast<float4*>(v)[c] = vi;
-        for (int p = 0; p < world; p++) reinterpret_cast<float4*>(peers.params[p])[c] = pi;
+        if (multicast) multimem_st(peers.mc_params + 4 * c, pi);
+        else
+            for (int p = 0; p < world; p++) reinterpret_cast<float4*>(peers.params[p])[c] = pi;
     }
 
     // ---- B: all CTAs of this rank have stored; publish, then wait until every peer's stores have landed here

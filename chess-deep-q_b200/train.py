@@ -52,46 +52,75 @@ class _DevicePtr:
 
 
 class PeerRegion:
-    """One device region per rank -- [flat parameters | flat gradients | flag row] -- exported with
-    CUDA IPC and mapped by every other rank of the data-parallel group, for cdq_dp_adam_step (the
-    fused reduce-scatter + Adam + all-gather kernel).  world = 1 needs no mapping at all."""
+    """One device region per rank -- [flat parameters | flat gradients | flag rows] -- mapped by every other rank of the
+    data-parallel group, for cdq_dp_adam_step / cdq_train_step (the fused reduce-scatter + Adam + all-gather kernel).
+    Two ways to get the mapping, both plumbing only:
+      * torch.distributed._symmetric_memory (default where it works): peer pointers AND, on NVSwitch machines, an NVLink
+        MULTICAST address of the region, with which the kernel reduces in the switch (multimem.ld_reduce) and broadcasts
+        with one store (multimem.st);
+      * CUDA IPC handles exchanged through the process group (cdq_ipc_*): unicast peer access only.
+    CDQ_DP_SYMM=0 forces the second, CDQ_DP_MULTICAST=0 keeps symmetric memory but ignores its multicast address.
+    world = 1 needs no mapping at all."""
 
     FLAG_BYTES = 256
 
     def __init__(self, group=None):
+        import os
         import torch.distributed as dist
         dev = _lib.require_cuda()
-        L = _lib.lib()
         self.rank, self.world = 0, 1
         if dist.is_available() and dist.is_initialized():
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > _lib.MAX_RANKS:
             raise _lib.CdqError("cdq_dp_adam_step supports at most %d ranks" % _lib.MAX_RANKS)
         nbytes = 2 * NPARAMS_PAD * 4 + self.FLAG_BYTES
-        base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-        _lib.check(L.cdq_ipc_alloc(nbytes, ctypes.byref(base), handle))
-        self._base, self._mapped = base, []
-        raw = torch.as_tensor(_DevicePtr(base.value, nbytes), device=dev)
+        self._base, self._mapped, self._symm = None, [], None
+        self.multicast = False
+        bases, mc = None, 0
+        if self.world > 1 and os.environ.get("CDQ_DP_SYMM", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                raw = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+                raw.zero_()
+                torch.cuda.synchronize()
+                hdl = symm.rendezvous(raw, group if group is not None else dist.group.WORLD)
+                bases = [int(p) for p in hdl.buffer_ptrs]
+                mc = int(hdl.multicast_ptr) if os.environ.get("CDQ_DP_MULTICAST", "1") != "0" else 0
+                self._symm = (raw, hdl)
+            except Exception as e:  # noqa: BLE001 -- symmetric memory is an optimisation; CUDA IPC below always works
+                self._symm_error = repr(e)
+                bases = None
+        if bases is None:
+            L = _lib.lib()
+            base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            _lib.check(L.cdq_ipc_alloc(nbytes, ctypes.byref(base), handle))
+            self._base = base
+            raw = torch.as_tensor(_DevicePtr(base.value, nbytes), device=dev)
+            bases = [None] * self.world
+            bases[self.rank] = base.value
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    ptr = ctypes.c_void_p()
+                    _lib.check(L.cdq_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(ptr)))
+                    self._mapped.append(ptr)
+                    bases[r] = ptr.value
         self.params = raw[:NPARAMS_PAD * 4].view(torch.float32)
         self.grads = raw[NPARAMS_PAD * 4:2 * NPARAMS_PAD * 4].view(torch.float32)
-        bases = [None] * self.world
-        bases[self.rank] = base.value
         if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    continue
-                ptr = ctypes.c_void_p()
-                _lib.check(L.cdq_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(ptr)))
-                self._mapped.append(ptr)
-                bases[r] = ptr.value
             dist.barrier(group=group)
         self.peers = _lib.CdqDpPeers()
         for r in range(self.world):
             self.peers.params[r] = bases[r]
             self.peers.grads[r] = bases[r] + NPARAMS_PAD * 4
             self.peers.flags[r] = bases[r] + 2 * NPARAMS_PAD * 4
+        if mc:
+            self.multicast = True
+            self.peers.mc_params = mc
+            self.peers.mc_grads = mc + NPARAMS_PAD * 4
 
     def close(self):
         L = _lib.lib()
@@ -99,10 +128,11 @@ class PeerRegion:
         for ptr in self._mapped:
             L.cdq_ipc_close(ptr)
         self._mapped = []
+        self.params = self.grads = None
         if self._base is not None:
-            self.params = self.grads = None
             L.cdq_ipc_free(self._base)
             self._base = None
+        self._symm = None
 
 
 def flatten_parameters(network, flat=None):

@@ -256,7 +256,13 @@ int cdq_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v,
 typedef struct CdqDpPeers {
     float* params[CDQ_MAX_RANKS];
     float* grads[CDQ_MAX_RANKS];
-    uint32_t* flags[CDQ_MAX_RANKS];   /* flags[r] = rank r's row of `world` uint32, zero-initialised */
+    uint32_t* flags[CDQ_MAX_RANKS];   /* flags[r] = rank r's row of 2 x CDQ_MAX_RANKS uint32, zero-initialised */
+    /* Optional NVLink-multicast (NVLS) addresses of the SAME two buffers, i.e. one virtual address that the NVSwitch maps onto
+     * every rank's copy (cuMulticast* objects; torch.distributed._symmetric_memory provides them): with both non-NULL the kernel
+     * sums a gradient chunk of all ranks with ONE multimem.ld_reduce (the addition happens in the switch) and writes a parameter
+     * chunk to all ranks with ONE multimem.st, instead of `world` peer loads and `world` peer stores.  NULL = unicast peer access. */
+    float* mc_params;
+    float* mc_grads;
 } CdqDpPeers;
 int cdq_dp_adam_step(const CdqDpPeers* peers, int rank, int world, float* d_m, float* d_v, int64_t n_params_padded,
                      int32_t* d_step, uint32_t* d_grid_bar, float lr, float beta1, float beta2, float eps, void* stream);
