@@ -213,6 +213,7 @@ enum { MC_SLIDE = 0, MC_KNIGHT = 8, MC_KING = 16, MC_PUSH = 17, MC_PUSH_PROMO = 
 struct MoveList {
     u64 t[MC_COUNT];
     u64 occ, king_bb, att_opp;   // white view
+    int first[MC_COUNT + 1];     // first[k] = index of class k's first move in the enumeration; first[MC_COUNT] = n
     int ep_sq, n;                // n = number of legal moves
     bool ep_legal;               // Board.has_legal_en_passant()
 };
@@ -243,7 +244,8 @@ static __device__ __noinline__ void list_moves(const Pos& w, MoveList& L) {
     gen_side<1>(w, q, L.att_opp, v);
     int n = 0;
 #pragma unroll 1
-    for (int k = 0; k < MC_COUNT; k++) n += popc(L.t[k]) * class_mult(k);
+    for (int k = 0; k < MC_COUNT; k++) { L.first[k] = n; n += popc(L.t[k]) * class_mult(k); }
+    L.first[MC_COUNT] = n;
     L.n = n;
     L.ep_legal = L.t[MC_EP] != 0;
 }
@@ -251,14 +253,10 @@ static __device__ __noinline__ void list_moves(const Pos& w, MoveList& L) {
 static __device__ __noinline__ PlainMove pick_from_list(const MoveList& L, int r) {
     PlainMove m;
     if (r < 0 || r >= L.n) return m;
-    int k = 0, base = 0;
+    int k = 0;
 #pragma unroll 1
-    for (; k < MC_COUNT; k++) {
-        const int c = popc(L.t[k]) * class_mult(k);
-        if (r < base + c) break;
-        base += c;
-    }
-    const int mult = class_mult(k), idx = r - base;
+    while (r >= L.first[k + 1]) k++;         // r < n = first[MC_COUNT]: terminates
+    const int mult = class_mult(k), idx = r - L.first[k];
     const int sq = nth_bit(L.t[k], idx / mult);
     m.found = true;
     m.to = sq;

@@ -409,6 +409,43 @@ def test_dqn_agent_train_is_the_graphed_step_and_matches_the_eager_one(cdq, orac
     assert len(m) == 4 and [x[1] for x in m] == [2, 3, 4, 5] and m[-1][1] == 5
 
 
+def test_split_optimizer_schedule_gives_the_same_step(cdq, oracle, eval_golden, train_golden):
+    """cdq_train_step's optional schedule (option train_split_optimizer = 1: fc1.weight's optimizer launch and repack on
+    the side stream under the convolution backward, the other parameters at the end of the step, the next step starting
+    with the convolution at once) is the same arithmetic on the same elements: parameters, Adam state and loss after
+    several graph replays match the default schedule's."""
+    from chess_deep_q_b200.train import FusedAdam, GraphedDQNStep, PARAM_ORDER
+    s_, ns, r, d = _golden_batch(oracle, eval_golden, train_golden)
+    to_dev = cdq.board_utils.to_device
+    p, pt = oracle.init_params(42, 2.0), oracle.init_params(43, 2.0)
+    runs = []
+    for split in (0, 1):
+        old = cdq._lib.set_option("train_split_optimizer", split)
+        try:
+            q, t = _net(cdq, p), _net(cdq, pt)
+            opt = FusedAdam(q)
+            step = GraphedDQNStep(q, t, opt, batch=len(s_))
+            step.load(to_dev(s_), to_dev(ns), torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda())
+            losses = []
+            for it in range(5):
+                losses.append(float(step.run().item()))
+                if it == 2:
+                    t.load_state_dict(q.state_dict())           # update_target_network between replays
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                v = q.forward_packed(to_dev(s_[:16])).cpu().numpy()     # eager inference sees the step's own repack
+            runs.append((losses, {k: x.detach().clone() for k, x in q.state_dict().items()}, opt.exp_avg.clone(), opt.step_count, v))
+        finally:
+            cdq._lib.set_option("train_split_optimizer", old)
+    (la, pa, ma, sa, va), (lb, pb, mb, sb, vb) = runs
+    assert sa == sb == 5
+    assert la == pytest.approx(lb, rel=1e-5)
+    for k in PARAM_ORDER:
+        assert float((pa[k] - pb[k]).abs().max()) <= 1e-6, k
+    assert float((ma - mb).abs().max()) <= 1e-6 * float(ma.abs().max()) + 1e-12
+    assert np.abs(va - vb).max() <= 1e-6
+
+
 def test_multi_gpu_fused_dp_step_matches_single_gpu():
     """W ranks x 1/W of a batch (even, uneven and ragged shards) through the one-kernel reduce-scatter + Adam +
     all-gather: the reduced GRADIENT (lr = 0) against the rank-ordered sum of the shard gradients (<= 1e-5) and
