@@ -376,7 +376,8 @@ def test_leaf_eval_matches_mcts_semantics(cdq, oracle, eval_golden):
 
 
 def test_full_size_properties_1m(cdq, oracle):
-    """BASELINE config[1] size (1M positions): size-independent properties + a sampled oracle check."""
+    """BASELINE config[1] size (1M positions): size-independent properties, the handcrafted score against the oracle
+    on every position, the network on a 20 000-position sample."""
     n = 1 << 20
     d = _dev_playouts(cdq, n, seed=42)
     net, p = _make_net(cdq, oracle, 2.0)
@@ -399,6 +400,13 @@ def test_full_size_properties_1m(cdq, oracle):
     assert np.array_equal(_np(out["score"])[idx], score_ref)
     assert np.array_equal(_np(out["flags"]).view(np.uint32)[idx] & 0xFFFF, flags_ref & 0xFFFF)
     assert np.abs(_np(out["leaf"])[idx] - leaf_ref).max() <= 1e-3
+    # (3b) the handcrafted half against the C oracle on ALL 1 048 576 positions: 24 integer terms, fp64 score, flags
+    all_boards = _np(d).view(np.uint64).reshape(-1).view(oracle.BOARD_DTYPE)
+    t_ref, s_ref, f_ref = oracle.evaluate(all_boards, nthreads=0)
+    terms, score_all, flags_all = _eval_gpu(cdq, d)
+    assert np.array_equal(terms, t_ref)
+    assert np.array_equal(score_all, s_ref) and np.array_equal(_np(out["score"]), s_ref)
+    assert np.array_equal(flags_all & 0xFFFF, f_ref & 0xFFFF)
     # (4) ranges
     assert float(out["leaf"].abs().max()) <= 1.0
     assert bool(torch.isfinite(out["score"]).all())
