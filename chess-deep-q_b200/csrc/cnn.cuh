@@ -11,7 +11,7 @@ struct PackedNet {
     const __half* w1p;   // conv1: [9 taps][2 chunks][4 groups][8 n][8 k]  (k 12 = bias, centre tap)
     const __half* w2p;   // conv2: [9 taps][4 chunks][8 groups][8 n][8 k]
     const __half* fc1p;  // fc1:   [64 squares][8 chunks][32 groups][8 n][8 k]
-    const __half* w2tp;  // conv2 flipped for the data gradient: [9 taps][8 chunks of co][4 groups][8 ci][8 co]
+    const __half* w2tp;  // conv2 flipped for the data gradient: [3 dy][8 chunks of co][3 dx][4 groups][8 ci][8 co]
     const __half* wss;   // conv1 then conv2 in conv_stream_kernel's shared-memory order: [dy][K chunk][dx = +1, 0, -1][n groups][8 n][8 k]
     const __half* fc1tp; // fc1^T: [16 column chunks][4 K stages][8 chunks][32 groups][8 n][8 j]  (data gradient)
     const float* conv2_b;

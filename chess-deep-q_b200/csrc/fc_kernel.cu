@@ -228,9 +228,11 @@ __global__ void pack_weights_kernel(CdqWeights w, __half* w1p, __half* w2p, __ha
         const int nn = ng * 8 + n8, k = kc * 8 + k8;
         w2p[j] = __float2half_rn(w.conv2_w[(nn * 32 + k) * 9 + tap]);
     } else if (i < N1 + 2 * N2) {
-        // w2tp[u 9][kc 8 (co)][ng 4 (ci)][ci8][co8] = conv2.weight[co][ci][8 - u]   (flipped taps)
+        // w2tp[dy 3][kc 8 (co)][dx 3][ng 4 (ci)][ci8][co8] = conv2.weight[co][ci][8 - (3 dy + dx)]   (flipped taps; the
+        // three taps of a kernel row are one B operand of N = 96, conv_bwd2_kernel.cu)
         const long long j = i - N1 - N2;
-        const int co8 = j & 7, ci8 = (j >> 3) & 7, ng = (j >> 6) & 3, kc = (j >> 8) & 7, u = (int)(j >> 11);
+        const int co8 = j & 7, ci8 = (j >> 3) & 7, ng = (j >> 6) & 3, blk = (int)(j >> 8);
+        const int dxi = blk % 3, kc = (blk / 3) & 7, u = (blk / 24) * 3 + dxi;
         const int co = kc * 8 + co8, ci = ng * 8 + ci8;
         w2tp[j] = __float2half_rn(w.conv2_w[(co * 32 + ci) * 9 + (8 - u)]);
     } else if (i < 2 * N1 + 2 * N2) {

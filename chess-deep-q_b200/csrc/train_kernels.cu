@@ -232,7 +232,11 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * 108 / 4; i += C1W_THREADS)
+#ifndef CB2_NO_ATOM
         atomicAdd(reinterpret_cast<float4*>(g_w) + i, reinterpret_cast<const float4*>(out)[i]);
+#else
+        if (out[4 * i] == 12345.f) g_w[i] = 0.f;
+#endif
     if (threadIdx.x < 32) {
         float v = 0.f;
         for (int w = 0; w < C1W_WARPS; w++) v += c1w_smem[w * (C1W_ROWS * 32) + (C1W_ROWS - 1) * 32 + threadIdx.x];
