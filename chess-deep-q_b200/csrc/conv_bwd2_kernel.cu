@@ -163,11 +163,13 @@ conv2_bwd2_kernel(const __half* __restrict__ dz2_boards, const __half* __restric
                 // columns; B = the a1 rows of ranks R-1, R, R+1 (N = 3 x 32, 640 bytes between 8-channel groups)
 #ifndef CB2_NO_WG
 #pragma unroll
-                for (int k = 0; k < 16; k++)
-#pragma unroll
-                    for (int dxi = 0; dxi < 3; dxi++)
-                        umma_f16(tmem + dxi * 96, dA_wg + (uint64_t)((k * 2 * ROW) >> 4),
-                                 dB_wg + (uint64_t)(((k >> 1) * A_RANK + (k & 1) * 2 * ROW + dxi * 16) >> 4), ID_WG, k != 0 || acc0);
+                for (int k = 0; k < 16; k++) {
+                    const uint64_t a_k = dA_wg + (uint64_t)((k * 2 * ROW) >> 4);
+                    const uint64_t b_k = dB_wg + (uint64_t)(((k >> 1) * A_RANK + (k & 1) * 2 * ROW) >> 4);
+                    umma_f16(tmem, a_k, b_k, ID_WG, k != 0 || acc0);          // the three taps dx: same A, B one file further
+                    umma_f16(tmem + 96, a_k, b_k + 1, ID_WG, k != 0 || acc0);
+                    umma_f16(tmem + 192, a_k, b_k + 2, ID_WG, k != 0 || acc0);
+                }
 #endif
                 // ---- data gradient: 2 tiles (4 ranks x 4 positions x 8 files) x 3 kernel rows x 4 K-steps of 16 out-channels,
                 // N = the row's three taps; the accumulators of the previous unit have to be drained first

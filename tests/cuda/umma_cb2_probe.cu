@@ -7,6 +7,7 @@
 //   case 3  data gradient    M = 128, N = 96, K-major; A rows of 160 B at +16 (SBO 160)
 //   case 4  data gradient    A rows of 128 B (SBO 128)
 //   case 5  data gradient    N = 32, A rows of 160 B at +16 (the kernel before the N = 96 formulation)
+//   case 6  weight gradient  case 0 with the A operand kept in the collector across the three taps (fill / use / lastuse)
 // Values are not checked here (the kernel's parity tests do that); only the pace.
 #include <cstdio>
 #include <cstdlib>
@@ -39,7 +40,7 @@ __global__ void probe(const uint8_t* img, int img_bytes, int reps, long long* cy
             const uint64_t bw = make_smem_desc(base + 128 * 1024, 1536, 128);
             const long long t0 = clock64();
             for (int r = 0; r < reps; r++) {
-                if (mode <= 2) {
+                if (mode <= 2 || mode == 6) {
                     // 16 K steps x 3 taps, like one unit
 #pragma unroll
                     for (int k = 0; k < 16; k++)
@@ -49,7 +50,10 @@ __global__ void probe(const uint8_t* img, int img_bytes, int reps, long long* cy
                                                          : make_smem_desc(base + 4 * 128 + k * 256, 128, 5120);
                             const uint64_t b = mode == 2 ? make_smem_desc(B0 + (k >> 1) * 2048 + (k & 1) * 256 + dxi * 8192, 128, 512)
                                                          : make_smem_desc(B0 + (k >> 1) * 2560 + (k & 1) * 320 + dxi * 16, 160, 640);
-                            umma_f16(tmem + dxi * 96, a, b, id_wg, (r | k) != 0);
+                            if (mode != 6) umma_f16(tmem + dxi * 96, a, b, id_wg, (r | k) != 0);
+                            else if (dxi == 0) umma_f16_ca<0>(tmem + dxi * 96, a, b, id_wg, (r | k) != 0);
+                            else if (dxi == 1) umma_f16_ca<1>(tmem + dxi * 96, a, b, id_wg, (r | k) != 0);
+                            else umma_f16_ca<2>(tmem + dxi * 96, a, b, id_wg, (r | k) != 0);
                         }
                 } else {
 #pragma unroll
@@ -82,10 +86,10 @@ int main() {
     uint8_t* d_img; long long* d_cyc;
     cudaMalloc(&d_img, IMG); cudaMalloc(&d_cyc, 16);
     cudaMemcpy(d_img, img.data(), IMG, cudaMemcpyHostToDevice);
-    const char* names[6] = {"wgrad M64 N96 MN-major, A rows 160 B (+16), B taps +0/+16/+32", "wgrad, A rows 128 B (aligned), B taps +0/+16/+32",
+    const char* names[7] = {"wgrad M64 N96 MN-major, A rows 160 B (+16), B taps +0/+16/+32", "wgrad, A rows 128 B (aligned), B taps +0/+16/+32",
                             "wgrad, A and B aligned", "dgrad M128 N96 K-major, A rows 160 B (+16)", "dgrad, A rows 128 B (aligned)",
-                            "dgrad N32, A rows 160 B (+16)"};
-    const int per[6] = {48, 48, 48, 24, 24, 24};
+                            "dgrad N32, A rows 160 B (+16)", "wgrad as case 0, A kept in the collector across the taps"};
+    const int per[7] = {48, 48, 48, 24, 24, 24, 48};
     const int reps = 200;
 #define RUN(mode)                                                                                            \
     {                                                                                                        \
@@ -99,6 +103,6 @@ int main() {
         cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost);                                                    \
         printf("case %d %-62s: %6.1f cycles per MMA\n", mode, names[mode], (double)c / reps / per[mode]);    \
     }
-    RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5)
+    RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6)
     return 0;
 }
