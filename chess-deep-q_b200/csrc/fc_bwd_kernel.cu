@@ -66,11 +66,16 @@ int launch_relu_mask(const __half* act2, long long n, unsigned* mask, cudaStream
 // ------------------------------------------------------------------------------------------ dgrad
 constexpr int DG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
 constexpr int DG_B_BYTES = 256 * 64 * 2;        // 32 KB: W1^T, 256 columns x 64 outputs
+// What sets the pace is the epilogue (build variants under ncu, profiles/r2c_dgrad_notes.txt: 23.4 us; without the epilogue
+// 12.8; with the epilogue but without its bulk copies 15.2; without the W1^T stream 23.0): 128 bulk copies of 640 bytes per
+// chunk, and the staging buffer could not be rewritten before they had read it.  The chunk is therefore staged in two halves
+// of its channel chunks, each in its own buffer: the copies of one half run under the conversion of the next.
 constexpr int DG_STAGES = 2;
 constexpr int DG_OFF_B = DG_A_BYTES;
-constexpr int DG_OFF_OUT = DG_OFF_B + DG_STAGES * DG_B_BYTES;   // one chunk of the output, staged as the 128 board blocks it becomes
-constexpr int DG_GROUP_STRIDE = 4 * 640 + 16;                   // [group of 4 positions][4 channel chunks][4 pos][10 files][16 B] (+16: bank spread)
-constexpr int DG_OUT_BYTES = 32 * DG_GROUP_STRIDE;
+constexpr int DG_OFF_OUT = DG_OFF_B + DG_STAGES * DG_B_BYTES;   // two buffers, each half a chunk of the output staged as the 64 board blocks it becomes
+constexpr int DG_GROUP_STRIDE = 2 * 640 + 16;                   // [group of 4 positions][2 channel chunks][4 pos][10 files][16 B] (+16: bank spread)
+constexpr int DG_HALF_BYTES = 32 * DG_GROUP_STRIDE;
+constexpr int DG_OUT_BYTES = 2 * DG_HALF_BYTES;
 constexpr int DG_OFF_BAR = DG_OFF_OUT + DG_OUT_BYTES;
 constexpr int DG_SMEM = DG_OFF_BAR + 128;
 constexpr int DG_THREADS = 192;
@@ -79,8 +84,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
 fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ relu_mask, const __half* __restrict__ fc1tp,
                  long long n, __half* __restrict__ dz2_boards) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + DG_OFF_BAR);   // [4]
-    uint64_t* empty = full + DG_STAGES;                                // [4]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + DG_OFF_BAR);   // [DG_STAGES]
+    uint64_t* empty = full + DG_STAGES;                                // [DG_STAGES]
     uint64_t* a_full = empty + DG_STAGES;
     uint64_t* a_empty = a_full + 1;
     uint64_t* acc_full = a_empty + 1;                                  // [2]
@@ -121,9 +126,13 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
                 for (int s = 0; s < 4; s++, it++) {
                     const int st = it % DG_STAGES;
                     mbar_wait(empty + st, ((it / DG_STAGES) & 1) ^ 1);
+#ifdef DG_NO_B
+                    mbar_arrive(full + st);
+#else
                     mbar_arrive_expect_tx(full + st, DG_B_BYTES);
                     bulk_g2s(smem + DG_OFF_B + st * DG_B_BYTES,
                              reinterpret_cast<const uint8_t*>(fc1tp) + ((long long)(ck * 4 + s) << 15), DG_B_BYTES, full + st);
+#endif
                 }
             }
         }
@@ -177,57 +186,84 @@ fc1_dgrad_kernel(const __half* __restrict__ dz1h, const unsigned* __restrict__ r
             if (gch + 1 < g_hi) mload(mnext, gch + 1);
             mbar_wait(acc_full + ab, (chunk_no >> 1) & 1);
             tc_fence_after();
-            // the TMEM load of block p + 1 is in flight while block p is converted and staged
-            uint32_t vv[2][32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256, vv[0]);
+            // Two passes over the accumulator, one per HALF of the 32 channels of a block (channel chunks 2 hh, 2 hh + 1).
+            // Block p is FILE p of the chunk's rank.  The pieces are staged in shared memory exactly as the board blocks
+            // they become -- [group of 4 positions][channel chunk][4 positions][10 files][16 B], 640 contiguous bytes per
+            // (group, channel chunk) both here and in global memory -- and leave as 64 bulk copies of 640 bytes per pass.
+            // (Written straight from the accumulator rows every warp store put 16 bytes on each of 32 different 128-byte
+            // lines: 22 of 39 us; as 64-byte runs through per-thread stores still 17 of 28.)
+            const bool live = (tile << 7) + pr < n;         // rows beyond n must be ZERO boards: conv2's backward contracts whole units
+#ifdef DG_NO_EPI
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + ab);
+            chunk_no++;
+            continue;
+#endif
+#pragma unroll 1
+            for (int hh = 0; hh < 2; hh++) {
+                // buffer hh is free: every thread finished copying it out before the barrier of the round in between
+                // four blocks per TMEM round trip (tcgen05.wait::ld waits for every outstanding load, and a round trip per
+                // block -- sixteen per chunk -- was most of the epilogue's time): blocks 4..7 are in flight while 0..3 are
+                // converted and staged
+                uint32_t vv[2][4][16];
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + hh * 16;
 #pragma unroll
-            for (int p = 0; p < 8; p++) {
-                tmem_ld_wait();
-                if (p + 1 < 8) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * 256 + (p + 1) * 32, vv[(p + 1) & 1]);
-                uint32_t (&v)[32] = vv[p & 1];
-                // Block p is FILE p of the chunk's rank, 32 channels = four 16-byte pieces.  They are staged in shared memory
-                // exactly as the board blocks they become -- [group of 4 positions][channel chunk][4 positions][10 files][16 B],
-                // 640 contiguous bytes per (group, channel chunk) both here and in global memory -- and leave as 128 bulk
-                // copies of 640 bytes per chunk.  (Written straight from the accumulator rows every warp store put 16 bytes
-                // on each of 32 different 128-byte lines: 22 of 39 us; as 64-byte runs through per-thread stores still 17 of 28.)
-                uint8_t* sdst = smem + DG_OFF_OUT + (pr >> 2) * DG_GROUP_STRIDE + (pr & 3) * 160 + (p + 1) * 16;
-                const bool live = (tile << 7) + pr < n;         // rows beyond n must be ZERO boards: conv2's backward contracts whole units
+                for (int p = 0; p < 4; p++) tmem_ld16(tbase + p * 32, vv[0][p]);
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    unsigned w[4];
+                for (int ph4 = 0; ph4 < 2; ph4++) {
+                    tmem_ld_wait();
+                    if (ph4 == 0) {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        // the value stays scaled (undone downstream)
-                        const __half2 h2 = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * e]), __uint_as_float(v[g * 8 + 2 * e + 1]));
-                        const unsigned two = live ? mcur[p] >> (g * 8 + 2 * e) : 0u;
-                        w[e] = *reinterpret_cast<const unsigned*>(&h2) & ((two & 1u ? 0xffffu : 0u) | (two & 2u ? 0xffff0000u : 0u));
+                        for (int p = 0; p < 4; p++) tmem_ld16(tbase + (4 + p) * 32, vv[1][p]);
                     }
-                    *reinterpret_cast<uint4*>(sdst + g * 640) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+                    for (int p4 = 0; p4 < 4; p4++) {
+                        const int p = ph4 * 4 + p4;
+                        uint32_t (&v)[16] = vv[ph4][p4];
+                        uint8_t* sdst = smem + DG_OFF_OUT + hh * DG_HALF_BYTES + (pr >> 2) * DG_GROUP_STRIDE + (pr & 3) * 160 + (p + 1) * 16;
+                        const unsigned mbits = live ? mcur[p] >> (hh * 16) : 0u;
+#pragma unroll
+                        for (int g = 0; g < 2; g++) {
+                            unsigned w[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                // the value stays scaled (undone downstream)
+                                const __half2 h2 = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * e]), __uint_as_float(v[g * 8 + 2 * e + 1]));
+                                const unsigned two = mbits >> (g * 8 + 2 * e);
+                                w[e] = *reinterpret_cast<const unsigned*>(&h2) & ((two & 1u ? 0xffffu : 0u) | (two & 2u ? 0xffff0000u : 0u));
+                            }
+                            *reinterpret_cast<uint4*>(sdst + g * 640) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
                 }
-            }
-            {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + ab);
-                chunk_no++;
-                // ---- copy-out: thread = (group of 4 positions, channel chunk): one 640-byte block [4 pos][10 files] of the unit
-                fence_proxy_async();                                        // staged with generic stores, read by the bulk copies
-                asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps: chunk staged
+                if (hh == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + ab);
+                }
+                // ---- copy-out with plain 16-byte stores, 512 contiguous bytes per warp instruction: a warp takes 16 of the
+                // half's 64 blocks (group of 4 positions, channel chunk), 640 bytes = 40 pieces each.  (As 64 bulk copies of
+                // 640 bytes per half the copy engine set the kernel's pace: 23.4 us, 16.8 without the copies.)
+                asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps: half chunk staged
                 {
-                    const int grp = pr >> 2, gg = pr & 3;
                     const int rank = ck >> 1, chalf = ck & 1;
-                    if ((tile << 7) + grp * 4 < n) {
-                        uint8_t* dst = reinterpret_cast<uint8_t*>(dz2_boards) + (tile * 32 + grp) * 51200 + (chalf * 4 + gg) * 6400 + (rank + 1) * 640;
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(dst), "r"(smem_u32(smem + DG_OFF_OUT + grp * DG_GROUP_STRIDE + gg * 640)), "r"(640) : "memory");
+                    uint8_t* gbase = reinterpret_cast<uint8_t*>(dz2_boards) + (chalf * 4 + hh * 2) * 6400 + (rank + 1) * 640;
+                    const uint8_t* sbase = smem + DG_OFF_OUT + hh * DG_HALF_BYTES;
+#pragma unroll 4
+                    for (int bi = 0; bi < 16; bi++) {
+                        const int blk = q * 16 + bi, grp = blk >> 1, gl = blk & 1;
+                        if ((tile << 7) + grp * 4 < n) {
+                            const uint8_t* src = sbase + grp * DG_GROUP_STRIDE + gl * 640;
+                            uint8_t* dst = gbase + (tile * 32 + grp) * 51200 + gl * 6400;
+                            reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(src)[lane];
+                            if (lane < 8) reinterpret_cast<uint4*>(dst)[32 + lane] = reinterpret_cast<const uint4*>(src)[32 + lane];
+                        }
                     }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the copies have read the staging buffer
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");             // staging buffer free for the next chunk
             }
+            chunk_no++;
         }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");           // all board blocks written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
