@@ -218,11 +218,11 @@ adam_single_kernel(float* __restrict__ params, float* __restrict__ grads, float*
     }
     __syncthreads();                                     // every thread of this CTA has read d_step / grid_bar[1]
     if (threadIdx.x == 0) {
-        if (atomicInc(grid_bar, gridDim.x - 1) == gridDim.x - 1) atomicExch(grid_bar + 3, gen);
-        if (blockIdx.x == 0) {
-            while (*reinterpret_cast<volatile unsigned*>(grid_bar + 3) != gen) { }   // co-resident CTAs of this cooperative launch
+        // last CTA out bumps the counters: every other CTA has arrived, i.e. has read them (no CTA waits for another one)
+        if (atomicInc(grid_bar, gridDim.x - 1) == gridDim.x - 1) {
             if (bump) *d_step = step;
             grid_bar[1] = gen;
+            grid_bar[3] = gen;
         }
     }
 }
