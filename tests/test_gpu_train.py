@@ -443,7 +443,9 @@ def test_split_optimizer_schedule_gives_the_same_step(cdq, oracle, eval_golden, 
     for k in PARAM_ORDER:
         assert float((pa[k] - pb[k]).abs().max()) <= 1e-6, k
     assert float((ma - mb).abs().max()) <= 1e-6 * float(ma.abs().max()) + 1e-12
-    assert np.abs(va - vb).max() <= 1e-6
+    # the gradients are summed with fp32 atomics (order-dependent last bits): parameters that differ by 1e-7 can round to
+    # neighbouring fp16 tile values, which moves an output by a few 1e-6
+    assert np.abs(va - vb).max() <= 2e-5
 
 
 def test_multi_gpu_fused_dp_step_matches_single_gpu():
