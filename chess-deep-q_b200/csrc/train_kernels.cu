@@ -88,8 +88,9 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
 
 // conv1 weight + bias gradient.  The input is one-hot, so the GEMM collapses to a gather:
 // dW1[co][p][tap] += dz1c[b][sq][co] for every piece p standing on square sq + tap.  A board is handled by
-// THREE warps that split the PIECE TYPES (white pawns + black rooks and queen / black pawns + white rooks and
-// queen / all knights, bishops and kings: 11 + 11 + 10 pieces on a full board), lane = output channel, and a
+// FOUR warps that split the PIECE TYPES (white pawns / black pawns / the other white pieces / the other black pieces:
+// 8 + 8 + 8 + 8 pieces on a full board; three warps with 11 + 11 + 10 until round 2c -- the gather runs at the pace of a
+// board's busiest warp and at 44 % of the issue slots, so more and shorter warps pay twice), lane = output channel, and a
 // lane's accumulators (its types x 9 taps) live in registers.  Per piece a warp pays the bit scan and the
 // address arithmetic once and then reads the nine output squares around the piece -- conflict-free
 // shared-memory reads (the previous split, one kernel row per warp, made every warp walk ALL pieces: three
@@ -101,9 +102,9 @@ head_bwd_kernel(const float* __restrict__ q, const float* __restrict__ qn, const
 // reductions: same-line atomics serialise in L2, so what matters is the number of transactions per 128-byte
 // line (one scalar atomic per cell and CTA with the channel as the fast index put 32 per CTA on each line
 // and cost more than the gather itself).
-constexpr int C1W_SLOTS = 6, C1W_WARPS = 3 * C1W_SLOTS, C1W_THREADS = 32 * C1W_WARPS;
+constexpr int C1W_SLOTS = 6, C1W_SUBS = 4, C1W_WARPS = C1W_SUBS * C1W_SLOTS, C1W_THREADS = 32 * C1W_WARPS;
 constexpr int C1W_STAGE_BYTES = C1W_SLOTS * 2 * 8192;             // [slot][2][64 squares][32 channels] fp32
-constexpr int C1W_ROWS = 6 * 9 + 1;                               // per warp: up to 6 types x 9 taps, + the bias row
+constexpr int C1W_ROWS = 5 * 9 + 1;                               // per warp: up to 5 types x 9 taps, + the bias row
 constexpr int C1W_RED_BYTES = C1W_WARPS * C1W_ROWS * 32 * 4;      // reduction buffer, aliases the staging buffers
 constexpr int C1W_OFF_BOARD = C1W_RED_BYTES > C1W_STAGE_BYTES ? C1W_RED_BYTES : C1W_STAGE_BYTES;   // [slot][2][8 bitboards]
 constexpr int C1W_OFF_OUT = C1W_OFF_BOARD + C1W_SLOTS * 2 * 64;   // [32 co][108] summed over the slots
@@ -115,21 +116,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-// piece types (channel = type + 6 * black, board_utils.py:17-30) of the three warp roles
-__host__ __device__ constexpr int c1w_ntypes(int g) { return g == 2 ? 6 : 3; }
-__host__ __device__ constexpr int c1w_type(int g, int i) {
-    return g == 0 ? (i == 0 ? 0 : i == 1 ? 9 : 10)
-         : g == 1 ? (i == 0 ? 6 : i == 1 ? 3 : 4)
-                  : (i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 5 : i == 3 ? 7 : i == 4 ? 8 : 11);
-}
-__constant__ int c1w_group_of[12] = {0, 2, 2, 1, 1, 2, 1, 2, 2, 0, 0, 2};
-__constant__ int c1w_local_of[12] = {0, 0, 1, 1, 2, 2, 0, 3, 4, 1, 2, 5};
+// piece types (channel = type + 6 * black; pawn, knight, bishop, rook, queen, king: board_utils.py:17-30) of the four warp roles
+__host__ __device__ constexpr int c1w_ntypes(int g) { return g < 2 ? 1 : 5; }
+__host__ __device__ constexpr int c1w_type(int g, int i) { return g == 0 ? 0 : g == 1 ? 6 : g == 2 ? 1 + i : 7 + i; }
+__constant__ int c1w_group_of[12] = {0, 2, 2, 2, 2, 2, 1, 3, 3, 3, 3, 3};
+__constant__ int c1w_local_of[12] = {0, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 4};
 
 template <int G>
 __device__ __forceinline__ void c1w_gather(const CdqBoard* __restrict__ boards, const float* __restrict__ dz1c, long long n,
                                            float* c1w_smem, uint8_t* c1w_raw, int slot, int sub, int lane, int warp) {
     constexpr int NT = c1w_ntypes(G);
-    const int t96 = sub * 32 + lane;
+    const int t128 = sub * 32 + lane;
     float acc[NT][9];
 #pragma unroll
     for (int p = 0; p < NT; p++)
@@ -139,16 +136,16 @@ __device__ __forceinline__ void c1w_gather(const CdqBoard* __restrict__ boards, 
     float* stage0 = c1w_smem + slot * 4096;             // two buffers of [64 squares][32 channels]
     unsigned long long* board0 = reinterpret_cast<unsigned long long*>(c1w_raw + C1W_OFF_BOARD) + slot * 16;
     const long long stride = (long long)gridDim.x * C1W_SLOTS;
-    auto fetch = [&](long long bb, int buf) {           // this thread's share of board bb: 512 16-byte pieces over 96 threads
+    auto fetch = [&](long long bb, int buf) {           // this thread's share of board bb: 512 16-byte pieces over 128 threads
         if (bb < n) {
             const float* src = dz1c + bb * 2048;
             float* dst = stage0 + buf * 2048;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const int u = i * 96 + t96;
-                if (u < 512) cp_async16(dst + 4 * u, src + 4 * u);
+            for (int i = 0; i < 4; i++) {
+                const int u = i * 128 + t128;
+                cp_async16(dst + 4 * u, src + 4 * u);
             }
-            if (t96 < 8) cp_async8(board0 + buf * 8 + t96, reinterpret_cast<const unsigned long long*>(boards) + bb * 9 + t96);
+            if (t128 < 8) cp_async8(board0 + buf * 8 + t128, reinterpret_cast<const unsigned long long*>(boards) + bb * 9 + t128);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -157,17 +154,16 @@ __device__ __forceinline__ void c1w_gather(const CdqBoard* __restrict__ boards, 
     for (int it = 0; b < n; b += stride, it++) {
         const int buf = it & 1;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("bar.sync %0, 96;" ::"r"(slot + 1) : "memory");   // all three warps: copies landed, previous board done
+        asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory");  // all four warps: copies landed, previous board done
         fetch(b + stride, buf ^ 1);
         const float* stage = stage0 + buf * 2048;
         const unsigned long long* r = board0 + buf * 8;
-        {   // bias: every thread sums a third of the squares of its channel
+        {   // bias: every thread sums a quarter of the squares of its channel
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 22; i += 2) {
-                const int q0 = sub + 3 * i, q1 = sub + 3 * (i + 1);
-                if (q0 < 64) s0 += stage[q0 * 32 + lane];
-                if (q1 < 64) s1 += stage[q1 * 32 + lane];
+            for (int i = 0; i < 16; i += 2) {
+                s0 += stage[(sub + 4 * i) * 32 + lane];
+                s1 += stage[(sub + 4 * i + 4) * 32 + lane];
             }
             bias += s0 + s1;
         }
@@ -215,10 +211,11 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
     extern __shared__ __align__(16) uint8_t c1w_raw[];
     float* c1w_smem = reinterpret_cast<float*>(c1w_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = warp / 3, sub = warp % 3;
+    const int slot = warp >> 2, sub = warp & 3;
     if (sub == 0) c1w_gather<0>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
     else if (sub == 1) c1w_gather<1>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
-    else c1w_gather<2>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
+    else if (sub == 2) c1w_gather<2>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
+    else c1w_gather<3>(boards, dz1c, n, c1w_smem, c1w_raw, slot, sub, lane, warp);
     __syncthreads();
     // ---- sum the slots (channel = fast index: conflict free) into PyTorch order, then coalesced 16-byte reductions
     float* out = reinterpret_cast<float*>(c1w_raw + C1W_OFF_OUT);
@@ -227,7 +224,7 @@ conv1_wgrad_kernel(const CdqBoard* __restrict__ boards, const float* __restrict_
         const int g = c1w_group_of[p], row = c1w_local_of[p] * 9 + tap;
         float v = 0.f;
 #pragma unroll
-        for (int sl = 0; sl < C1W_SLOTS; sl++) v += c1w_smem[(sl * 3 + g) * (C1W_ROWS * 32) + row * 32 + co];
+        for (int sl = 0; sl < C1W_SLOTS; sl++) v += c1w_smem[(sl * C1W_SUBS + g) * (C1W_ROWS * 32) + row * 32 + co];
         out[co * 108 + cell] = v;                                                 // conv1.weight[co][p][tap]
     }
     __syncthreads();
@@ -520,7 +517,7 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
         // ---- conv1: weight + bias gradient by scatter over the one-hot input
         ProfileScope ps(KK_CONV1_WGRAD, st);
         once_per_device(ONCE_CONV1_WGRAD, [] { cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1W_SMEM); });
-        const long long want = (n + C1W_SLOTS - 1) / C1W_SLOTS;     // one CTA of 18 warps per SM
+        const long long want = (n + C1W_SLOTS - 1) / C1W_SLOTS;     // one CTA of 24 warps per SM
         const unsigned blocks = (unsigned)(want < device_sm_count() ? want : device_sm_count());
         conv1_wgrad_kernel<<<blocks, C1W_THREADS, C1W_SMEM, st>>>(states, ws.dz1c, n, (float*)g.conv1_w, (float*)g.conv1_b);
         count_launch();
