@@ -15,7 +15,8 @@
 //                     dZ2[pos][sq][ch] = ReLU'(act2) * sum_j dz1[pos][j] W1[j][ch*64+sq], written (still
 //                     scaled, fp16) as the zero-bordered board blocks conv_bwd2_kernel.cu consumes
 //                     M = 128 positions, N = 256 (the 8 squares of one board rank x 32 channels), K = 256; W1^T tiles
-//                     streamed by bulk copies, the masked chunk leaves as 128 bulk copies of 640 bytes
+//                     streamed by bulk copies, the masked chunk is staged as the board blocks it becomes and copied out with
+//                     coalesced 16-byte stores
 //  relu_mask_kernel   one bit per ReLU(conv2) output for the above (side stream, under the fc forward)
 //  fc1_wgrad_kernel   dW1[j][ch*64+sq] += sum_pos dz1[pos][j] act2[pos][sq][ch]
 //                     M = 2 x 128 outputs, N = 128 (16 squares x 8 channels), K = positions (split over CTAs)
@@ -68,8 +69,9 @@ constexpr int DG_A_BYTES = 128 * 256 * 2;       // 64 KB: dz1h tile
 constexpr int DG_B_BYTES = 256 * 64 * 2;        // 32 KB: W1^T, 256 columns x 64 outputs
 // What sets the pace is the epilogue (build variants under ncu, profiles/r2c_dgrad_notes.txt: 23.4 us; without the epilogue
 // 12.8; with the epilogue but without its bulk copies 15.2; without the W1^T stream 23.0): 128 bulk copies of 640 bytes per
-// chunk, and the staging buffer could not be rewritten before they had read it.  The chunk is therefore staged in two halves
-// of its channel chunks, each in its own buffer: the copies of one half run under the conversion of the next.
+// chunk, at the copy engine's rate for such small copies (a second staging buffer, so that they ran under the conversion of the
+// next half, changed nothing).  The chunk is staged in two halves of its channel chunks, each in its own buffer, and the four
+// epilogue warps copy a half out themselves with plain 16-byte stores, 512 contiguous bytes per instruction.
 constexpr int DG_STAGES = 2;
 constexpr int DG_OFF_B = DG_A_BYTES;
 constexpr int DG_OFF_OUT = DG_OFF_B + DG_STAGES * DG_B_BYTES;   // two buffers, each half a chunk of the output staged as the 64 board blocks it becomes
