@@ -241,27 +241,16 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
         else if (part == 2) { hi = FC1_LO; lo2 = FC1_HI; hi2 = all_chunks; }
         const long long n_chunks = (hi - lo) + (hi2 - lo2);
         int grid = (int)((n_chunks + DP_THREADS - 1) / DP_THREADS);
-        // block 0 waits for the arrival of all others, so the grid must be co-resident: cooperative launch,
-        // at most what the occupancy calculator says fits (4 CTAs of 512 threads per SM at 32 registers)
-        static std::atomic<int> per_sm_cached{0};      // a property of the kernel and the architecture (sm_100 only)
-        int per_sm = per_sm_cached.load(std::memory_order_relaxed);
-        if (!per_sm) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_single_kernel, DP_THREADS, 0) != cudaSuccess || per_sm < 1)
-                per_sm = 1;
-            per_sm_cached.store(per_sm, std::memory_order_relaxed);
-        }
-        if (grid > sms * per_sm) grid = sms * per_sm;
-        // fc1.weight's launch runs UNDER conv2's backward (cdq_train_step): one CTA per SM is co-resident with that kernel's
-        // CTAs, a grid that needs four per SM would wait for it to drain (a cooperative launch starts only when it fits)
-        if (part == 1 && grid > sms) grid = sms;
+        // no CTA waits for another one (the last to arrive bumps the counters), so this is a plain launch: one 16-byte chunk per
+        // thread, CTAs start wherever an SM has room -- also next to the CTAs of conv2's backward when fc1.weight's launch
+        // runs under it (cdq_train_step, train_split_optimizer)
         if (grid < 1) grid = 1;
         float* params = peers.params[0];
         float* grads = peers.grads[0];
         ProfileScope ps(KK_ADAM, st);
-        void* args[] = {&params, &grads, &m, &v, &lo, &hi, &lo2, &hi2, (void*)&phase, (void*)&bump, &d_step, &grid_bar, &lr, &b1, &b2, &eps};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void*)adam_single_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
+        adam_single_kernel<<<grid, DP_THREADS, 0, st>>>(params, grads, m, v, lo, hi, lo2, hi2, phase, bump, d_step, grid_bar, lr, b1, b2, eps);
         count_launch();
-        return (int)e;
+        return (int)cudaGetLastError();
     }
     unsigned long long timeout_ns = (unsigned long long)(option(OPT_DP_TIMEOUT_S) > 0 ? option(OPT_DP_TIMEOUT_S) : 1) * 1000000000ull;
     long long lo = 0, hi = all_chunks, lo2 = 0, hi2 = 0;

@@ -439,9 +439,9 @@ int train_fwd_bwd(const CdqNet* net, const CdqNet* target, const CdqWeights& w, 
     // Two schedules for the optimizer (option "train_split_optimizer"):
     //   0  the parameters are repacked at the head of the step and ONE optimizer launch closes it;
     //   1  fc1.weight's optimizer launch and repack follow its weight gradient on the side stream, the rest closes the step and
-    //      the next step starts with the convolution at once.  On one GPU the backward kernels already fill the machine from the
-    //      head to conv1's gradient, so 1 only moves work around (163 against 160 us, profiles/README.md); it is for peer groups,
-    //      where the optimizer kernel waits on NVLink round trips that the convolution backward can cover.
+    //      the next step starts with the convolution at once.  The step is bound by SM-time, so 1 only moves work around: on
+    //      one GPU 0.1467 against 0.1455 ms (0.1482 against 0.1475 with conv2's backward capped at 168 registers so that an
+    //      optimizer CTA fits next to it), on eight GPUs the same span (the second launch keeps its handshake floor).
     const bool split_opt = opt && option(OPT_TRAIN_SPLIT_OPT) != 0;
     if (opt && !split_opt) loss_kind_flags |= CDQ_TRAIN_REPACK;
     if (split_opt) {
