@@ -261,6 +261,8 @@ int launch_dp_adam(const CdqDpPeers& peers, int rank, int world, float* m, float
     if (grid > sms) grid = sms;          // all CTAs must be co-resident: block 0 waits for the others
     if (grid < 1) grid = 1;
     ProfileScope ps(KK_ADAM, st);
+    // cooperative: the CTAs wait for each other.  (A plain launch -- co-residency would hold by construction, one CTA of 512
+    // threads per SM -- gains nothing here: 0.1384 against 0.1372 ms at 2 GPUs; the kernel's start is gated by the peers.)
     void* args[] = {(void*)&peers, &rank, &world, &m, &v, &lo, &hi, &lo2, &hi2, (void*)&phase, (void*)&bump, &d_step, &grid_bar, &lr, &b1, &b2,
                     &eps, &timeout_ns};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)dp_adam_kernel, dim3(grid), dim3(DP_THREADS), args, 0, st);
