@@ -173,12 +173,19 @@ __device__ __forceinline__ void sample_children(const unsigned (&mv)[MOVE_BLOCKS
 // _expand_node (mcts.py:166-194) by one warp: all legal moves of `p` with their tactical weights, lane l owning moves
 // l + 32 j, then select_weighted_moves' draw of `width` children without replacement (same integer arithmetic as
 // sample_children_kernel).  Returns the number of children stored (0 for a finished game).
+//
+// The move list lives in SHARED memory, one per warp.  On the stack it was 368 bytes of local memory per LANE for values that
+// are the same in every lane: with one expansion per (simulation, level) the tree kernel wrote 742 MB of local memory per
+// wave of 1 024 trees (ncu, profiles/r2c_tree_level_summary.txt).  Every lane stores the same value to the same address; the
+// __syncwarp()s keep a lane that still reads the previous list out of the way of the next one.  (has_legal_ep, called for
+// the few positions with an ep square, keeps its list on the stack.)
 __device__ __noinline__ int expand_node(const Forest& f, const Pos& p, int hmc, u64 seed, unsigned* e_move, int* e_n, double* e_q,
-                                        int lane) {
+                                        int lane, MoveList& L) {
     const bool white = p.meta & CDQ_META_TURN_WHITE;
     const Pos wv = white_view(p);
-    MoveList L;
-    list_moves(wv, L);                       // every lane holds the same list; lane l picks moves l, l + 32, ...
+    __syncwarp();
+    list_moves(wv, L);                       // one list per warp; lane l picks moves l, l + 32, ...
+    __syncwarp();
     // Board(fen).is_game_over(): no legal move (checkmate / stalemate), insufficient material, 75-move rule; a board built
     // from a FEN has no history, so no repetition rule here (mcts.py:172-177)
     if (L.n == 0 || insufficient_material(p) || hmc >= 150) return 0;
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(MAXW * 32, MAXW <= 8 ? 2 : 1)
 tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alpha, int max_moves) {
     __shared__ u64 sh_key[MAXW];
     __shared__ int sh_need[MAXW], sh_node[MAXW], sh_new[MAXW];
+    __shared__ MoveList sh_list[MAXW];                   // the expansion's move list of each simulation (warp)
     const int t = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = f.workers, D = f.depth;
     const long long s = (long long)t * W + w;
@@ -285,7 +293,7 @@ tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alp
         node = f.n_count[t] + rank;
         if (node < f.max_nodes) {
             const long long nb = (long long)t * f.max_nodes + node, eb = nb * f.width;
-            const int nchild = expand_node(f, p, hmc, mix64(search_seed ^ key), f.e_move + eb, f.e_n + eb, f.e_q + eb, lane);
+            const int nchild = expand_node(f, p, hmc, mix64(search_seed ^ key), f.e_move + eb, f.e_n + eb, f.e_q + eb, lane, sh_list[w]);
             if (lane == 0) {
                 f.n_key[nb] = key;
                 f.n_nchild[nb] = nchild;
