@@ -233,8 +233,8 @@ struct ListVisitor {
 };
 __device__ __forceinline__ int class_mult(int k) { return (k == MC_PUSH_PROMO || k == MC_CAP_W_PROMO || k == MC_CAP_E_PROMO) ? 4 : 1; }
 
-// `w` must be a white view (white_view(p)).  The only place the list kernels expand gen_side.
-static __device__ __noinline__ void list_moves(const Pos& w, MoveList& L) {
+// `w` must be a white view (white_view(p)).  The only place the list kernels expand gen_side: the classes' target sets.
+static __device__ __noinline__ void list_classes(const Pos& w, MoveList& L) {
     L.occ = w.co[0] | w.co[1];
     L.king_bb = w.K & w.co[1];
     const Props q = make_props(~L.occ);
@@ -242,12 +242,31 @@ static __device__ __noinline__ void list_moves(const Pos& w, MoveList& L) {
     L.ep_sq = 0;
     ListVisitor v(L);
     gen_side<1>(w, q, L.att_opp, v);
+}
+// ... and the enumeration (first[], n), by one thread
+__device__ __forceinline__ void list_moves(const Pos& w, MoveList& L) {
+    list_classes(w, L);
     int n = 0;
 #pragma unroll 1
     for (int k = 0; k < MC_COUNT; k++) { L.first[k] = n; n += popc(L.t[k]) * class_mult(k); }
     L.first[MC_COUNT] = n;
     L.n = n;
     L.ep_legal = L.t[MC_EP] != 0;
+}
+// ... or by a whole warp on ONE list in shared memory (every lane passes the same w): lane k counts class k, a shuffle scan
+// gives first[] -- 27 dependent load / popc / store rounds otherwise, 7 % of the tree kernel's samples
+__device__ __forceinline__ void list_moves_warp(const Pos& w, MoveList& L, int lane) {
+    list_classes(w, L);
+    __syncwarp();
+    int c = lane < MC_COUNT ? popc(L.t[lane]) * class_mult(lane) : 0, incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane < MC_COUNT) L.first[lane] = incl - c;
+    if (lane == MC_COUNT) { L.first[MC_COUNT] = incl; L.n = incl; L.ep_legal = L.t[MC_EP] != 0; }
+    __syncwarp();
 }
 // the r-th move of the list (enumeration order = class order, targets ascending, promotions Q R B N), white-view coordinates
 static __device__ __noinline__ PlainMove pick_from_list(const MoveList& L, int r) {

@@ -184,8 +184,7 @@ __device__ __noinline__ int expand_node(const Forest& f, const Pos& p, int hmc, 
     const bool white = p.meta & CDQ_META_TURN_WHITE;
     const Pos wv = white_view(p);
     __syncwarp();
-    list_moves(wv, L);                       // one list per warp; lane l picks moves l, l + 32, ...
-    __syncwarp();
+    list_moves_warp(wv, L, lane);            // one list per warp; lane l picks moves l, l + 32, ...
     // Board(fen).is_game_over(): no legal move (checkmate / stalemate), insufficient material, 75-move rule; a board built
     // from a FEN has no history, so no repetition rule here (mcts.py:172-177)
     if (L.n == 0 || insufficient_material(p) || hmc >= 150) return 0;
