@@ -244,8 +244,10 @@ __device__ __forceinline__ Pushed push_move(const Pos& p, unsigned code, int hmc
 template <int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, MAXW <= 8 ? 2 : 1)
 tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alpha, int max_moves) {
-    __shared__ u64 sh_key[MAXW];
-    __shared__ int sh_need[MAXW], sh_node[MAXW], sh_new[MAXW];
+    // per-level exchange between the simulations of the tree, double buffered by level parity: the next level posts into the other
+    // buffer, so no barrier is needed at the end of a level (three barriers per level instead of five)
+    __shared__ u64 sh_key2[2][MAXW];
+    __shared__ int sh_need2[2][MAXW], sh_node2[2][MAXW], sh_new2[2][MAXW], sh_dup2[2][MAXW];
     __shared__ MoveList sh_list[MAXW];                   // the expansion's move list of each simulation (warp)
     const int t = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = f.workers, D = f.depth;
@@ -267,6 +269,8 @@ tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alp
     __syncwarp();
 
   for (int level = 0; level < D; level++) {
+    u64* sh_key = sh_key2[level & 1];
+    int *sh_need = sh_need2[level & 1], *sh_node = sh_node2[level & 1], *sh_new = sh_new2[level & 1], *sh_dup = sh_dup2[level & 1];
 
     // ---- phase 1: find the node of the current position, expanding it if this tree has not seen it (mcts.py:128-133)
     u64 key = 0;
@@ -288,6 +292,7 @@ tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alp
             rank += first;
         }
     }
+    if (lane == 0) sh_dup[w] = dup_of;       // a duplicate's node is its original's: sh_node[sh_dup[w]] after the next barrier
     if (need && dup_of < 0) {
         node = f.n_count[t] + rank;
         if (node < f.max_nodes) {
@@ -321,8 +326,6 @@ tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alp
     //      the back-up, after the wave).  So every simulation replays the claims of the lower-numbered simulations standing on
     //      its node (their draws are counter-based hashes it can recompute) and then takes its own action: all in parallel, no
     //      turn-taking; the highest-numbered simulation on a node stores the mask it leaves behind.
-    if (lane == 0) sh_node[w] = alive ? node : -1;
-    __syncthreads();
     unsigned move = NO_MOVE;
     unsigned fresh_after = 0;
     bool store_mask = false;
@@ -342,7 +345,7 @@ tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alp
             unsigned fresh = f.n_unexp[nb];
             store_mask = true;
             for (int a = 0; a < W; a++) {
-                if (a == w || sh_node[a] != node) continue;
+                if (a == w || (sh_dup[a] >= 0 ? sh_node[sh_dup[a]] : sh_node[a]) != node) continue;
                 if (a > w) { store_mask = false; continue; }
                 if (fresh) fresh &= ~(1u << kth_bit(fresh, (int)__umul64hi(draw(a), (u64)__popc(fresh))));
             }
@@ -395,7 +398,6 @@ tree_level_kernel(const Forest f, int wave, int wave_size, double ew, double alp
     } else {
         alive = false;                      // finished game, depth limit, or a slot beyond the (partial) wave
     }
-    __syncthreads();                        // sh_* are reused by the next level
   }
     // the leaf: this array IS the batch cdq_leaf_eval evaluates next
     if (lane == 0) {
