@@ -446,9 +446,12 @@ def self_play_games(neural_net, n_games, max_moves=200, iterations=50, samples_p
         # host bookkeeping and five small synchronous copies).  The search enqueued after the last game ended finds every
         # game inactive and plays nothing.
         dev = forest.game_boards.device
-        pin = [dict(rec=torch.empty((n_games, 9), dtype=torch.int64).pin_memory(), status=torch.empty(n_games, dtype=torch.int32).pin_memory(),
-                    best=torch.empty(n_games, dtype=torch.int32).pin_memory(), score=torch.empty(n_games, dtype=torch.float64).pin_memory(),
-                    flags=torch.empty(n_games, dtype=torch.int32).pin_memory(), done=torch.cuda.Event()) for _ in range(2)]
+        pin = getattr(forest, "_selfplay_pin", None)       # pinned landing buffers, two plies deep, kept with the (cached) forest
+        if pin is None:
+            pin = forest._selfplay_pin = [
+                dict(rec=torch.empty((n_games, 9), dtype=torch.int64).pin_memory(), status=torch.empty(n_games, dtype=torch.int32).pin_memory(),
+                     best=torch.empty(n_games, dtype=torch.int32).pin_memory(), score=torch.empty(n_games, dtype=torch.float64).pin_memory(),
+                     flags=torch.empty(n_games, dtype=torch.int32).pin_memory(), done=torch.cuda.Event()) for _ in range(2)]
         active_d = torch.from_numpy(active.astype(np.int32)).to(dev)
         in_flight = None                                   # the ply whose result is on its way to the host
         for ply in range(max_moves + 1 if active.any() else 0):
