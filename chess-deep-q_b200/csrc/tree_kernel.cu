@@ -73,8 +73,8 @@ __device__ __forceinline__ PlainMove decode_move(unsigned code) {
 __device__ __forceinline__ bool has_legal_ep(const Pos& p) {
     if (((p.meta >> CDQ_META_EP_SHIFT) & CDQ_META_EP_MASK) <= 1) return false;
     MoveList L;
-    list_moves(white_view(p), L);
-    return L.ep_legal;
+    list_classes(white_view(p), L);          // the target sets only: the enumeration (first[], n) is not needed here
+    return L.t[MC_EP] != 0;
 }
 
 // Board._transposition_key() as a 64-bit hash: the eight bitboards, turn, clean castling rights, ep square if capturable
