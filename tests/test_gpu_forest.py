@@ -126,6 +126,17 @@ def test_self_play_on_the_device_is_legal_reproducible_and_trains(cdq, oracle):
         assert np.array_equal(np.array(g["scores"]), sc)
     alone = cdq.self_play_games(net, 1, seeds=[9], **kw)[0]
     assert alone["positions"].tobytes() == games[2]["positions"].tobytes()
+    # the pipelined loop (which games go on is decided on the device, a ply is booked while the next search runs) and the
+    # synchronous one (taken when a callback or an agent needs every ply's result first) play the same games
+    seen = []
+    sync = cdq.self_play_games(net, 5, seeds=[7, 8, 9, 10, 11], on_ply=lambda ply, active: seen.append(int(active.sum())), **kw)
+    assert len(seen) >= 4 and seen[0] <= 5
+    for a, b in zip(games, sync):
+        assert a["positions"].tobytes() == b["positions"].tobytes() and a["moves"] == b["moves"]
+        assert a["scores"] == b["scores"] and a["rewards"] == b["rewards"] and a["result_flags"] == b["result_flags"]
+    # games that end at different plies, up to the move limit: a short limit, then a position one move from mate
+    short = cdq.self_play_games(net, 3, seeds=[1, 2, 3], max_moves=1, iterations=16, samples_per_level=[8, 5, 3], num_workers=4)
+    assert [len(g["moves"]) for g in short] == [1, 1, 1]
     # without a network: the heuristic leaf (mcts.py:226-229)
     h = cdq.self_play_games(None, 2, seeds=[1, 2], **kw)
     assert all(len(g["moves"]) > 4 for g in h)
